@@ -1,0 +1,229 @@
+/*
+ * vaegan_b200.h -- C ABI of libvaegan_sm100.so: hand-written sm_100a kernels for the VAE-GAN
+ * training step of Don-Yin/VAE-GAN (reference: /root/reference/README.md, cited per entry).
+ *
+ * The reference has no FFI of its own: its "operator API" is the set of torch calls its
+ * nn.Modules make (nn.Conv2d, nn.BatchNorm2d, ...).  Each entry point below replaces one of
+ * those call sites (forward and the autograd backward torch would run for it); the
+ * reference-side binding is a torch.autograd.Function that passes raw device pointers through
+ * ctypes (see INTEGRATION.md and vae_gan_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - activations are NHWC (channels innermost), dtype VG_F32 or VG_BF16;
+ *     parameters, statistics and gradients of parameters are fp32 in torch's own layouts;
+ *   - the caller owns every buffer (incl. workspaces); the library never allocates device
+ *     memory and keeps no pointer after a call returns;
+ *   - all work is enqueued on `stream` (a cudaStream_t); no host synchronisation, CUDA-graph
+ *     capturable;
+ *   - return value: VG_OK or a negative VgStatus; vg_last_error() gives a thread-local
+ *     message.  There is NO CPU fallback and no cuDNN/cuBLAS fallback: unsupported
+ *     configurations are VG_EUNSUPPORTED.
+ */
+#ifndef VAEGAN_B200_H_
+#define VAEGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vg_stream_t; /* cudaStream_t */
+
+typedef enum {
+  VG_OK = 0,
+  VG_EINVAL = -1,       /* bad argument (null pointer, misaligned, inconsistent shape) */
+  VG_ECUDA = -2,        /* CUDA runtime / launch failure */
+  VG_EARCH = -3,        /* device is not sm_100 */
+  VG_EUNSUPPORTED = -4  /* valid but not implemented by these kernels */
+} VgStatus;
+
+typedef enum { VG_F32 = 0, VG_BF16 = 1 } VgDtype;
+
+/* ---- library ------------------------------------------------------------------------- */
+int vg_version(void);
+int vg_init(int device);                 /* checks compute capability 10.x, sets smem attrs */
+const char* vg_last_error(void);
+unsigned long long vg_launch_count(void);  /* kernels launched by this library so far */
+/* force every convolution through the SIMT kernels (debug/bisect); returns previous value */
+int vg_set_force_simt(int on);
+
+/* ---- convolutions: nn.Conv2d (README.md:148,151,163,165,170,379,383,387,441,556-571) and
+ *      nn.ConvTranspose2d (README.md:156,158) -------------------------------------------- */
+typedef struct {
+  int n, h_in, w_in, c_in;      /* input activation, NHWC */
+  int h_out, w_out, c_out;      /* output activation */
+  int kh, kw, stride, pad;      /* square stride/pad as the reference uses */
+  int transposed;               /* 0: Conv2d (weight OIHW), 1: ConvTranspose2d (weight IOHW) */
+  int act_dtype;                /* VgDtype of x, dy, dx and of the weight packs */
+  int out_dtype;                /* VgDtype of y (VG_F32 allowed with bf16 inputs) */
+} VgConvDesc;
+
+/* elements in one weight pack = kh*kw*c_in*c_out */
+/* Re-layout (+ optional 1/sigma scaling for spectral norm, README.md:378) of a torch-layout
+ * fp32 weight into the two GEMM packs the kernels consume, in act_dtype:
+ *   pack_kn  [tap][c_out][c_in]   (reduction over c_in contiguous)
+ *   pack_nk  [tap][c_in][c_out]   (reduction over c_out contiguous)
+ * sigma: device scalar or NULL. */
+int vg_conv_pack_weights(const VgConvDesc* d, const float* w, const float* sigma,
+                         void* pack_kn, void* pack_nk, vg_stream_t stream);
+
+/* y = conv(x) [+ bias] [* colscale[n][c_out]]  (colscale = Dropout2d keep/(1-p), README.md:413).
+ * stats (nullable): double[2*c_out], accumulates per-channel sum(y) and sum(y^2) of the
+ * values written, for the BatchNorm that follows (README.md:192).  Must be zeroed by caller. */
+int vg_conv_forward(const VgConvDesc* d, const void* x, const void* pack_kn, const void* pack_nk,
+                    const float* bias, const float* colscale, void* y, double* stats,
+                    vg_stream_t stream);
+/* dx = conv^T(dy): gradient w.r.t. the input. */
+int vg_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pack_kn, const void* pack_nk,
+                  void* dx, vg_stream_t stream);
+/* dw += x (*) dy in torch's weight layout, fp32 (caller zeroes dw for a fresh gradient);
+ * dbias (nullable) += per-channel sum of dy. */
+int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias,
+                  vg_stream_t stream);
+
+/* ---- BatchNorm2d (+LeakyReLU +Dropout) fused family: README.md:143,152,159,166,169,172,
+ *      144/180/190 (nn.Dropout), 376,382,388,394,442 --------------------------------------- */
+typedef struct {
+  long long rows;               /* N*H*W of this rank's tensor */
+  int c;                        /* channels */
+  int hw;                       /* H*W (row / hw = local sample index) */
+  int dtype;                    /* VgDtype of x, y, dy, dx */
+  float slope;                  /* LeakyReLU negative slope; 1.0f = no activation */
+  float drop_p;                 /* elementwise dropout probability; 0 = none */
+  unsigned long long seed;      /* Philox key */
+  unsigned long long offset;    /* Philox stream id (one per dropout site and step) */
+  long long sample_offset;      /* global index of local sample 0 (partition invariance) */
+  int training;                 /* 1: batch statistics; 0: running statistics (eval) */
+} VgBnDesc;
+
+/* sums[0..c) += sum_x, sums[c..2c) += sum_x^2 over rows (double, caller zeroes). */
+int vg_bn_stats(const void* x, const VgBnDesc* d, double* sums, vg_stream_t stream);
+/* mean_rstd[0..c) = mean, [c..2c) = 1/sqrt(var_biased+eps); running stats updated with
+ * momentum and the UNBIASED variance when running_mean != NULL (torch semantics). */
+int vg_bn_finalize(const double* sums, double count, int c, float eps, float momentum,
+                   float* running_mean, float* running_var, float* mean_rstd, vg_stream_t stream);
+/* eval mode: mean_rstd from running statistics. */
+int vg_bn_eval_stats(const float* running_mean, const float* running_var, int c, float eps,
+                     float* mean_rstd, vg_stream_t stream);
+/* y = dropout(leaky_relu(gamma * (x - mean) * rstd + beta)) */
+int vg_bn_act_forward(const void* x, const float* mean_rstd, const float* gamma, const float* beta,
+                      const VgBnDesc* d, void* y, vg_stream_t stream);
+/* g = dy * dropout' * lrelu'; sums[0..c) += sum g, sums[c..2c) += sum g*xhat (double). */
+int vg_bn_act_backward_reduce(const void* dy, const void* x, const float* mean_rstd,
+                              const float* gamma, const float* beta, const VgBnDesc* d,
+                              double* sums, vg_stream_t stream);
+/* dx = out_colscale[n][c] * gamma*rstd*(g - sum_g/count - xhat*sum_gx/count) + addend
+ * (training=0: dx = gamma*rstd*g).  out_colscale, addend nullable. `count` is the GLOBAL
+ * element count per channel (all ranks). */
+int vg_bn_act_backward_apply(const void* dy, const void* x, const float* mean_rstd,
+                             const float* gamma, const float* beta, const double* sums,
+                             double count, const VgBnDesc* d, const float* out_colscale,
+                             const void* addend, void* dx, vg_stream_t stream);
+/* dgamma += sum g*xhat, dbeta += sum g  (fp32 params grads from the double sums) */
+int vg_bn_param_grads(const double* sums, int c, float* dgamma, float* dbeta, vg_stream_t stream);
+
+/* out = leaky_relu( bnA(a) + bnB(b) ), either BN optional (mean_rstd_* NULL = identity):
+ * the `out += shortcut(x)` of README.md:183,195,405,417.  stats (nullable, double[2c]) +=
+ * per-channel sum / sum of squares of `out` for the next block's bn1. */
+int vg_bn_add_forward(const void* a, const float* mean_rstd_a, const float* gamma_a,
+                      const float* beta_a, const void* b, const float* mean_rstd_b,
+                      const float* gamma_b, const float* beta_b, const VgBnDesc* d, void* out,
+                      double* stats, vg_stream_t stream);
+/* dx = dy * (y_ref > 0 ? 1 : slope) */
+int vg_lrelu_backward(const void* dy, const void* y_ref, long long n, int dtype, float slope,
+                      void* dx, vg_stream_t stream);
+/* out = a + b (elementwise, same dtype) -- gradient accumulation at residual forks */
+int vg_add(const void* a, const void* b, long long n, int dtype, void* out, vg_stream_t stream);
+
+/* ---- Philox4x32-10 randomness (replaces torch's bernoulli_/randn_like: README.md:144,381,581) */
+/* keep-mask bytes for the elementwise dropout that vg_bn_act_forward applies */
+int vg_dropout_mask(const VgBnDesc* d, uint8_t* mask, vg_stream_t stream);
+/* Dropout2d scale per (n, c): 0 or 1/(1-p); index = (sample_offset + n)*c + ch */
+int vg_dropout2d_scale(float* scale, int n, int c, float p, unsigned long long seed,
+                       unsigned long long offset, long long sample_offset, vg_stream_t stream);
+/* standard normal noise, element i uses Philox index start+i */
+int vg_philox_normal(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                     long long start, vg_stream_t stream);
+
+/* ---- avg_pool2d(k) + flatten in NCHW order (README.md:471-473) -------------------------- */
+int vg_avgpool_flatten_forward(const void* x, int n, int h, int w, int c, int k, int dtype,
+                               void* out, vg_stream_t stream);
+int vg_avgpool_flatten_backward(const void* dout, int n, int h, int w, int c, int k, int dtype,
+                                void* dx, vg_stream_t stream);
+
+/* ---- nn.Linear (+LeakyReLU 0.2) README.md:458-461,474-483 ------------------------------- */
+/* y[m][n] = lrelu(x[m][k] . w[n][k]^T + bias[n]); x,y,w in `dtype`, bias fp32; slope 1 = none */
+int vg_linear_forward(const void* x, const void* w, const float* bias, int m, int n, int k,
+                      int dtype, float slope, void* y, vg_stream_t stream);
+int vg_linear_dgrad(const void* dy, const void* w, int m, int n, int k, int dtype, void* dx,
+                    vg_stream_t stream);
+/* dw[n][k] += dy^T x (fp32), dbias[n] += column sums of dy */
+int vg_linear_wgrad(const void* x, const void* dy, int m, int n, int k, int dtype, float* dw,
+                    float* dbias, vg_stream_t stream);
+
+/* ---- spectral norm (legacy torch hook, 1 power iteration; README.md:378,383,387) -------- */
+/* w_orig [rows][cols] fp32.  training=1: v <- normalize(W^T u), u <- normalize(W v) in place.
+ * sigma (device scalar) = u^T W v.  workspace: float[rows + cols + 4]. */
+int vg_spectral_norm_sigma(const float* w_orig, int rows, int cols, float* u, float* v,
+                           int training, float eps, float* sigma, float* workspace,
+                           vg_stream_t stream);
+/* dw_orig += (dw_hat - <dw_hat, w_orig/sigma> u v^T) / sigma ; workspace float[1] */
+int vg_spectral_norm_backward(const float* dw_hat, const float* w_orig, const float* u,
+                              const float* v, const float* sigma, int rows, int cols,
+                              float* dw_orig, float* workspace, vg_stream_t stream);
+
+/* ---- reparameterisation (README.md:575-582) --------------------------------------------- */
+/* lv = clamp(lv_raw, -50, 50); z = mu + exp(0.5 lv) * eps (training) or mu (eval). z in z_dtype */
+int vg_reparam_forward(const float* mu, const float* lv_raw, const float* eps, long long n,
+                       int training, int z_dtype, void* z, float* lv_clamped, vg_stream_t stream);
+/* d_mu = dz ; d_lv_raw = dz * 0.5*exp(0.5 lv)*eps inside the clamp, 0 outside */
+int vg_reparam_backward(const void* dz, const float* lv_raw, const float* eps, long long n,
+                        int training, int z_dtype, float* d_mu, float* d_lv_raw, vg_stream_t stream);
+
+/* ---- fused generator loss + gradients (README.md:816-831) ------------------------------- */
+typedef struct {
+  long long n_pix;        /* elements of xhat / x on this rank */
+  long long n_pix_global; /* mean denominators use the GLOBAL batch (data parallel) */
+  long long n_lat;        /* elements of mu / log_var on this rank */
+  int n_logits;           /* D(xhat) logits on this rank */
+  int n_logits_global;
+  int adv_mode;           /* 0: BCE-with-logits vs target 1 (north_star); 1: -mean(D) (ref) */
+  float w_adv, w_recon, w_kl;
+  int xhat_dtype;         /* VgDtype of xhat and d_xhat */
+} VgLossDesc;
+/* losses (device, double[4], caller zeroes): [0] total, [1] L1+MSE, [2] KL (sum), [3] adv.
+ * Writes d_xhat (recon part only; the adversarial part arrives through D's dgrad),
+ * d_mu, d_lv (KL part), d_logits -- all already multiplied by the loss weights. */
+int vg_generator_loss(const void* xhat, const float* x, const float* mu, const float* lv,
+                      const float* logits, const VgLossDesc* d, void* d_xhat, float* d_mu,
+                      float* d_lv, float* d_logits, double* losses, vg_stream_t stream);
+/* discriminator loss (README.md:792-793 or BCE): losses double[3] = total, real, fake */
+int vg_discriminator_loss(const float* d_real, const float* d_fake, int n, int n_global,
+                          int adv_mode, float* g_real, float* g_fake, double* losses,
+                          vg_stream_t stream);
+
+/* ---- fused optimizers over flat fp32 buffers (README.md:802-806,834,918-919) ------------ */
+typedef struct {
+  int kind;               /* 0 Adam (north_star), 1 RMSprop (reference) */
+  float lr, beta1, beta2, alpha, eps, weight_decay;
+  float bias_corr1, bias_corr2;   /* Adam: 1-beta^t */
+  float clamp;            /* > 0: clamp params to +-clamp after the update (README.md:805) */
+  float grad_scale;       /* multiplies the gradient first (1/world_size after allreduce-sum) */
+} VgOptDesc;
+int vg_optimizer_step(float* p, const float* g, float* m, float* v, long long n,
+                      const VgOptDesc* d, vg_stream_t stream);
+
+/* ---- layout / dtype helpers at the module boundary --------------------------------------- */
+int vg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, vg_stream_t stream);
+/* NCHW fp32 <-> NHWC dtype */
+int vg_nchw_to_nhwc(const float* src, int n, int c, int h, int w, int dst_dtype, void* dst, vg_stream_t stream);
+int vg_nhwc_to_nchw(const void* src, int src_dtype, int n, int c, int h, int w, float* dst, vg_stream_t stream);
+int vg_fill_zero(void* p, size_t bytes, vg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAEGAN_B200_H_ */

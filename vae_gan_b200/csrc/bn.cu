@@ -1,0 +1,871 @@
+// BatchNorm2d-family memory-bound kernels (NHWC): statistics, apply + LeakyReLU + Philox dropout,
+// backward reduce / apply, residual add.  Replaces nn.BatchNorm2d / nn.LeakyReLU / nn.Dropout /
+// `out += shortcut(x)` of the reference (README.md:143-197, 376-419, 442, 466-468).
+//
+// Thread mapping (vector path, C % 8 == 0): a thread owns ONE group of 8 consecutive channels
+// for its whole life (per-channel constants live in registers) and walks rows with a grid
+// stride; consecutive threads touch consecutive 16 B (bf16) / 32 B (f32) chunks, so every warp
+// access is fully coalesced.  Per-channel reductions: registers -> shared -> one fp64
+// atomicAdd per (block, channel).  C == 1 tensors are folded into an [rows/8][8] view.
+// Anything else takes the scalar path.
+#include <algorithm>
+#include "vg_common.cuh"
+
+namespace vg {
+
+constexpr int kBnThreads = 256;
+constexpr int kUnroll = 4;
+
+struct RowMap {
+  int cg;        // channel groups per row (C/8)
+  int tpb;       // threads per block actually used = (256/cg)*cg
+  int rpb;       // rows per block iteration
+};
+
+__host__ __device__ inline RowMap make_rowmap(int c) {
+  RowMap m;
+  m.cg = c / 8;
+  m.rpb = kBnThreads / m.cg;
+  m.tpb = m.rpb * m.cg;
+  return m;
+}
+
+static inline bool vec_ok(int c) { return c % 8 == 0 && c / 8 <= kBnThreads; }
+
+static inline int grid_for(long long rows, int rpb, int iters_target = kUnroll * 2) {
+  long long blocks = cdiv(rows, (long long)rpb * iters_target);
+  long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// 16-bit Philox keep decisions for 8 consecutive elements starting at linear index e0 (e0 % 8 == 0)
+__device__ __forceinline__ void keep8(const Philox& ph, unsigned long long e0, uint32_t thr16, bool keep[8]) {
+  uint4 r = ph.block(e0 >> 3);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    keep[2 * i] = (w[i] & 0xffffu) >= thr16;
+    keep[2 * i + 1] = (w[i] >> 16) >= thr16;
+  }
+}
+__device__ __forceinline__ bool keep1(const Philox& ph, unsigned long long e, uint32_t thr16) {
+  uint4 r = ph.block(e >> 3);
+  uint32_t j = (uint32_t)e & 7u;
+  uint32_t w = (j >> 1) == 0 ? r.x : ((j >> 1) == 1 ? r.y : ((j >> 1) == 2 ? r.z : r.w));
+  uint32_t h = (j & 1u) ? (w >> 16) : (w & 0xffffu);
+  return h >= thr16;
+}
+__host__ __device__ inline uint32_t thr16_of(float p) {
+  double t = (double)p * 65536.0;
+  return t >= 65535.0 ? 65535u : (uint32_t)t;
+}
+
+// block-level per-channel reduction of NV values per thread-channel, then fp64 atomics.
+// acc[v][8]: v-th quantity for the thread's 8 channels.  `fold`: all 8 lanes are channel 0.
+template <int NV>
+__device__ __forceinline__ void block_reduce_to_global(float (&acc)[NV][8], const RowMap& m, int c, bool fold,
+                                                       double* out /* [NV][c] */, float* smem) {
+  const int tid = threadIdx.x;
+  // smem layout [NV*8][kBnThreads]
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) smem[(v * 8 + j) * kBnThreads + tid] = (tid < m.tpb) ? acc[v][j] : 0.f;
+  __syncthreads();
+  if (fold) {
+    // every (thread, lane) belongs to channel 0
+    for (int v = 0; v < NV; ++v) {
+      double s = 0.0;
+      for (int i = tid; i < 8 * kBnThreads; i += kBnThreads) s += (double)smem[v * 8 * kBnThreads + i];
+      s = warp_sum(s);
+      __shared__ double wsum[kBnThreads / 32];
+      if ((tid & 31) == 0) wsum[tid >> 5] = s;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kBnThreads / 32; ++w) t += wsum[w];
+        atomicAdd(&out[v * c], t);
+      }
+      __syncthreads();
+    }
+    return;
+  }
+  // channel ch = g*8 + j is handled by thread index (g*8+j) over NV values
+  for (int idx = tid; idx < NV * c; idx += kBnThreads) {
+    int v = idx / c, ch = idx - v * c;
+    int g = ch >> 3, j = ch & 7;
+    double s = 0.0;
+    for (int r = 0; r < m.rpb; ++r) s += (double)smem[(v * 8 + j) * kBnThreads + r * m.cg + g];
+    atomicAdd(&out[v * c + ch], s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// statistics
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_vec_kernel(const T* __restrict__ x, long long rows, int c,
+                                                                   bool fold, double* __restrict__ sums) {
+  extern __shared__ float smem[];
+  const int cv = fold ? 8 : c;
+  const RowMap m = make_rowmap(cv);
+  const int tid = threadIdx.x;
+  const int g = tid % m.cg, r0 = tid / m.cg;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  if (tid < m.tpb) {
+    const long long stride = (long long)gridDim.x * m.rpb;
+    long long row = (long long)blockIdx.x * m.rpb + r0;
+    for (; row + (kUnroll - 1) * stride < rows; row += kUnroll * stride) {
+      Vec8<T> v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) v[u].load(x + (row + u * stride) * cv + g * 8);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[0][j] += v[u].v[j]; acc[1][j] += v[u].v[j] * v[u].v[j]; }
+    }
+    for (; row < rows; row += stride) {
+      Vec8<T> v;
+      v.load(x + row * cv + g * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[0][j] += v.v[j]; acc[1][j] += v.v[j] * v.v[j]; }
+    }
+  }
+  block_reduce_to_global<2>(acc, m, c, fold, sums, smem);
+}
+
+template <typename T>
+__global__ void bn_stats_scalar_kernel(const T* __restrict__ x, long long total, int c, double* __restrict__ sums) {
+  extern __shared__ double dsm[];  // [2*c]
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) dsm[i] = 0.0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v = to_f32(x[i]);
+    int ch = (int)(i % c);
+    atomicAdd(&dsm[ch], (double)v);
+    atomicAdd(&dsm[c + ch], (double)v * v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) atomicAdd(&sums[i], dsm[i]);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int c, float eps, float momentum,
+                                   float* running_mean, float* running_var, float* __restrict__ mean_rstd) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double mean = sums[ch] / count;
+  double var = sums[c + ch] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mean_rstd[ch] = (float)mean;
+  mean_rstd[c + ch] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean != nullptr) {
+    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[ch] = (float)((1.0 - momentum) * (double)running_mean[ch] + momentum * mean);
+    running_var[ch] = (float)((1.0 - momentum) * (double)running_var[ch] + momentum * unbiased);
+  }
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int c, float eps,
+                                     float* __restrict__ mean_rstd) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  mean_rstd[ch] = rm[ch];
+  mean_rstd[c + ch] = (float)(1.0 / sqrt((double)rv[ch] + (double)eps));
+}
+
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, int c, float* dgamma, float* dbeta) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  if (dbeta) dbeta[ch] += (float)sums[ch];
+  if (dgamma) dgamma[ch] += (float)sums[c + ch];
+}
+
+// ------------------------------------------------------------------------------------------
+// forward apply: y = drop(lrelu(a*x + b)),  a = gamma*rstd, b = beta - mean*a
+// ------------------------------------------------------------------------------------------
+struct BnK {
+  long long rows;
+  int c, hw;
+  float slope, drop_scale;
+  uint32_t thr16;
+  unsigned long long seed, offset;
+  long long sample_offset;
+  int training;
+  bool fold;
+};
+
+static inline BnK make_bnk(const VgBnDesc* d) {
+  BnK k;
+  k.rows = d->rows; k.c = d->c; k.hw = d->hw; k.slope = d->slope;
+  k.drop_scale = d->drop_p > 0.f ? 1.0f / (1.0f - d->drop_p) : 1.0f;
+  k.thr16 = d->drop_p > 0.f ? thr16_of(d->drop_p) : 0u;
+  k.seed = d->seed; k.offset = d->offset; k.sample_offset = d->sample_offset; k.training = d->training;
+  k.fold = false;
+  return k;
+}
+
+template <typename T, bool DROP>
+__global__ void __launch_bounds__(kBnThreads) bn_act_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ mean_rstd,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     BnK k, T* __restrict__ y) {
+  const int cv = k.fold ? 8 : k.c;
+  const RowMap m = make_rowmap(cv);
+  const int tid = threadIdx.x;
+  if (tid >= m.tpb) return;
+  const int g = tid % m.cg, r0 = tid / m.cg;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int ch = k.fold ? 0 : g * 8 + j;
+    float aa = gamma[ch] * mean_rstd[k.c + ch];
+    a[j] = aa;
+    b[j] = beta[ch] - mean_rstd[ch] * aa;
+  }
+  Philox ph(k.seed, k.offset);
+  const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
+  const long long stride = (long long)gridDim.x * m.rpb;
+  long long row = (long long)blockIdx.x * m.rpb + r0;
+  auto body = [&](Vec8<T>& v, long long rw) {
+    bool kp[8];
+    if (DROP) keep8(ph, ebase + (unsigned long long)rw * cv + g * 8, k.thr16, kp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(a[j], v.v[j], b[j]);
+      t = t > 0.f ? t : t * k.slope;
+      if (DROP) t = kp[j] ? t * k.drop_scale : 0.f;
+      v.v[j] = t;
+    }
+  };
+  for (; row + (kUnroll - 1) * stride < k.rows; row += kUnroll * stride) {
+    Vec8<T> v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) v[u].load(x + (row + u * stride) * cv + g * 8);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      body(v[u], row + u * stride);
+      v[u].store(y + (row + u * stride) * cv + g * 8);
+    }
+  }
+  for (; row < k.rows; row += stride) {
+    Vec8<T> v;
+    v.load(x + row * cv + g * 8);
+    body(v, row);
+    v.store(y + row * cv + g * 8);
+  }
+}
+
+template <typename T>
+__global__ void bn_act_fwd_scalar_kernel(const T* __restrict__ x, const float* __restrict__ mean_rstd,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, BnK k,
+                                         T* __restrict__ y) {
+  Philox ph(k.seed, k.offset);
+  const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
+  const long long total = k.rows * k.c;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % k.c);
+    float aa = gamma[ch] * mean_rstd[k.c + ch];
+    float t = fmaf(aa, to_f32(x[i]), beta[ch] - mean_rstd[ch] * aa);
+    t = t > 0.f ? t : t * k.slope;
+    if (k.thr16) t = keep1(ph, ebase + (unsigned long long)i, k.thr16) ? t * k.drop_scale : 0.f;
+    y[i] = from_f32<T>(t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: g = dy * drop' * lrelu'(a*x+b);  reduce: sum g, sum g*xhat;  apply: dx
+// ------------------------------------------------------------------------------------------
+template <typename T, bool DROP, bool APPLY>
+__global__ void __launch_bounds__(kBnThreads) bn_act_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                     const float* __restrict__ mean_rstd,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     BnK k, double* __restrict__ sums_out /* reduce */,
+                                                                     const double* __restrict__ sums_in /* apply */, double count,
+                                                                     const float* __restrict__ out_colscale,
+                                                                     const T* __restrict__ addend, T* __restrict__ dx) {
+  extern __shared__ float smem[];
+  const int cv = k.fold ? 8 : k.c;
+  const RowMap m = make_rowmap(cv);
+  const int tid = threadIdx.x;
+  const int g = tid % m.cg, r0 = tid / m.cg;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  if (tid < m.tpb) {
+    float a[8], b[8], mean[8], rstd[8], k1[8], k2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int ch = k.fold ? 0 : g * 8 + j;
+      mean[j] = mean_rstd[ch];
+      rstd[j] = mean_rstd[k.c + ch];
+      a[j] = gamma[ch] * rstd[j];
+      b[j] = beta[ch] - mean[j] * a[j];
+      if (APPLY) {
+        if (k.training) {
+          k1[j] = (float)(sums_in[ch] / count);
+          k2[j] = (float)(sums_in[k.c + ch] / count);
+        } else {
+          k1[j] = 0.f; k2[j] = 0.f;
+        }
+      }
+    }
+    Philox ph(k.seed, k.offset);
+    const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
+    const long long stride = (long long)gridDim.x * m.rpb;
+    long long row = (long long)blockIdx.x * m.rpb + r0;
+    auto body = [&](Vec8<T>& vdy, const Vec8<T>& vx, long long rw) {
+      bool kp[8];
+      if (DROP) keep8(ph, ebase + (unsigned long long)rw * cv + g * 8, k.thr16, kp);
+      float cs[8];
+      if (APPLY && out_colscale != nullptr) {
+        long long n = rw / k.hw;
+        const float* p = out_colscale + n * k.c + g * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] = p[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float pre = fmaf(a[j], vx.v[j], b[j]);
+        float gg = vdy.v[j] * (pre > 0.f ? 1.f : k.slope);
+        if (DROP) gg = kp[j] ? gg * k.drop_scale : 0.f;
+        float xh = (vx.v[j] - mean[j]) * rstd[j];
+        if (APPLY) {
+          float r = a[j] * (gg - k1[j] - xh * k2[j]);
+          if (out_colscale != nullptr) r *= cs[j];
+          vdy.v[j] = r;
+        } else {
+          acc[0][j] += gg;
+          acc[1][j] += gg * xh;
+        }
+      }
+    };
+    for (; row + (kUnroll / 2 - 1) * stride < k.rows; row += (kUnroll / 2) * stride) {
+      Vec8<T> vd[kUnroll / 2], vx[kUnroll / 2];
+#pragma unroll
+      for (int u = 0; u < kUnroll / 2; ++u) {
+        vd[u].load(dy + (row + u * stride) * cv + g * 8);
+        vx[u].load(x + (row + u * stride) * cv + g * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll / 2; ++u) {
+        body(vd[u], vx[u], row + u * stride);
+        if (APPLY) {
+          if (addend != nullptr) {
+            Vec8<T> ad;
+            ad.load(addend + (row + u * stride) * cv + g * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vd[u].v[j] += ad.v[j];
+          }
+          vd[u].store(dx + (row + u * stride) * cv + g * 8);
+        }
+      }
+    }
+    for (; row < k.rows; row += stride) {
+      Vec8<T> vd, vx;
+      vd.load(dy + row * cv + g * 8);
+      vx.load(x + row * cv + g * 8);
+      body(vd, vx, row);
+      if (APPLY) {
+        if (addend != nullptr) {
+          Vec8<T> ad;
+          ad.load(addend + row * cv + g * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vd.v[j] += ad.v[j];
+        }
+        vd.store(dx + row * cv + g * 8);
+      }
+    }
+  }
+  if (!APPLY) block_reduce_to_global<2>(acc, m, k.c, k.fold, sums_out, smem);
+}
+
+template <typename T, bool APPLY>
+__global__ void bn_act_bwd_scalar_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean_rstd,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, BnK k,
+                                         double* __restrict__ sums_out, const double* __restrict__ sums_in, double count,
+                                         const float* __restrict__ out_colscale, const T* __restrict__ addend,
+                                         T* __restrict__ dx) {
+  extern __shared__ double dsm[];
+  if (!APPLY) {
+    for (int i = threadIdx.x; i < 2 * k.c; i += blockDim.x) dsm[i] = 0.0;
+    __syncthreads();
+  }
+  Philox ph(k.seed, k.offset);
+  const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
+  const long long total = k.rows * k.c;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % k.c);
+    float mean = mean_rstd[ch], rstd = mean_rstd[k.c + ch];
+    float aa = gamma[ch] * rstd;
+    float xv = to_f32(x[i]);
+    float pre = fmaf(aa, xv, beta[ch] - mean * aa);
+    float gg = to_f32(dy[i]) * (pre > 0.f ? 1.f : k.slope);
+    if (k.thr16) gg = keep1(ph, ebase + (unsigned long long)i, k.thr16) ? gg * k.drop_scale : 0.f;
+    float xh = (xv - mean) * rstd;
+    if (APPLY) {
+      float k1 = k.training ? (float)(sums_in[ch] / count) : 0.f;
+      float k2 = k.training ? (float)(sums_in[k.c + ch] / count) : 0.f;
+      float r = aa * (gg - k1 - xh * k2);
+      if (out_colscale != nullptr) r *= out_colscale[(i / k.c / k.hw) * k.c + ch];
+      if (addend != nullptr) r += to_f32(addend[i]);
+      dx[i] = from_f32<T>(r);
+    } else {
+      atomicAdd(&dsm[ch], (double)gg);
+      atomicAdd(&dsm[k.c + ch], (double)gg * xh);
+    }
+  }
+  if (!APPLY) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * k.c; i += blockDim.x) atomicAdd(&sums_out[i], dsm[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// residual add: out = lrelu(bnA(a) + bnB(b)) (+ stats of out)
+// ------------------------------------------------------------------------------------------
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(kBnThreads) bn_add_vec_kernel(const T* __restrict__ A, const float* __restrict__ mrA,
+                                                                 const float* __restrict__ gA, const float* __restrict__ bA,
+                                                                 const T* __restrict__ B, const float* __restrict__ mrB,
+                                                                 const float* __restrict__ gB, const float* __restrict__ bB, BnK k,
+                                                                 T* __restrict__ out, double* __restrict__ stats) {
+  extern __shared__ float smem[];
+  const int cv = k.fold ? 8 : k.c;
+  const RowMap m = make_rowmap(cv);
+  const int tid = threadIdx.x;
+  const int g = tid % m.cg, r0 = tid / m.cg;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  if (tid < m.tpb) {
+    float sa[8], ta[8], sb[8], tb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int ch = k.fold ? 0 : g * 8 + j;
+      if (mrA) { sa[j] = gA[ch] * mrA[k.c + ch]; ta[j] = bA[ch] - mrA[ch] * sa[j]; } else { sa[j] = 1.f; ta[j] = 0.f; }
+      if (mrB) { sb[j] = gB[ch] * mrB[k.c + ch]; tb[j] = bB[ch] - mrB[ch] * sb[j]; } else { sb[j] = 1.f; tb[j] = 0.f; }
+    }
+    const long long stride = (long long)gridDim.x * m.rpb;
+    for (long long row = (long long)blockIdx.x * m.rpb + r0; row < k.rows; row += 2 * stride) {
+      Vec8<T> va[2], vb[2];
+      bool has2 = row + stride < k.rows;
+      va[0].load(A + row * cv + g * 8);
+      vb[0].load(B + row * cv + g * 8);
+      if (has2) {
+        va[1].load(A + (row + stride) * cv + g * 8);
+        vb[1].load(B + (row + stride) * cv + g * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !has2) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = fmaf(sa[j], va[u].v[j], ta[j]) + fmaf(sb[j], vb[u].v[j], tb[j]);
+          t = t > 0.f ? t : t * k.slope;
+          va[u].v[j] = t;
+        }
+        va[u].store(out + (row + u * stride) * cv + g * 8);
+        if (STATS) {
+          // statistics are taken on the values as STORED (bf16-rounded on the bf16 path)
+          Vec8<T> rb;
+          rb = va[u];
+          if (sizeof(T) == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rb.v[j] = to_f32(from_f32<T>(rb.v[j]));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc[0][j] += rb.v[j]; acc[1][j] += rb.v[j] * rb.v[j]; }
+        }
+      }
+    }
+  }
+  if (STATS) block_reduce_to_global<2>(acc, m, k.c, k.fold, stats, smem);
+}
+
+template <typename T>
+__global__ void bn_add_scalar_kernel(const T* __restrict__ A, const float* __restrict__ mrA, const float* __restrict__ gA,
+                                     const float* __restrict__ bA, const T* __restrict__ B, const float* __restrict__ mrB,
+                                     const float* __restrict__ gB, const float* __restrict__ bB, BnK k, T* __restrict__ out,
+                                     double* __restrict__ stats) {
+  extern __shared__ double dsm[];
+  if (stats) {
+    for (int i = threadIdx.x; i < 2 * k.c; i += blockDim.x) dsm[i] = 0.0;
+    __syncthreads();
+  }
+  const long long total = k.rows * k.c;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % k.c);
+    float va = to_f32(A[i]), vb = to_f32(B[i]);
+    if (mrA) { float s = gA[ch] * mrA[k.c + ch]; va = fmaf(s, va, bA[ch] - mrA[ch] * s); }
+    if (mrB) { float s = gB[ch] * mrB[k.c + ch]; vb = fmaf(s, vb, bB[ch] - mrB[ch] * s); }
+    float t = va + vb;
+    t = t > 0.f ? t : t * k.slope;
+    T o = from_f32<T>(t);
+    out[i] = o;
+    if (stats) {
+      float r = to_f32(o);
+      atomicAdd(&dsm[ch], (double)r);
+      atomicAdd(&dsm[k.c + ch], (double)r * r);
+    }
+  }
+  if (stats) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * k.c; i += blockDim.x) atomicAdd(&stats[i], dsm[i]);
+  }
+}
+
+// elementwise helpers -----------------------------------------------------------------------
+template <typename T>
+__global__ void lrelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ yref, long long n, float slope, T* __restrict__ dx) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = from_f32<T>(to_f32(dy[i]) * (to_f32(yref[i]) > 0.f ? 1.f : slope));
+}
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, long long n, T* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = from_f32<T>(to_f32(a[i]) + to_f32(b[i]));
+}
+template <typename T>
+__global__ void add_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, long long nvec, T* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    Vec8<T> va, vb;
+    va.load(a + i * 8);
+    vb.load(b + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) va.v[j] += vb.v[j];
+    va.store(out + i * 8);
+  }
+}
+
+__global__ void dropout_mask_kernel(BnK k, uint8_t* __restrict__ mask) {
+  Philox ph(k.seed, k.offset);
+  const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
+  const long long total = k.rows * k.c;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    mask[i] = k.thr16 ? (keep1(ph, ebase + (unsigned long long)i, k.thr16) ? 1 : 0) : 1;
+}
+
+__global__ void dropout2d_scale_kernel(float* __restrict__ scale, long long total, int c, float p, unsigned long long seed,
+                                       unsigned long long offset, long long sample_offset) {
+  Philox ph(seed, offset);
+  uint32_t thr = drop_threshold(p);
+  float sc = 1.0f / (1.0f - p);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long e = (unsigned long long)sample_offset * c + (unsigned long long)i;
+    scale[i] = (p <= 0.f) ? 1.f : (ph.word(e) >= thr ? sc : 0.f);
+  }
+}
+
+__global__ void philox_normal_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
+                                     long long start) {
+  Philox ph(seed, offset);
+  const long long nblk = (n + 3) / 4;
+  for (long long bidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; bidx < nblk; bidx += (long long)gridDim.x * blockDim.x) {
+    // element e = start + 4*bidx + l uses block (e >> 2) only when start % 4 == 0 (enforced by the host)
+    uint4 r = ph.block((unsigned long long)(start / 4 + bidx));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float u1 = ((float)w[2 * h] + 0.5f) * 2.3283064365386963e-10f;  // (0,1]
+      float u2 = ((float)w[2 * h + 1] + 0.5f) * 2.3283064365386963e-10f;
+      u1 = fminf(fmaxf(u1, 1e-12f), 1.0f);
+      float rad = sqrtf(-2.0f * logf(u1));
+      float s, c;
+      sincospif(2.0f * u2, &s, &c);
+      z[2 * h] = rad * c;
+      z[2 * h + 1] = rad * s;
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      if (4 * bidx + l < n) out[4 * bidx + l] = z[l];
+  }
+}
+
+}  // namespace vg
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace vg;
+
+static int check_desc(const VgBnDesc* d) {
+  VG_CHECK_ARG(d != nullptr, "VgBnDesc is null");
+  VG_CHECK_ARG(d->rows >= 0 && d->c > 0 && d->hw > 0, "bad VgBnDesc dims rows=%lld c=%d hw=%d", d->rows, d->c, d->hw);
+  VG_CHECK_ARG(d->dtype == VG_F32 || d->dtype == VG_BF16, "bad dtype %d", d->dtype);
+  VG_CHECK_ARG(d->drop_p >= 0.f && d->drop_p < 1.f, "bad dropout p %f", d->drop_p);
+  return VG_OK;
+}
+
+// decide the mapping: 0 scalar, 1 vector, 2 folded single channel
+static inline int path_for(const VgBnDesc* d) {
+  if (vec_ok(d->c)) return 1;
+  if (d->c == 1 && d->rows % 8 == 0 && d->rows > 0) return 2;
+  return 0;
+}
+static inline size_t vec_smem() { return (size_t)2 * 8 * kBnThreads * sizeof(float); }
+
+extern "C" int vg_bn_stats(const void* x, const VgBnDesc* d, double* sums, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(x && sums, "null pointer");
+  if (d->rows == 0) return VG_OK;
+  cudaStream_t s = as_stream(stream);
+  int path = path_for(d);
+  if (path) {
+    bool fold = path == 2;
+    long long rows = fold ? d->rows / 8 : d->rows;
+    int cv = fold ? 8 : d->c;
+    RowMap m = make_rowmap(cv);
+    int grid = grid_for(rows, m.rpb);
+    if (d->dtype == VG_BF16)
+      bn_stats_vec_kernel<__nv_bfloat16><<<grid, kBnThreads, vec_smem(), s>>>((const __nv_bfloat16*)x, rows, d->c, fold, sums);
+    else
+      bn_stats_vec_kernel<float><<<grid, kBnThreads, vec_smem(), s>>>((const float*)x, rows, d->c, fold, sums);
+  } else {
+    long long total = d->rows * d->c;
+    int grid = (int)std::min<long long>(cdiv(total, 256 * 8), (long long)num_sms() * 4);
+    size_t sm = (size_t)2 * d->c * sizeof(double);
+    VG_CHECK_ARG(sm <= 48 * 1024, "scalar BN path supports c <= 3072 (c=%d)", d->c);
+    if (d->dtype == VG_BF16)
+      bn_stats_scalar_kernel<__nv_bfloat16><<<grid, 256, sm, s>>>((const __nv_bfloat16*)x, total, d->c, sums);
+    else
+      bn_stats_scalar_kernel<float><<<grid, 256, sm, s>>>((const float*)x, total, d->c, sums);
+  }
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_bn_finalize(const double* sums, double count, int c, float eps, float momentum, float* running_mean,
+                              float* running_var, float* mean_rstd, vg_stream_t stream) {
+  VG_CHECK_ARG(sums && mean_rstd && c > 0 && count > 0, "bad args");
+  VG_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "running_mean/var must both be given or both null");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, count, c, eps, momentum, running_mean, running_var, mean_rstd);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_bn_eval_stats(const float* running_mean, const float* running_var, int c, float eps, float* mean_rstd,
+                                vg_stream_t stream) {
+  VG_CHECK_ARG(running_mean && running_var && mean_rstd && c > 0, "bad args");
+  bn_eval_stats_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(running_mean, running_var, c, eps, mean_rstd);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_bn_param_grads(const double* sums, int c, float* dgamma, float* dbeta, vg_stream_t stream) {
+  VG_CHECK_ARG(sums && c > 0, "bad args");
+  bn_param_grads_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, c, dgamma, dbeta);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+template <typename T>
+static int bn_act_forward_t(const T* x, const float* mr, const float* gamma, const float* beta, const VgBnDesc* d, T* y,
+                            cudaStream_t s) {
+  BnK k = make_bnk(d);
+  int path = path_for(d);
+  if (path) {
+    k.fold = path == 2;
+    long long rows = k.fold ? d->rows / 8 : d->rows;
+    k.rows = rows;
+    RowMap m = make_rowmap(k.fold ? 8 : d->c);
+    int grid = grid_for(rows, m.rpb);
+    if (k.thr16)
+      bn_act_fwd_vec_kernel<T, true><<<grid, kBnThreads, 0, s>>>(x, mr, gamma, beta, k, y);
+    else
+      bn_act_fwd_vec_kernel<T, false><<<grid, kBnThreads, 0, s>>>(x, mr, gamma, beta, k, y);
+  } else {
+    long long total = d->rows * d->c;
+    int grid = (int)std::min<long long>(cdiv(total, 256 * 4), (long long)num_sms() * 8);
+    bn_act_fwd_scalar_kernel<T><<<grid, 256, 0, s>>>(x, mr, gamma, beta, k, y);
+  }
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_bn_act_forward(const void* x, const float* mean_rstd, const float* gamma, const float* beta,
+                                 const VgBnDesc* d, void* y, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(x && mean_rstd && gamma && beta && y, "null pointer");
+  if (d->rows == 0) return VG_OK;
+  if (d->dtype == VG_BF16)
+    return bn_act_forward_t<__nv_bfloat16>((const __nv_bfloat16*)x, mean_rstd, gamma, beta, d, (__nv_bfloat16*)y, as_stream(stream));
+  return bn_act_forward_t<float>((const float*)x, mean_rstd, gamma, beta, d, (float*)y, as_stream(stream));
+}
+
+template <typename T, bool APPLY>
+static int bn_act_backward_t(const T* dy, const T* x, const float* mr, const float* gamma, const float* beta, const VgBnDesc* d,
+                             double* sums_out, const double* sums_in, double count, const float* ocs, const T* addend, T* dx,
+                             cudaStream_t s) {
+  BnK k = make_bnk(d);
+  int path = path_for(d);
+  if (path == 2 && ocs != nullptr) path = 0;  // per-sample colscale needs real row indices
+  if (path) {
+    k.fold = path == 2;
+    long long rows = k.fold ? d->rows / 8 : d->rows;
+    k.rows = rows;
+    RowMap m = make_rowmap(k.fold ? 8 : d->c);
+    int grid = grid_for(rows, m.rpb, kUnroll);
+    size_t sm = APPLY ? 0 : vec_smem();
+    if (k.thr16)
+      bn_act_bwd_vec_kernel<T, true, APPLY><<<grid, kBnThreads, sm, s>>>(dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
+    else
+      bn_act_bwd_vec_kernel<T, false, APPLY><<<grid, kBnThreads, sm, s>>>(dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
+  } else {
+    long long total = d->rows * d->c;
+    int grid = (int)std::min<long long>(cdiv(total, 256 * 4), (long long)num_sms() * 8);
+    size_t sm = APPLY ? 0 : (size_t)2 * d->c * sizeof(double);
+    VG_CHECK_ARG(sm <= 48 * 1024, "scalar BN path supports c <= 3072 (c=%d)", d->c);
+    bn_act_bwd_scalar_kernel<T, APPLY><<<grid, 256, sm, s>>>(dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
+  }
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_bn_act_backward_reduce(const void* dy, const void* x, const float* mean_rstd, const float* gamma,
+                                         const float* beta, const VgBnDesc* d, double* sums, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(dy && x && mean_rstd && gamma && beta && sums, "null pointer");
+  if (d->rows == 0) return VG_OK;
+  if (d->dtype == VG_BF16)
+    return bn_act_backward_t<__nv_bfloat16, false>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean_rstd, gamma, beta, d, sums,
+                                                   nullptr, 1.0, nullptr, nullptr, nullptr, as_stream(stream));
+  return bn_act_backward_t<float, false>((const float*)dy, (const float*)x, mean_rstd, gamma, beta, d, sums, nullptr, 1.0, nullptr,
+                                         nullptr, nullptr, as_stream(stream));
+}
+
+extern "C" int vg_bn_act_backward_apply(const void* dy, const void* x, const float* mean_rstd, const float* gamma,
+                                        const float* beta, const double* sums, double count, const VgBnDesc* d,
+                                        const float* out_colscale, const void* addend, void* dx, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(dy && x && mean_rstd && gamma && beta && dx, "null pointer");
+  VG_CHECK_ARG(!d->training || (sums != nullptr && count > 0), "training-mode BN backward needs sums and count");
+  if (d->rows == 0) return VG_OK;
+  if (d->dtype == VG_BF16)
+    return bn_act_backward_t<__nv_bfloat16, true>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean_rstd, gamma, beta, d, nullptr,
+                                                  sums, count, out_colscale, (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx,
+                                                  as_stream(stream));
+  return bn_act_backward_t<float, true>((const float*)dy, (const float*)x, mean_rstd, gamma, beta, d, nullptr, sums, count,
+                                        out_colscale, (const float*)addend, (float*)dx, as_stream(stream));
+}
+
+template <typename T>
+static int bn_add_t(const T* a, const float* mra, const float* ga, const float* ba, const T* b, const float* mrb, const float* gb,
+                    const float* bb, const VgBnDesc* d, T* out, double* stats, cudaStream_t s) {
+  BnK k = make_bnk(d);
+  int path = path_for(d);
+  if (path) {
+    k.fold = path == 2;
+    long long rows = k.fold ? d->rows / 8 : d->rows;
+    k.rows = rows;
+    RowMap m = make_rowmap(k.fold ? 8 : d->c);
+    int grid = grid_for(rows, m.rpb, kUnroll);
+    if (stats)
+      bn_add_vec_kernel<T, true><<<grid, kBnThreads, vec_smem(), s>>>(a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
+    else
+      bn_add_vec_kernel<T, false><<<grid, kBnThreads, 0, s>>>(a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
+  } else {
+    long long total = d->rows * d->c;
+    int grid = (int)std::min<long long>(cdiv(total, 256 * 4), (long long)num_sms() * 8);
+    size_t sm = stats ? (size_t)2 * d->c * sizeof(double) : 0;
+    VG_CHECK_ARG(sm <= 48 * 1024, "scalar BN path supports c <= 3072 (c=%d)", d->c);
+    bn_add_scalar_kernel<T><<<grid, 256, sm, s>>>(a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
+  }
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_bn_add_forward(const void* a, const float* mean_rstd_a, const float* gamma_a, const float* beta_a,
+                                 const void* b, const float* mean_rstd_b, const float* gamma_b, const float* beta_b,
+                                 const VgBnDesc* d, void* out, double* stats, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(a && b && out, "null pointer");
+  VG_CHECK_ARG(!mean_rstd_a || (gamma_a && beta_a), "bnA needs gamma/beta");
+  VG_CHECK_ARG(!mean_rstd_b || (gamma_b && beta_b), "bnB needs gamma/beta");
+  if (d->rows == 0) return VG_OK;
+  if (d->dtype == VG_BF16)
+    return bn_add_t<__nv_bfloat16>((const __nv_bfloat16*)a, mean_rstd_a, gamma_a, beta_a, (const __nv_bfloat16*)b, mean_rstd_b, gamma_b,
+                                   beta_b, d, (__nv_bfloat16*)out, stats, as_stream(stream));
+  return bn_add_t<float>((const float*)a, mean_rstd_a, gamma_a, beta_a, (const float*)b, mean_rstd_b, gamma_b, beta_b, d, (float*)out,
+                         stats, as_stream(stream));
+}
+
+extern "C" int vg_lrelu_backward(const void* dy, const void* y_ref, long long n, int dtype, float slope, void* dx,
+                                 vg_stream_t stream) {
+  VG_CHECK_ARG(dy && y_ref && dx && n >= 0, "bad args");
+  if (n == 0) return VG_OK;
+  int grid = (int)std::min<long long>(cdiv(n, 256 * 4), (long long)num_sms() * 8);
+  if (dtype == VG_BF16)
+    lrelu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y_ref, n, slope,
+                                                                         (__nv_bfloat16*)dx);
+  else
+    lrelu_bwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy, (const float*)y_ref, n, slope, (float*)dx);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_add(const void* a, const void* b, long long n, int dtype, void* out, vg_stream_t stream) {
+  VG_CHECK_ARG(a && b && out && n >= 0, "bad args");
+  if (n == 0) return VG_OK;
+  cudaStream_t s = as_stream(stream);
+  bool aligned = ((uintptr_t)a % 32 == 0) && ((uintptr_t)b % 32 == 0) && ((uintptr_t)out % 32 == 0) && (n % 8 == 0);
+  if (aligned) {
+    long long nv = n / 8;
+    int grid = (int)std::min<long long>(cdiv(nv, 256 * 2), (long long)num_sms() * 8);
+    if (dtype == VG_BF16)
+      add_vec_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nv, (__nv_bfloat16*)out);
+    else
+      add_vec_kernel<float><<<grid, 256, 0, s>>>((const float*)a, (const float*)b, nv, (float*)out);
+  } else {
+    int grid = (int)std::min<long long>(cdiv(n, 256 * 4), (long long)num_sms() * 8);
+    if (dtype == VG_BF16)
+      add_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, (__nv_bfloat16*)out);
+    else
+      add_kernel<float><<<grid, 256, 0, s>>>((const float*)a, (const float*)b, n, (float*)out);
+  }
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_dropout_mask(const VgBnDesc* d, uint8_t* mask, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(mask, "null pointer");
+  if (d->rows == 0) return VG_OK;
+  BnK k = make_bnk(d);
+  long long total = d->rows * d->c;
+  int grid = (int)std::min<long long>(cdiv(total, 256 * 4), (long long)num_sms() * 8);
+  dropout_mask_kernel<<<grid, 256, 0, as_stream(stream)>>>(k, mask);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_dropout2d_scale(float* scale, int n, int c, float p, unsigned long long seed, unsigned long long offset,
+                                  long long sample_offset, vg_stream_t stream) {
+  VG_CHECK_ARG(scale && n >= 0 && c > 0 && p >= 0.f && p < 1.f, "bad args");
+  long long total = (long long)n * c;
+  if (total == 0) return VG_OK;
+  int grid = (int)std::min<long long>(cdiv(total, 256), (long long)num_sms() * 4);
+  dropout2d_scale_kernel<<<grid, 256, 0, as_stream(stream)>>>(scale, total, c, p, seed, offset, sample_offset);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_philox_normal(float* out, long long n, unsigned long long seed, unsigned long long offset, long long start,
+                                vg_stream_t stream) {
+  VG_CHECK_ARG(out && n >= 0 && start >= 0 && start % 4 == 0, "bad args (start must be a multiple of 4)");
+  if (n == 0) return VG_OK;
+  long long nblk = (n + 3) / 4;
+  int grid = (int)std::min<long long>(cdiv(nblk, 256), (long long)num_sms() * 8);
+  philox_normal_kernel<<<grid, 256, 0, as_stream(stream)>>>(out, n, seed, offset, start);
+  VG_LAUNCHED();
+  return VG_OK;
+}

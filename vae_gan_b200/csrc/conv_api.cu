@@ -1,0 +1,95 @@
+// C-ABI entry points for the convolutions: validation + dispatch between the tcgen05 implicit
+// GEMM kernels (conv_tc.cu) and the CUDA-core kernels (conv_simt.cu).  Both are this library's
+// own sm_100a kernels; there is no library (cuDNN/cuBLAS) or CPU fallback.
+#include "vg_common.cuh"
+
+namespace vg {
+int simt_conv_forward(const VgConvDesc*, const void*, const void*, const float*, const float*, void*, cudaStream_t);
+int simt_conv_dgrad(const VgConvDesc*, const void*, const void*, void*, cudaStream_t);
+int simt_conv_wgrad(const VgConvDesc*, const void*, const void*, float*, cudaStream_t);
+int simt_colsum(const void*, long long, int, int, float*, cudaStream_t);
+int simt_pack_weights(const VgConvDesc*, const float*, const float*, void*, void*, cudaStream_t);
+bool tc_conv_supported(const VgConvDesc*, bool dgrad);
+bool tc_wgrad_supported(const VgConvDesc*);
+int tc_conv_run(const VgConvDesc*, bool dgrad, const void* in, const void* wpack, const float* bias, const float* colscale, void* out,
+                int out_dtype, cudaStream_t);
+int tc_wgrad_run(const VgConvDesc*, const void* x, const void* dy, float* dw, cudaStream_t);
+}  // namespace vg
+
+using namespace vg;
+
+static int check_conv(const VgConvDesc* d) {
+  VG_CHECK_ARG(d != nullptr, "VgConvDesc is null");
+  VG_CHECK_ARG(d->n >= 0 && d->h_in > 0 && d->w_in > 0 && d->c_in > 0 && d->c_out > 0, "bad conv dims");
+  VG_CHECK_ARG(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->pad >= 0, "bad conv kernel geometry");
+  VG_CHECK_ARG(d->act_dtype == VG_F32 || d->act_dtype == VG_BF16, "bad act_dtype");
+  VG_CHECK_ARG(d->out_dtype == VG_F32 || d->out_dtype == VG_BF16, "bad out_dtype");
+  int eh, ew;
+  if (d->transposed) {
+    eh = (d->h_in - 1) * d->stride - 2 * d->pad + d->kh;
+    ew = (d->w_in - 1) * d->stride - 2 * d->pad + d->kw;
+  } else {
+    eh = (d->h_in + 2 * d->pad - d->kh) / d->stride + 1;
+    ew = (d->w_in + 2 * d->pad - d->kw) / d->stride + 1;
+  }
+  VG_CHECK_ARG(eh == d->h_out && ew == d->w_out, "output dims %dx%d inconsistent with geometry (expected %dx%d)", d->h_out, d->w_out, eh, ew);
+  return VG_OK;
+}
+
+extern "C" int vg_conv_pack_weights(const VgConvDesc* d, const float* w, const float* sigma, void* pack_kn, void* pack_nk,
+                                    vg_stream_t stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(w && (pack_kn || pack_nk), "null pointer");
+  return simt_pack_weights(d, w, sigma, pack_kn, pack_nk, as_stream(stream));
+}
+
+extern "C" int vg_conv_forward(const VgConvDesc* d, const void* x, const void* pack_kn, const void* pack_nk, const float* bias,
+                               const float* colscale, void* y, double* stats, vg_stream_t stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(x && y && pack_kn && pack_nk, "null pointer");
+  cudaStream_t s = as_stream(stream);
+  if (d->n == 0) return VG_OK;
+  if (tc_conv_supported(d, false))
+    rc = tc_conv_run(d, false, x, pack_kn, bias, colscale, y, d->out_dtype, s);
+  else
+    rc = simt_conv_forward(d, x, pack_nk, bias, colscale, y, s);
+  if (rc) return rc;
+  if (stats != nullptr) {
+    VgBnDesc b{};
+    b.rows = (long long)d->n * d->h_out * d->w_out;
+    b.c = d->c_out;
+    b.hw = d->h_out * d->w_out;
+    b.dtype = d->out_dtype;
+    b.slope = 1.f;
+    rc = vg_bn_stats(y, &b, stats, stream);
+  }
+  return rc;
+}
+
+extern "C" int vg_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pack_kn, const void* pack_nk, void* dx,
+                             vg_stream_t stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(dy && dx && pack_kn && pack_nk, "null pointer");
+  if (d->n == 0) return VG_OK;
+  cudaStream_t s = as_stream(stream);
+  if (tc_conv_supported(d, true)) return tc_conv_run(d, true, dy, pack_nk, nullptr, nullptr, dx, d->act_dtype, s);
+  return simt_conv_dgrad(d, dy, pack_kn, dx, s);
+}
+
+extern "C" int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias, vg_stream_t stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(x && dy && dw, "null pointer");
+  if (d->n == 0) return VG_OK;
+  cudaStream_t s = as_stream(stream);
+  if (tc_wgrad_supported(d))
+    rc = tc_wgrad_run(d, x, dy, dw, s);
+  else
+    rc = simt_conv_wgrad(d, x, dy, dw, s);
+  if (rc) return rc;
+  if (dbias != nullptr) rc = simt_colsum(dy, (long long)d->n * d->h_out * d->w_out, d->c_out, d->act_dtype, dbias, s);
+  return rc;
+}

@@ -1,0 +1,313 @@
+// CUDA-core convolution kernels (NHWC): the fp32 parity path, and the product path for the
+// degenerate layers (c_in == 1 or c_out == 1, README.md:230,289,441) that are memory-bound and
+// have no GEMM shape worth a tensor-core tile.  Also the weight re-layout ("pack") kernel.
+//
+// Two index patterns cover Conv2d and ConvTranspose2d, forward and dgrad:
+//   gather : out[o]  = sum_k in[o*s - p + k] . W_k        (Conv2d fwd, ConvTranspose2d dgrad)
+//   scatter: out[j]  = sum_{k : (j+p-k) % s == 0} in[(j+p-k)/s] . W_k
+//                                                          (ConvTranspose2d fwd, Conv2d dgrad)
+// W_k is [tap][c_red][c_out'] with c_out' contiguous, so a thread owning 8 output channels
+// reads 8 contiguous weights per (tap, c_red).
+#include <algorithm>
+#include "vg_common.cuh"
+
+namespace vg {
+
+struct ConvGeom {
+  int n, hi, wi, cr;   // input of THIS kernel (reduction channels cr)
+  int ho, wo, co;      // output of this kernel
+  int kh, kw, stride, pad;
+};
+
+// ---- weight pack ---------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int c_out, int c_in, int taps,
+                                    int transposed, T* __restrict__ pack_kn, T* __restrict__ pack_nk) {
+  const long long total = (long long)taps * c_out * c_in;
+  const float inv = sigma ? 1.0f / *sigma : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // i enumerates the torch layout so the read is coalesced
+    int tap = (int)(i % taps);
+    long long r = i / taps;
+    int co, ci;
+    if (transposed) { co = (int)(r % c_out); ci = (int)(r / c_out); }   // [ci][co][tap]
+    else            { ci = (int)(r % c_in);  co = (int)(r / c_in); }    // [co][ci][tap]
+    T v = from_f32<T>(w[i] * inv);
+    if (pack_kn) pack_kn[((long long)tap * c_out + co) * c_in + ci] = v;
+    if (pack_nk) pack_nk[((long long)tap * c_in + ci) * c_out + co] = v;
+  }
+}
+
+// ---- generic direct convolution --------------------------------------------------------------
+// thread -> (output pixel, group of CO_T output channels)
+template <typename TI, typename TO, bool SCATTER, int CO_T>
+__global__ void __launch_bounds__(256) conv_direct_kernel(const TI* __restrict__ in, const TI* __restrict__ W,
+                                                          const float* __restrict__ bias, const float* __restrict__ colscale,
+                                                          ConvGeom g, TO* __restrict__ out) {
+  const int cog = g.co / CO_T;
+  const long long total = (long long)g.n * g.ho * g.wo * cog;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cog);
+    long long pix = idx / cog;
+    const int ox = (int)(pix % g.wo);
+    long long t = pix / g.wo;
+    const int oy = (int)(t % g.ho);
+    const int n = (int)(t / g.ho);
+    const int co0 = cg * CO_T;
+    float acc[CO_T];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < g.kh; ++ky) {
+      int iy;
+      if (SCATTER) {
+        int ty = oy + g.pad - ky;
+        if (ty < 0 || ty % g.stride != 0) continue;
+        iy = ty / g.stride;
+      } else {
+        iy = oy * g.stride - g.pad + ky;
+      }
+      if (iy < 0 || iy >= g.hi) continue;
+      for (int kx = 0; kx < g.kw; ++kx) {
+        int ix;
+        if (SCATTER) {
+          int tx = ox + g.pad - kx;
+          if (tx < 0 || tx % g.stride != 0) continue;
+          ix = tx / g.stride;
+        } else {
+          ix = ox * g.stride - g.pad + kx;
+        }
+        if (ix < 0 || ix >= g.wi) continue;
+        const TI* ip = in + (((long long)n * g.hi + iy) * g.wi + ix) * g.cr;
+        const TI* wp = W + (long long)(ky * g.kw + kx) * g.cr * g.co + co0;
+        int c = 0;
+        if ((g.cr & 7) == 0) {
+          for (; c < g.cr; c += 8) {
+            Vec8<TI> xv;
+            xv.load(ip + c);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (CO_T == 8) {
+                Vec8<TI> wv;
+                wv.load(wp + (long long)(c + q) * g.co);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv.v[q], wv.v[j], acc[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(xv.v[q], to_f32(wp[(long long)(c + q) * g.co + j]), acc[j]);
+              }
+            }
+          }
+        }
+        for (; c < g.cr; ++c) {
+          float xs = to_f32(ip[c]);
+          if (CO_T == 8) {
+            Vec8<TI> wv;
+            wv.load(wp + (long long)c * g.co);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(xs, wv.v[j], acc[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(xs, to_f32(wp[(long long)c * g.co + j]), acc[j]);
+          }
+        }
+      }
+    }
+    TO* op = out + pix * g.co + co0;
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) {
+      float v = acc[j];
+      if (bias) v += bias[co0 + j];
+      if (colscale) v *= colscale[(long long)n * g.co + co0 + j];
+      acc[j] = v;
+    }
+    if (CO_T == 8) {
+      Vec8<TO> ov;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ov.v[j] = acc[j];
+      ov.store(op);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j) op[j] = from_f32<TO>(acc[j]);
+    }
+  }
+}
+
+// ---- generic weight gradient -----------------------------------------------------------------
+// dw[cu][cs][tap] += sum_q U[q][cu] * S[q*s - p + k][cs];  U lives on the coarse grid (hu x wu),
+// S on the fine grid (hs x ws).  Block tile 32(cu) x 32(cs), 256 threads, 2x2 micro tile.
+struct WgradGeom {
+  int n, hu, wu, cu, hs, ws, cs, kh, kw, stride, pad;
+  long long q_per_split;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(const T* __restrict__ U, const T* __restrict__ S, WgradGeom g,
+                                                          float* __restrict__ dw) {
+  __shared__ float su[32][33];
+  __shared__ float ss[32][33];
+  const int tiles_s = (g.cs + 31) / 32;
+  const int tile_u = blockIdx.x / tiles_s, tile_s = blockIdx.x % tiles_s;
+  const int tap = blockIdx.y;
+  const int ky = tap / g.kw, kx = tap % g.kw;
+  const long long qtot = (long long)g.n * g.hu * g.wu;
+  const long long q0 = (long long)blockIdx.z * g.q_per_split;
+  const long long q1 = (q0 + g.q_per_split < qtot) ? q0 + g.q_per_split : qtot;
+  const int tid = threadIdx.x;
+  const int tu = tid / 16, ts = tid % 16;   // micro tile rows tu*2.., cols ts*2..
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  const int lc = tid % 32, lq = tid / 32;   // loader: channel lc, pixel row lq (8 per pass)
+  for (long long qb = q0; qb < q1; qb += 32) {
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      int qq = lq + pass * 8;
+      long long q = qb + qq;
+      float uv = 0.f, sv = 0.f;
+      if (q < q1) {
+        int xq = (int)(q % g.wu);
+        long long t = q / g.wu;
+        int yq = (int)(t % g.hu);
+        int n = (int)(t / g.hu);
+        int cu = tile_u * 32 + lc;
+        if (cu < g.cu) uv = to_f32(U[q * g.cu + cu]);
+        int sy = yq * g.stride - g.pad + ky, sx = xq * g.stride - g.pad + kx;
+        int cs = tile_s * 32 + lc;
+        if (cs < g.cs && sy >= 0 && sy < g.hs && sx >= 0 && sx < g.ws)
+          sv = to_f32(S[(((long long)n * g.hs + sy) * g.ws + sx) * g.cs + cs]);
+      }
+      su[qq][lc] = uv;
+      ss[qq][lc] = sv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int qq = 0; qq < 32; ++qq) {
+      float u0 = su[qq][tu * 2], u1 = su[qq][tu * 2 + 1];
+      float s0 = ss[qq][ts * 2], s1 = ss[qq][ts * 2 + 1];
+      acc[0][0] = fmaf(u0, s0, acc[0][0]);
+      acc[0][1] = fmaf(u0, s1, acc[0][1]);
+      acc[1][0] = fmaf(u1, s0, acc[1][0]);
+      acc[1][1] = fmaf(u1, s1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+  const int taps = g.kh * g.kw;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      int cu = tile_u * 32 + tu * 2 + a, cs = tile_s * 32 + ts * 2 + b;
+      if (cu < g.cu && cs < g.cs) atomicAdd(&dw[((long long)cu * g.cs + cs) * taps + tap], acc[a][b]);
+    }
+}
+
+// dbias[c] += sum over rows of dy[row][c]
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long long rows, int c, long long rows_per_block, float* __restrict__ out) {
+  long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += to_f32(x[r * c + ch]);
+    atomicAdd(&out[ch], s);
+  }
+}
+
+// ---- host-side launchers (called from conv_api.cu) -------------------------------------------
+template <typename TI, typename TO>
+static int launch_direct(bool scatter, const TI* in, const TI* W, const float* bias, const float* colscale, const ConvGeom& g,
+                         TO* out, cudaStream_t s) {
+  const bool v8 = (g.co % 8 == 0);
+  const long long total = (long long)g.n * g.ho * g.wo * (v8 ? g.co / 8 : g.co);
+  if (total == 0) return VG_OK;
+  int grid = (int)std::min<long long>(cdiv(total, 256), (long long)num_sms() * 32);
+  if (scatter) {
+    if (v8) conv_direct_kernel<TI, TO, true, 8><<<grid, 256, 0, s>>>(in, W, bias, colscale, g, out);
+    else    conv_direct_kernel<TI, TO, true, 1><<<grid, 256, 0, s>>>(in, W, bias, colscale, g, out);
+  } else {
+    if (v8) conv_direct_kernel<TI, TO, false, 8><<<grid, 256, 0, s>>>(in, W, bias, colscale, g, out);
+    else    conv_direct_kernel<TI, TO, false, 1><<<grid, 256, 0, s>>>(in, W, bias, colscale, g, out);
+  }
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+int simt_conv_forward(const VgConvDesc* d, const void* x, const void* pack_nk, const float* bias, const float* colscale, void* y,
+                      cudaStream_t s) {
+  ConvGeom g{d->n, d->h_in, d->w_in, d->c_in, d->h_out, d->w_out, d->c_out, d->kh, d->kw, d->stride, d->pad};
+  const bool scatter = d->transposed != 0;
+  if (d->act_dtype == VG_BF16) {
+    if (d->out_dtype == VG_BF16)
+      return launch_direct<__nv_bfloat16, __nv_bfloat16>(scatter, (const __nv_bfloat16*)x, (const __nv_bfloat16*)pack_nk, bias, colscale, g,
+                                                         (__nv_bfloat16*)y, s);
+    return launch_direct<__nv_bfloat16, float>(scatter, (const __nv_bfloat16*)x, (const __nv_bfloat16*)pack_nk, bias, colscale, g, (float*)y, s);
+  }
+  VG_CHECK_ARG(d->out_dtype == VG_F32, "fp32 activations require fp32 output");
+  return launch_direct<float, float>(scatter, (const float*)x, (const float*)pack_nk, bias, colscale, g, (float*)y, s);
+}
+
+int simt_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pack_kn, void* dx, cudaStream_t s) {
+  // reduce over c_out; output has c_in channels on the input grid
+  ConvGeom g{d->n, d->h_out, d->w_out, d->c_out, d->h_in, d->w_in, d->c_in, d->kh, d->kw, d->stride, d->pad};
+  const bool scatter = d->transposed == 0;   // Conv2d dgrad scatters, ConvTranspose2d dgrad gathers
+  if (d->act_dtype == VG_BF16)
+    return launch_direct<__nv_bfloat16, __nv_bfloat16>(scatter, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pack_kn, nullptr, nullptr, g,
+                                                       (__nv_bfloat16*)dx, s);
+  return launch_direct<float, float>(scatter, (const float*)dy, (const float*)pack_kn, nullptr, nullptr, g, (float*)dx, s);
+}
+
+int simt_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* dw, cudaStream_t s) {
+  WgradGeom g;
+  const void *U, *S;
+  if (!d->transposed) {   // dw[co][ci][tap]: U = dy on the output grid, S = x
+    g = WgradGeom{d->n, d->h_out, d->w_out, d->c_out, d->h_in, d->w_in, d->c_in, d->kh, d->kw, d->stride, d->pad, 0};
+    U = dy; S = x;
+  } else {                // dw[ci][co][tap]: U = x on the input grid, S = dy
+    g = WgradGeom{d->n, d->h_in, d->w_in, d->c_in, d->h_out, d->w_out, d->c_out, d->kh, d->kw, d->stride, d->pad, 0};
+    U = x; S = dy;
+  }
+  const long long qtot = (long long)g.n * g.hu * g.wu;
+  if (qtot == 0) return VG_OK;
+  const int tiles = ((g.cu + 31) / 32) * ((g.cs + 31) / 32);
+  const int taps = g.kh * g.kw;
+  long long want = std::max<long long>(1, (long long)num_sms() * 4 / ((long long)tiles * taps));
+  long long splits = std::min<long long>(want, cdiv(qtot, 256));
+  splits = std::max<long long>(1, std::min<long long>(splits, 65535));
+  g.q_per_split = cdiv(cdiv(qtot, splits), 32) * 32;
+  splits = cdiv(qtot, g.q_per_split);
+  dim3 grid(tiles, taps, (unsigned)splits);
+  if (d->act_dtype == VG_BF16)
+    wgrad_simt_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)U, (const __nv_bfloat16*)S, g, dw);
+  else
+    wgrad_simt_kernel<float><<<grid, 256, 0, s>>>((const float*)U, (const float*)S, g, dw);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+int simt_colsum(const void* x, long long rows, int c, int dtype, float* out, cudaStream_t s) {
+  if (rows == 0) return VG_OK;
+  long long blocks = std::min<long long>(cdiv(rows, 64), (long long)num_sms() * 4);
+  long long rpb = cdiv(rows, blocks);
+  blocks = cdiv(rows, rpb);
+  int threads = std::min(1024, ((c + 31) / 32) * 32);
+  if (dtype == VG_BF16)
+    colsum_kernel<__nv_bfloat16><<<(int)blocks, threads, 0, s>>>((const __nv_bfloat16*)x, rows, c, rpb, out);
+  else
+    colsum_kernel<float><<<(int)blocks, threads, 0, s>>>((const float*)x, rows, c, rpb, out);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+int simt_pack_weights(const VgConvDesc* d, const float* w, const float* sigma, void* pack_kn, void* pack_nk, cudaStream_t s) {
+  const int taps = d->kh * d->kw;
+  const long long total = (long long)taps * d->c_in * d->c_out;
+  if (total == 0) return VG_OK;
+  int grid = (int)std::min<long long>(cdiv(total, 256), (long long)num_sms() * 8);
+  if (d->act_dtype == VG_BF16)
+    pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(w, sigma, d->c_out, d->c_in, taps, d->transposed, (__nv_bfloat16*)pack_kn,
+                                                            (__nv_bfloat16*)pack_nk);
+  else
+    pack_weights_kernel<float><<<grid, 256, 0, s>>>(w, sigma, d->c_out, d->c_in, taps, d->transposed, (float*)pack_kn, (float*)pack_nk);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+}  // namespace vg

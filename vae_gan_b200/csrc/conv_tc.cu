@@ -1,0 +1,627 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a (bf16 in, fp32 accumulate).
+//
+// One kernel family covers every dense contraction of the reference's hot path (SURVEY.md K1-K3,
+// K5): Conv2d 3x3 / 1x1 at stride 1 and 2, ConvTranspose2d 4x4 stride 2, forward and dgrad
+// (tc_conv_kernel, "tap table" form) and all their weight gradients (tc_wgrad_kernel).
+//
+// tc_conv_kernel: D[128 pixels][BN channels] = sum over taps t, 64-channel chunks kc of
+//     A_t,kc[128 pixels][64]  .  W_t,kc[BN][64]^T
+//   * A tile = ONE TMA box {64 ch, TW, TH, TN} of the NHWC activation at the tap's (dx,dy) shift;
+//     out-of-bounds coordinates are zero-filled by TMA, which is exactly the convolution padding.
+//     A box lands as 128 rows x 128 B with the 128B swizzle = the canonical K-major UMMA layout.
+//   * stride-2 gathers read one of four "parity" tensor maps (even/odd rows x even/odd columns
+//     of the fine tensor), so every load is still a dense unit-stride box;
+//   * stride-2 scatters (ConvTranspose2d forward, Conv2d-s2 dgrad) are decomposed into the four
+//     output sub-pixel phases (blockIdx.z), each a small stride-1 convolution - no zero insertion.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+//     warps 4-7 = epilogue (tcgen05.ld -> bias / Dropout2d column scale -> bf16|f32 -> global).
+//
+// tc_wgrad_kernel: dW[128 = 2 x 64 (tap, c_s chunk)][BN = c_u tile] += S^T . U over a range of
+//   64-pixel boxes (split-K across CTAs, fp32 atomics into the torch-layout gradient).  Both
+//   operands are MN-major (channels contiguous, pixels along K) straight from the same TMA boxes.
+#include <algorithm>
+#include <mutex>
+#include "vg_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace vg {
+
+// ------------------------------------------------------------------------------------------
+// parameter blocks (passed by value as __grid_constant__)
+// ------------------------------------------------------------------------------------------
+struct TcTap {
+  int8_t map, dy, dx, pad_;
+  int32_t wrow;   // row offset of this tap's slab in the weight tensor map (= tap * n_out)
+};
+struct TcPhase {
+  int32_t ntaps, oy_off, ox_off, pad_;
+  TcTap taps[16];
+};
+struct alignas(64) TcConvParams {
+  CUtensorMap in_maps[4];
+  CUtensorMap w_map;
+  TcPhase phases[4];
+  int tiles_x, tiles_y, tiles_n;
+  int tw_log2, th_log2, TW, TH, TN;
+  int gw, gh, gn;        // GEMM pixel grid of one phase
+  int k_chunks;          // reduction channels / 64
+  int n_out;             // output channels
+  int OH, OW, os;        // output tensor spatial dims and phase stride
+  int out_f32;
+  void* out;
+  const float* bias;
+  const float* colscale;
+};
+
+struct alignas(64) TcWgradParams {
+  CUtensorMap s_maps[4];
+  CUtensorMap u_map;
+  TcTap taps[16];
+  int ntaps, cs_chunks, cs, cu;
+  int tiles_x, tiles_y, tiles_n, TW, TH, TN;
+  int n_boxes, boxes_per_split;
+  float* dw;
+};
+
+constexpr int kTcThreads = 256;
+constexpr int kABytes = 128 * 128;   // 128 rows x 64 bf16
+
+template <int BN, int STAGES>
+struct ConvSmem {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBytes = STAGES * (kABytes + kBBytes) + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+// ------------------------------------------------------------------------------------------
+// forward / dgrad implicit GEMM
+// ------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int kBBytes = BN * 128;
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kABytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * kBBytes);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TcPhase& ph = p.phases[blockIdx.z];
+  const int ntaps = ph.ntaps;
+  const int num_k = ntaps * p.k_chunks;
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  const int tn = t / p.tiles_y;
+  const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+  const int ncol0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.w_map);
+    ptx::prefetch_tmap(&p.in_maps[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<BN>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tp = 0; tp < ntaps; ++tp) {
+          const TcTap tap = ph.taps[tp];
+          const CUtensorMap* im = &p.in_maps[tap.map];
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(&full[stage], kABytes + kBBytes);
+            ptx::tma_load_4d(sA + stage * kABytes, im, &full[stage], kc * 64, x0 + tap.dx, y0 + tap.dy, n0);
+            ptx::tma_load_2d(sB + stage * kBBytes, &p.w_map, &full[stage], kc * 64, tap.wrow + ncol0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < num_k; ++i) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(sA + stage * kABytes);
+          const uint32_t b_addr = ptx::smem_u32(sB + stage * kBBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
+            ptx::mma_bf16_ss(tmem_base, ad, bd, idesc, (i | k) != 0);
+          }
+          ptx::mma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(tmem_full);
+      }
+    }
+  }
+
+  if (warp >= 4) {
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int xl = row & (p.TW - 1);
+    const int yl = (row >> p.tw_log2) & (p.TH - 1);
+    const int nl = row >> (p.tw_log2 + p.th_log2);
+    const int gx = x0 + xl, gy = y0 + yl, gn = n0 + nl;
+    const bool valid = gx < p.gw && gy < p.gh && gn < p.gn;
+    const long long opix = ((long long)gn * p.OH + (long long)gy * p.os + ph.oy_off) * p.OW + (long long)gx * p.os + ph.ox_off;
+    if (num_k > 0) {
+      ptx::mbar_wait(tmem_full, 0);
+      ptx::tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      if (num_k > 0) {
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (valid) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + ncol0 + c0 + j);
+        }
+        if (p.colscale != nullptr) {
+          const float* cs = p.colscale + (long long)gn * p.n_out + ncol0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
+        }
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.n_out + ncol0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * i], v[j + 2 * i + 1]);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(o + j) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<BN>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------
+template <int NB, int STAGES>
+struct WgradSmem {
+  static constexpr int kStageBytes = (2 + NB) * 8192;
+  static constexpr int kBytes = STAGES * kStageBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int NB, int STAGES>
+__global__ void __launch_bounds__(kTcThreads) tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int BN = NB * 64;
+  constexpr int kStageBytes = (2 + NB) * 8192;
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_slabs = p.ntaps * p.cs_chunks;
+  const int slab0 = blockIdx.x * 2;
+  const bool has2 = slab0 + 1 < n_slabs;
+  const int slab1 = has2 ? slab0 + 1 : slab0;
+  const int box_begin = blockIdx.z * p.boxes_per_split;
+  const int box_end = min(p.n_boxes, box_begin + p.boxes_per_split);
+  const int num_k = max(0, box_end - box_begin);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.u_map);
+    ptx::prefetch_tmap(&p.s_maps[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const int tapA = slab0 / p.cs_chunks, chA = slab0 % p.cs_chunks;
+        const int tapB = slab1 / p.cs_chunks, chB = slab1 % p.cs_chunks;
+        const TcTap ta = p.taps[tapA], tb = p.taps[tapB];
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int b = box_begin; b < box_end; ++b) {
+          int t = b;
+          const int tx = t % p.tiles_x; t /= p.tiles_x;
+          const int ty = t % p.tiles_y;
+          const int tn = t / p.tiles_y;
+          const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+          ptx::mbar_wait(&empty[stage], phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full[stage], kStageBytes);
+          uint8_t* st = smem + stage * kStageBytes;
+          ptx::tma_load_4d(st, &p.s_maps[ta.map], &full[stage], chA * 64, x0 + ta.dx, y0 + ta.dy, n0);
+          ptx::tma_load_4d(st + 8192, &p.s_maps[tb.map], &full[stage], chB * 64, x0 + tb.dx, y0 + tb.dy, n0);
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+            ptx::tma_load_4d(st + (2 + j) * 8192, &p.u_map, &full[stage], (blockIdx.y * NB + j) * 64, x0, y0, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < num_k; ++i) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * kStageBytes);
+          const uint32_t b_addr = a_addr + 2 * 8192;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // 16 pixels (two 8-row atoms) per MMA
+            const uint64_t ad = ptx::make_smem_desc(a_addr + k * 2048, 8192, 1024);
+            const uint64_t bd = ptx::make_smem_desc(b_addr + k * 2048, 8192, 1024);
+            ptx::mma_bf16_ss(tmem_base, ad, bd, idesc, (i | k) != 0);
+          }
+          ptx::mma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(tmem_full);
+      }
+    }
+  }
+
+  if (warp >= 4 && num_k > 0) {
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int slab = (row < 64) ? slab0 : slab1;
+    const bool row_valid = (row < 64) || has2;
+    const int tap = slab / p.cs_chunks, chunk = slab % p.cs_chunks;
+    const int cs = chunk * 64 + (row & 63);
+    ptx::mbar_wait(tmem_full, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      ptx::tmem_ld_wait();
+      if (row_valid) {
+        const int cu0 = blockIdx.y * BN + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float* dst = p.dw + ((long long)(cu0 + j) * p.cs + cs) * p.ntaps + tap;
+          atomicAdd(dst, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+}
+
+// ==========================================================================================
+// host side: tensor maps, tap tables, launch
+// ==========================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static EncodeTiledFn get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  return g_encode;
+}
+
+// NHWC bf16 activation [n][h][w][c]; parity (py,px) with step `s` selects rows py, py+s, ... and
+// columns px, px+s, ...  Box = {64, TW, TH, TN}.
+static int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int s, int py, int px, int TW, int TH,
+                        int TN) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return VG_ECUDA;
+  }
+  const int hs = (h - py + s - 1) / s, ws = (w - px + s - 1) / s;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)std::max(ws, 1), (cuuint64_t)std::max(hs, 1), (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)s * c * 2, (cuuint64_t)s * w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  void* addr = (void*)((const char*)base + ((size_t)py * w + px) * c * 2);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, addr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activation) failed: %d (n=%d h=%d w=%d c=%d s=%d box=%d,%d,%d)", (int)r, n, h, w, c, s, TW, TH, TN);
+    return VG_ECUDA;
+  }
+  return VG_OK;
+}
+
+static int make_weight_map(CUtensorMap* m, const void* base, long long rows, int k, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return VG_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weights) failed: %d (rows=%lld k=%d box_rows=%d)", (int)r, rows, k, box_rows);
+    return VG_ECUDA;
+  }
+  return VG_OK;
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// choose a {TW,TH,TN} box of `pixels` (power of two) GEMM rows minimising padded work
+static void choose_box(int gw, int gh, int gn, int pixels, int* TW, int* TH, int* TN) {
+  double best = 1e30;
+  int bw = 1, bh = 1;
+  for (int tw = 1; tw <= pixels; tw *= 2)
+    for (int th = 1; tw * th <= pixels; th *= 2) {
+      int tn = pixels / (tw * th);
+      if (tw > 256 || th > 256 || tn > 256) continue;
+      double padded = (double)cdiv(gw, tw) * tw * (double)cdiv(gh, th) * th * (double)cdiv(gn, tn) * tn;
+      double score = padded - 1e-3 * tw - 1e-6 * th;   // ties: prefer wide boxes (longer contiguous runs)
+      if (score < best) { best = score; bw = tw; bh = th; }
+    }
+  *TW = bw; *TH = bh; *TN = pixels / (bw * bh);
+}
+
+bool tc_conv_supported(const VgConvDesc* d, bool dgrad) {
+  if (g_force_simt) return false;
+  if (d->act_dtype != VG_BF16) return false;
+  if (d->stride != 1 && d->stride != 2) return false;
+  if (d->kh != d->kw || d->kh * d->kw > 16) return false;
+  const int c_red = dgrad ? d->c_out : d->c_in;
+  const int n_out = dgrad ? d->c_in : d->c_out;
+  if (c_red % 64 != 0 || n_out % 64 != 0) return false;
+  if (d->stride == 2 && ((d->transposed ? d->h_out : d->h_in) % 2 != 0 || (d->transposed ? d->w_out : d->w_in) % 2 != 0)) return false;
+  if (dgrad && d->out_dtype != VG_BF16 && false) return false;
+  return get_encode() != nullptr;
+}
+
+bool tc_wgrad_supported(const VgConvDesc* d) {
+  if (g_force_simt) return false;
+  if (d->act_dtype != VG_BF16) return false;
+  if (d->stride != 1 && d->stride != 2) return false;
+  if (d->kh != d->kw || d->kh * d->kw > 16) return false;
+  if (d->c_in % 64 != 0 || d->c_out % 64 != 0) return false;
+  if (d->stride == 2 && ((d->transposed ? d->h_out : d->h_in) % 2 != 0 || (d->transposed ? d->w_out : d->w_in) % 2 != 0)) return false;
+  return get_encode() != nullptr;
+}
+
+template <int BN, int STAGES>
+static int launch_conv(const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    VG_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<BN, STAGES>::kBytes));
+    attr_done = true;
+  }
+  tc_conv_kernel<BN, STAGES><<<grid, kTcThreads, ConvSmem<BN, STAGES>::kBytes, s>>>(p);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+template <int NB, int STAGES>
+static int launch_wgrad(const TcWgradParams& p, dim3 grid, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    VG_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<NB, STAGES>::kBytes));
+    attr_done = true;
+  }
+  tc_wgrad_kernel<NB, STAGES><<<grid, kTcThreads, WgradSmem<NB, STAGES>::kBytes, s>>>(p);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+// Build the tap table(s).  `gather` : out grid coarse (or same), input fine via parity maps when
+// stride 2.  `scatter`: out grid fine, decomposed into s*s phases over the coarse input grid.
+// flip=false: weight slab index = ky*kw+kx.
+static void build_gather_taps(TcPhase* ph, int k, int stride, int pad, int n_out) {
+  ph->ntaps = 0; ph->oy_off = 0; ph->ox_off = 0;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      TcTap& t = ph->taps[ph->ntaps++];
+      const int ty = ky - pad, tx = kx - pad;
+      if (stride == 1) {
+        t.map = 0; t.dy = (int8_t)ty; t.dx = (int8_t)tx;
+      } else {
+        const int py = ((ty % 2) + 2) % 2, px = ((tx % 2) + 2) % 2;
+        t.map = (int8_t)(py * 2 + px);
+        t.dy = (int8_t)((ty - py) / 2);
+        t.dx = (int8_t)((tx - px) / 2);
+      }
+      t.pad_ = 0;
+      t.wrow = (ky * k + kx) * n_out;
+    }
+}
+static void build_scatter_phase(TcPhase* ph, int k, int stride, int pad, int n_out, int phy, int phx) {
+  ph->ntaps = 0; ph->oy_off = phy; ph->ox_off = phx;
+  for (int ky = 0; ky < k; ++ky) {
+    if (((phy + pad - ky) % stride + stride) % stride != 0) continue;
+    for (int kx = 0; kx < k; ++kx) {
+      if (((phx + pad - kx) % stride + stride) % stride != 0) continue;
+      TcTap& t = ph->taps[ph->ntaps++];
+      t.map = 0;
+      // input index = q + (ph + pad - k)/stride (exact division, may be negative)
+      t.dy = (int8_t)((phy + pad - ky) / stride);
+      t.dx = (int8_t)((phx + pad - kx) / stride);
+      t.pad_ = 0;
+      t.wrow = (ky * k + kx) * n_out;
+    }
+  }
+}
+
+static int pick_bn(int n_out) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("VG_TC_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced && n_out % forced == 0) return forced;
+  if (n_out % 128 == 0) return 128;
+  return 64;
+}
+
+// dgrad=false: y = conv(x).  dgrad=true: dx from dy.  `in` is the tensor being read.
+int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpack, const float* bias, const float* colscale,
+                void* out, int out_dtype, cudaStream_t s) {
+  TcConvParams p;
+  memset(&p, 0, sizeof(p));
+  // pattern: which side is the coarse grid
+  //   Conv2d fwd           : gather  (in = x fine, out = y coarse)
+  //   Conv2d dgrad         : scatter (in = dy coarse, out = dx fine)
+  //   ConvTranspose2d fwd  : scatter (in = x coarse, out = y fine)
+  //   ConvTranspose2d dgrad: gather  (in = dy fine, out = dx coarse)
+  const bool gather = (d->transposed != 0) == dgrad;
+  const int in_h = dgrad ? d->h_out : d->h_in, in_w = dgrad ? d->w_out : d->w_in, in_c = dgrad ? d->c_out : d->c_in;
+  const int out_h = dgrad ? d->h_in : d->h_out, out_w = dgrad ? d->w_in : d->w_out, n_out = dgrad ? d->c_in : d->c_out;
+  const int k = d->kh, st = d->stride, pad = d->pad;
+  p.k_chunks = in_c / 64;
+  p.n_out = n_out;
+  p.OH = out_h; p.OW = out_w;
+  p.out = out; p.out_f32 = out_dtype == VG_F32;
+  p.bias = bias; p.colscale = colscale;
+  int nphase = 1;
+  if (gather) {
+    p.gw = out_w; p.gh = out_h; p.gn = d->n; p.os = 1;
+    build_gather_taps(&p.phases[0], k, st, pad, n_out);
+  } else {
+    p.os = st;
+    nphase = st * st;
+    p.gw = (out_w + st - 1) / st; p.gh = (out_h + st - 1) / st; p.gn = d->n;
+    for (int phy = 0; phy < st; ++phy)
+      for (int phx = 0; phx < st; ++phx) build_scatter_phase(&p.phases[phy * st + phx], k, st, pad, n_out, phy, phx);
+  }
+  choose_box(p.gw, p.gh, p.gn, 128, &p.TW, &p.TH, &p.TN);
+  p.tw_log2 = ilog2(p.TW); p.th_log2 = ilog2(p.TH);
+  p.tiles_x = (int)cdiv(p.gw, p.TW); p.tiles_y = (int)cdiv(p.gh, p.TH); p.tiles_n = (int)cdiv(p.gn, p.TN);
+  int rc;
+  if (gather && st == 2) {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        if ((rc = make_act_map(&p.in_maps[py * 2 + px], in, d->n, in_h, in_w, in_c, 2, py, px, p.TW, p.TH, p.TN))) return rc;
+  } else {
+    if ((rc = make_act_map(&p.in_maps[0], in, d->n, in_h, in_w, in_c, 1, 0, 0, p.TW, p.TH, p.TN))) return rc;
+    p.in_maps[1] = p.in_maps[2] = p.in_maps[3] = p.in_maps[0];
+  }
+  const int BN = pick_bn(n_out);
+  if ((rc = make_weight_map(&p.w_map, wpack, (long long)k * k * n_out, in_c, BN))) return rc;
+  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.tiles_n), (unsigned)(n_out / BN), (unsigned)nphase);
+  if (grid.x == 0) return VG_OK;
+  switch (BN) {
+    case 64: return launch_conv<64, 4>(p, grid, s);
+    case 128: return launch_conv<128, 3>(p, grid, s);
+    case 256: return launch_conv<256, 4>(p, grid, s);
+    default: set_error("unsupported BN %d", BN); return VG_EUNSUPPORTED;
+  }
+}
+
+int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, cudaStream_t s) {
+  TcWgradParams p;
+  memset(&p, 0, sizeof(p));
+  // dw[cu][cs][tap] += sum_q U[q][cu] * S[q*stride - pad + k][cs]
+  const void *U, *S;
+  int hu, wu, cu, hs, ws, cs;
+  if (!d->transposed) { U = dy; hu = d->h_out; wu = d->w_out; cu = d->c_out; S = x; hs = d->h_in; ws = d->w_in; cs = d->c_in; }
+  else                { U = x;  hu = d->h_in;  wu = d->w_in;  cu = d->c_in;  S = dy; hs = d->h_out; ws = d->w_out; cs = d->c_out; }
+  const int k = d->kh, st = d->stride, pad = d->pad;
+  TcPhase tmp;
+  build_gather_taps(&tmp, k, st, pad, 0);
+  p.ntaps = tmp.ntaps;
+  for (int i = 0; i < tmp.ntaps; ++i) p.taps[i] = tmp.taps[i];
+  p.cs_chunks = cs / 64; p.cs = cs; p.cu = cu;
+  choose_box(wu, hu, d->n, 64, &p.TW, &p.TH, &p.TN);
+  p.tiles_x = (int)cdiv(wu, p.TW); p.tiles_y = (int)cdiv(hu, p.TH); p.tiles_n = (int)cdiv(d->n, p.TN);
+  p.n_boxes = p.tiles_x * p.tiles_y * p.tiles_n;
+  p.dw = dw;
+  int rc;
+  if (st == 2) {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        if ((rc = make_act_map(&p.s_maps[py * 2 + px], S, d->n, hs, ws, cs, 2, py, px, p.TW, p.TH, p.TN))) return rc;
+  } else {
+    if ((rc = make_act_map(&p.s_maps[0], S, d->n, hs, ws, cs, 1, 0, 0, p.TW, p.TH, p.TN))) return rc;
+    p.s_maps[1] = p.s_maps[2] = p.s_maps[3] = p.s_maps[0];
+  }
+  if ((rc = make_act_map(&p.u_map, U, d->n, hu, wu, cu, 1, 0, 0, p.TW, p.TH, p.TN))) return rc;
+  const int NB = (cu % 256 == 0) ? 4 : ((cu % 128 == 0) ? 2 : 1);
+  const int m_tiles = (p.ntaps * p.cs_chunks + 1) / 2;
+  const int n_tiles = cu / (NB * 64);
+  if (p.n_boxes == 0) return VG_OK;
+  long long want = std::max<long long>(1, cdiv(2LL * num_sms(), (long long)m_tiles * n_tiles));
+  long long splits = std::min<long long>(want, std::max<long long>(1, p.n_boxes / 4));
+  p.boxes_per_split = (int)cdiv(p.n_boxes, splits);
+  splits = cdiv(p.n_boxes, p.boxes_per_split);
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
+  switch (NB) {
+    case 1: return launch_wgrad<1, 6>(p, grid, s);
+    case 2: return launch_wgrad<2, 5>(p, grid, s);
+    default: return launch_wgrad<4, 4>(p, grid, s);
+  }
+}
+
+}  // namespace vg

@@ -1,0 +1,659 @@
+// The remaining (memory- or latency-bound) pieces of the VAE-GAN step: Linear layers of the
+// discriminator head, avg_pool2d+flatten, spectral-norm power iteration, reparameterisation,
+// the fused loss+gradient kernels, the fused Adam/RMSprop update, and layout/dtype helpers.
+#include <algorithm>
+#include "vg_common.cuh"
+
+namespace vg {
+
+// ------------------------------------------------------------------------------------------
+// generic small GEMM  C[i][j] (+)= sum_l A(i,l) * B(l,j)   (fp32 accumulate)
+//   A(i,l) = A[i*sai + l*sal], B(l,j) = B[l*sbl + j*sbj].  32x32 tile, 256 threads, 2x2 micro.
+//   mode 0: C = acc ; mode 1: C += acc (single writer) ; mode 2: atomicAdd (split-K)
+// ------------------------------------------------------------------------------------------
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256) gemm_small_kernel(const TA* __restrict__ A, long long sai, long long sal,
+                                                          const TB* __restrict__ B, long long sbl, long long sbj, int I, int J,
+                                                          int L, int l_per_split, float* __restrict__ C, int mode) {
+  __shared__ float sa[32][33];   // [l][i]
+  __shared__ float sb[32][33];   // [l][j]
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int lbeg = blockIdx.z * l_per_split, lend = min(L, lbeg + l_per_split);
+  const int tid = threadIdx.x;
+  const int ti = tid / 16, tj = tid % 16;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  // loader index: fast index along whichever dimension is contiguous
+  const bool a_l_fast = (sal == 1), b_l_fast = (sbl == 1);
+  for (int lb = lbeg; lb < lend; lb += 32) {
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      int f = tid % 32, sl = tid / 32 + pass * 8;
+      {
+        int l = a_l_fast ? f : sl, i = a_l_fast ? sl : f;
+        float v = 0.f;
+        if (lb + l < lend && i0 + i < I) v = to_f32(A[(long long)(i0 + i) * sai + (long long)(lb + l) * sal]);
+        sa[l][i] = v;
+      }
+      {
+        int l = b_l_fast ? f : sl, j = b_l_fast ? sl : f;
+        float v = 0.f;
+        if (lb + l < lend && j0 + j < J) v = to_f32(B[(long long)(lb + l) * sbl + (long long)(j0 + j) * sbj]);
+        sb[l][j] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) {
+      float a0 = sa[l][ti * 2], a1 = sa[l][ti * 2 + 1];
+      float b0 = sb[l][tj * 2], b1 = sb[l][tj * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]);
+      acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]);
+      acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      int i = i0 + ti * 2 + a, j = j0 + tj * 2 + b;
+      if (i < I && j < J) {
+        float* c = C + (long long)i * J + j;
+        if (mode == 0) *c = acc[a][b];
+        else if (mode == 1) *c += acc[a][b];
+        else atomicAdd(c, acc[a][b]);
+      }
+    }
+}
+
+__global__ void bias_lrelu_kernel(float* __restrict__ y, const float* __restrict__ bias, long long total, int n, float slope) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v = y[i] + (bias ? bias[i % n] : 0.f);
+    y[i] = v > 0.f ? v : v * slope;
+  }
+}
+__global__ void colsum_f32_kernel(const float* __restrict__ x, int rows, int c, float* __restrict__ out) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += x[(long long)r * c + ch];
+  out[ch] += s;
+}
+
+template <typename TA, typename TB>
+static int launch_gemm(const TA* A, long long sai, long long sal, const TB* B, long long sbl, long long sbj, int I, int J, int L,
+                       float* C, int mode, int splits, cudaStream_t s) {
+  int lps = (int)cdiv(cdiv(L, splits), 32) * 32;
+  if (lps < 32) lps = 32;
+  splits = (int)cdiv(L, lps);
+  dim3 grid((unsigned)cdiv(J, 32), (unsigned)cdiv(I, 32), (unsigned)splits);
+  gemm_small_kernel<TA, TB><<<grid, 256, 0, s>>>(A, sai, sal, B, sbl, sbj, I, J, L, lps, C, mode);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// avg_pool2d(k) + flatten (NCHW order): out[n][ch*(ph*pw) + py*pw + px]  (fp32)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void avgpool_flatten_fwd_kernel(const T* __restrict__ x, int n, int h, int w, int c, int k, float* __restrict__ out) {
+  const int ph = h / k, pw = w / k;
+  const long long total = (long long)n * ph * pw * c;
+  const float inv = 1.0f / (float)(k * k);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c);
+    long long t = i / c;
+    int px = (int)(t % pw); t /= pw;
+    int py = (int)(t % ph);
+    int nn = (int)(t / ph);
+    float s = 0.f;
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) s += to_f32(x[(((long long)nn * h + py * k + dy) * w + px * k + dx) * c + ch]);
+    out[(long long)nn * c * ph * pw + (long long)ch * ph * pw + py * pw + px] = s * inv;
+  }
+}
+template <typename T>
+__global__ void avgpool_flatten_bwd_kernel(const float* __restrict__ dout, int n, int h, int w, int c, int k, T* __restrict__ dx) {
+  const int ph = h / k, pw = w / k;
+  const long long total = (long long)n * h * w * c;
+  const float inv = 1.0f / (float)(k * k);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % c);
+    long long t = i / c;
+    int x = (int)(t % w); t /= w;
+    int y = (int)(t % h);
+    int nn = (int)(t / h);
+    int py = y / k, px = x / k;
+    float v = 0.f;
+    if (py < ph && px < pw) v = dout[(long long)nn * c * ph * pw + (long long)ch * ph * pw + py * pw + px] * inv;
+    dx[i] = from_f32<T>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// spectral norm
+// ------------------------------------------------------------------------------------------
+// t[j] += sum_{i in slice} W[i][j] u[i]
+__global__ void sn_wt_u_kernel(const float* __restrict__ W, const float* __restrict__ u, int rows, int cols, int rows_per_slice,
+                               float* __restrict__ t) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  int r0 = blockIdx.y * rows_per_slice, r1 = min(rows, r0 + rows_per_slice);
+  float s = 0.f;
+  for (int i = r0; i < r1; ++i) s = fmaf(W[(long long)i * cols + j], u[i], s);
+  atomicAdd(&t[j], s);
+}
+// one warp per row: s[i] = (W[i] . t) / max(||t||, eps)   (normalize=1), or W[i] . t (normalize=0);
+// the warp of row 0 also writes v = t / max(||t||, eps)
+__global__ void sn_w_v_kernel(const float* __restrict__ W, const float* __restrict__ t, int rows, int cols, int normalize, float eps,
+                              float* __restrict__ v_out, float* __restrict__ s_out) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float dot = 0.f, nt = 0.f;
+  for (int j = lane; j < cols; j += 32) {
+    float tv = t[j];
+    dot = fmaf(W[(long long)row * cols + j], tv, dot);
+    nt = fmaf(tv, tv, nt);
+  }
+  dot = warp_sum(dot);
+  nt = warp_sum(nt);
+  float inv = normalize ? 1.0f / fmaxf(sqrtf(nt), eps) : 1.0f;
+  if (lane == 0) s_out[row] = dot * inv;
+  if (normalize && row == 0 && v_out != nullptr)
+    for (int j = lane; j < cols; j += 32) v_out[j] = t[j] * inv;
+}
+// single block: training: u = s / max(||s||, eps); sigma = sum u*s.  eval: sigma = sum u*s.
+__global__ void sn_finish_kernel(const float* __restrict__ s, float* __restrict__ u, int rows, int training, float eps,
+                                 float* __restrict__ sigma) {
+  __shared__ float red[32];
+  __shared__ float bc;
+  int tid = threadIdx.x;
+  float part = 0.f;
+  if (training) {
+    for (int i = tid; i < rows; i += blockDim.x) part = fmaf(s[i], s[i], part);
+    part = warp_sum(part);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+      bc = 1.0f / fmaxf(sqrtf(tot), eps);
+    }
+    __syncthreads();
+    float inv = bc;
+    for (int i = tid; i < rows; i += blockDim.x) u[i] = s[i] * inv;
+    __syncthreads();
+  }
+  part = 0.f;
+  for (int i = tid; i < rows; i += blockDim.x) part = fmaf(u[i], s[i], part);
+  part = warp_sum(part);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    *sigma = tot;
+  }
+}
+__global__ void sn_bwd_dot_kernel(const float* __restrict__ dwh, const float* __restrict__ w, long long n, float* __restrict__ acc) {
+  float part = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    part = fmaf(dwh[i], w[i], part);
+  part = warp_sum(part);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += red[k];
+    atomicAdd(acc, tot);
+  }
+}
+__global__ void sn_bwd_apply_kernel(const float* __restrict__ dwh, const float* __restrict__ u, const float* __restrict__ v,
+                                    const float* __restrict__ sigma, const float* __restrict__ dot, int rows, int cols,
+                                    float* __restrict__ dw) {
+  const long long n = (long long)rows * cols;
+  const float inv = 1.0f / *sigma;
+  const float c = *dot * inv;   // <dw_hat, W> / sigma
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int r = (int)(i / cols), cc = (int)(i % cols);
+    dw[i] += (dwh[i] - c * u[r] * v[cc]) * inv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// reparameterisation
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv_raw, const float* __restrict__ eps,
+                                   long long n, int training, T* __restrict__ z, float* __restrict__ lv) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float l = fminf(fmaxf(lv_raw[i], -50.f), 50.f);
+    lv[i] = l;
+    float zz = mu[i];
+    if (training) zz = fmaf(expf(0.5f * l), eps[i], zz);
+    z[i] = from_f32<T>(zz);
+  }
+}
+template <typename T>
+__global__ void reparam_bwd_kernel(const T* __restrict__ dz, const float* __restrict__ lv_raw, const float* __restrict__ eps,
+                                   long long n, int training, float* __restrict__ d_mu, float* __restrict__ d_lv) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = to_f32(dz[i]);
+    d_mu[i] = g;
+    float raw = lv_raw[i];
+    float r = 0.f;
+    if (training && raw >= -50.f && raw <= 50.f) r = g * 0.5f * expf(0.5f * raw) * eps[i];
+    d_lv[i] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused generator loss + gradients
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_atomic_add(double v, double* dst) {
+  __shared__ double red[32];
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(dst, t);
+  }
+}
+__device__ __forceinline__ float softplus_f(float x) { return x > 0.f ? x + log1pf(expf(-x)) : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) generator_loss_kernel(const T* __restrict__ xhat, const float* __restrict__ x,
+                                                              const float* __restrict__ mu, const float* __restrict__ lv,
+                                                              const float* __restrict__ logits, VgLossDesc d, T* __restrict__ d_xhat,
+                                                              float* __restrict__ d_mu, float* __restrict__ d_lv,
+                                                              float* __restrict__ d_logits, double* __restrict__ losses) {
+  const long long gsz = (long long)gridDim.x * blockDim.x;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // reconstruction: mean|d| + mean d^2 over the GLOBAL pixel count
+  double recon = 0.0;
+  const float inv_pix = 1.0f / (float)d.n_pix_global;
+  for (long long i = gid; i < d.n_pix; i += gsz) {
+    float df = to_f32(xhat[i]) - x[i];
+    recon += (double)(fabsf(df) + df * df);
+    float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+    d_xhat[i] = from_f32<T>(d.w_recon * inv_pix * (sg + 2.f * df));
+  }
+  // KL = -0.5 * sum(1 + lv - mu^2 - exp(lv))
+  double kl = 0.0;
+  for (long long i = gid; i < d.n_lat; i += gsz) {
+    float m = mu[i], l = lv[i], e = expf(l);
+    kl += (double)(-0.5f * (1.f + l - m * m - e));
+    d_mu[i] = d.w_kl * m;
+    d_lv[i] = d.w_kl * 0.5f * (e - 1.f);
+  }
+  // adversarial term on D(xhat) logits
+  double adv = 0.0;
+  const float inv_b = 1.0f / (float)d.n_logits_global;
+  for (long long i = gid; i < d.n_logits; i += gsz) {
+    float z = logits[i];
+    if (d.adv_mode == 0) {          // BCE-with-logits, target 1: softplus(-z)
+      adv += (double)softplus_f(-z);
+      d_logits[i] = d.w_adv * inv_b * (sigmoid_f(z) - 1.f);
+    } else {                         // -mean(D)
+      adv += (double)(-z);
+      d_logits[i] = -d.w_adv * inv_b;
+    }
+  }
+  recon *= (double)inv_pix;
+  adv *= (double)inv_b;
+  block_atomic_add(recon, &losses[1]);
+  block_atomic_add(kl, &losses[2]);
+  block_atomic_add(adv, &losses[3]);
+  block_atomic_add((double)d.w_recon * recon + (double)d.w_kl * kl + (double)d.w_adv * adv, &losses[0]);
+}
+
+__global__ void discriminator_loss_kernel(const float* __restrict__ d_real, const float* __restrict__ d_fake, int n, int n_global,
+                                          int adv_mode, float* __restrict__ g_real, float* __restrict__ g_fake,
+                                          double* __restrict__ losses) {
+  double lr = 0.0, lf = 0.0;
+  const float inv = 1.0f / (float)n_global;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float r = d_real[i], f = d_fake[i];
+    if (adv_mode == 0) {
+      lr += (double)softplus_f(-r);            // BCE(real, 1)
+      lf += (double)softplus_f(f);             // BCE(fake, 0)
+      g_real[i] = inv * (sigmoid_f(r) - 1.f);
+      g_fake[i] = inv * sigmoid_f(f);
+    } else {
+      lr += (double)(-r);                      // -mean(D(real))   README.md:792
+      lf += (double)f;                         //  mean(D(fake))   README.md:793
+      g_real[i] = -inv;
+      g_fake[i] = inv;
+    }
+  }
+  lr *= (double)inv;
+  lf *= (double)inv;
+  block_atomic_add(lr, &losses[1]);
+  block_atomic_add(lf, &losses[2]);
+  block_atomic_add(lr + lf, &losses[0]);
+}
+
+// ------------------------------------------------------------------------------------------
+// fused optimizer
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) optimizer_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, long long n4, long long n, VgOptDesc d) {
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    gg *= d.grad_scale;
+    if (d.weight_decay != 0.f) gg = fmaf(d.weight_decay, pp, gg);
+    if (d.kind == 0) {
+      mm = d.beta1 * mm + (1.f - d.beta1) * gg;
+      vv = d.beta2 * vv + (1.f - d.beta2) * gg * gg;
+      float denom = sqrtf(vv) / sqrtf(d.bias_corr2) + d.eps;
+      pp -= (d.lr / d.bias_corr1) * (mm / denom);
+    } else {
+      vv = d.alpha * vv + (1.f - d.alpha) * gg * gg;
+      pp -= d.lr * gg / (sqrtf(vv) + d.eps);
+    }
+    if (d.clamp > 0.f) pp = fminf(fmaxf(pp, -d.clamp), d.clamp);
+  };
+  const long long gsz = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gsz) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float4 mm = d.kind == 0 ? reinterpret_cast<float4*>(m)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    upd(pp.x, gg.x, mm.x, vv.x);
+    upd(pp.y, gg.y, mm.y, vv.y);
+    upd(pp.z, gg.z, mm.z, vv.z);
+    upd(pp.w, gg.w, mm.w, vv.w);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (d.kind == 0) reinterpret_cast<float4*>(m)[i] = mm;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gsz) {
+    float mm = d.kind == 0 ? m[i] : 0.f;
+    upd(p[i], g[i], mm, v[i]);
+    if (d.kind == 0) m[i] = mm;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// layout / dtype
+// ------------------------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = from_f32<TD>(to_f32(src[i]));
+}
+// tiled transpose of [c][hw] <-> [hw][c] per image
+template <typename TD>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int c, int hw, TD* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const float* s = src + (long long)n * c * hw;
+  TD* d = dst + (long long)n * c * hw;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int cc = c0 + r, pp = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (cc < c && pp < hw) ? s[(long long)cc * hw + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int pp = p0 + r, cc = c0 + threadIdx.x;
+    if (pp < hw && cc < c) d[(long long)pp * c + cc] = from_f32<TD>(tile[threadIdx.x][r]);
+  }
+}
+template <typename TS>
+__global__ void nhwc_to_nchw_kernel(const TS* __restrict__ src, int c, int hw, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const TS* s = src + (long long)n * c * hw;
+  float* d = dst + (long long)n * c * hw;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int pp = p0 + r, cc = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (pp < hw && cc < c) ? to_f32(s[(long long)pp * c + cc]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int cc = c0 + r, pp = p0 + threadIdx.x;
+    if (cc < c && pp < hw) d[(long long)cc * hw + pp] = tile[threadIdx.x][r];
+  }
+}
+
+}  // namespace vg
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace vg;
+
+static inline int ew_grid(long long n, int per_thread = 4) {
+  return (int)std::max<long long>(1, std::min<long long>(cdiv(n, 256LL * per_thread), (long long)num_sms() * 8));
+}
+
+extern "C" int vg_linear_forward(const void* x, const void* w, const float* bias, int m, int n, int k, int dtype, float slope,
+                                 void* y, vg_stream_t stream) {
+  VG_CHECK_ARG(x && w && y && m >= 0 && n > 0 && k > 0, "bad args");
+  if (m == 0) return VG_OK;
+  cudaStream_t s = as_stream(stream);
+  // x, y are fp32 (the head's activations are tiny); w is `dtype`.  y = x w^T: I=m, J=n, L=k
+  int tiles = (int)(cdiv(n, 32) * cdiv(m, 32));
+  int splits = (int)std::max<long long>(1, std::min<long long>(cdiv(2LL * num_sms(), tiles), cdiv(k, 256)));
+  int mode = 0;
+  if (splits > 1) {
+    VG_CUDA(cudaMemsetAsync(y, 0, (size_t)m * n * sizeof(float), s));
+    mode = 2;
+  }
+  int rc;
+  if (dtype == VG_BF16)
+    rc = launch_gemm<float, __nv_bfloat16>((const float*)x, k, 1, (const __nv_bfloat16*)w, 1, k, m, n, k, (float*)y, mode, splits, s);
+  else
+    rc = launch_gemm<float, float>((const float*)x, k, 1, (const float*)w, 1, k, m, n, k, (float*)y, mode, splits, s);
+  if (rc) return rc;
+  if (bias != nullptr || slope != 1.0f) {
+    long long total = (long long)m * n;
+    bias_lrelu_kernel<<<ew_grid(total, 1), 256, 0, s>>>((float*)y, bias, total, n, slope);
+    VG_LAUNCHED();
+  }
+  return VG_OK;
+}
+
+extern "C" int vg_linear_dgrad(const void* dy, const void* w, int m, int n, int k, int dtype, void* dx, vg_stream_t stream) {
+  VG_CHECK_ARG(dy && w && dx && m >= 0 && n > 0 && k > 0, "bad args");
+  if (m == 0) return VG_OK;
+  cudaStream_t s = as_stream(stream);
+  // dx[m][k] = dy[m][n] w[n][k]: I=m, J=k, L=n
+  if (dtype == VG_BF16)
+    return launch_gemm<float, __nv_bfloat16>((const float*)dy, n, 1, (const __nv_bfloat16*)w, k, 1, m, k, n, (float*)dx, 0, 1, s);
+  return launch_gemm<float, float>((const float*)dy, n, 1, (const float*)w, k, 1, m, k, n, (float*)dx, 0, 1, s);
+}
+
+extern "C" int vg_linear_wgrad(const void* x, const void* dy, int m, int n, int k, int dtype, float* dw, float* dbias,
+                               vg_stream_t stream) {
+  (void)dtype;
+  VG_CHECK_ARG(x && dy && dw && m >= 0 && n > 0 && k > 0, "bad args");
+  if (m == 0) return VG_OK;
+  cudaStream_t s = as_stream(stream);
+  // dw[n][k] += dy^T x : I=n, J=k, L=m ; A(i,l) = dy[l*n + i], B(l,j) = x[l*k + j]
+  int rc = launch_gemm<float, float>((const float*)dy, 1, n, (const float*)x, k, 1, n, k, m, dw, 1, 1, s);
+  if (rc) return rc;
+  if (dbias != nullptr) {
+    colsum_f32_kernel<<<(n + 127) / 128, 128, 0, s>>>((const float*)dy, m, n, dbias);
+    VG_LAUNCHED();
+  }
+  return VG_OK;
+}
+
+extern "C" int vg_avgpool_flatten_forward(const void* x, int n, int h, int w, int c, int k, int dtype, void* out, vg_stream_t stream) {
+  VG_CHECK_ARG(x && out && n >= 0 && h > 0 && w > 0 && c > 0 && k > 0, "bad args");
+  long long total = (long long)n * (h / k) * (w / k) * c;
+  if (total == 0) return VG_OK;
+  if (dtype == VG_BF16)
+    avgpool_flatten_fwd_kernel<__nv_bfloat16><<<ew_grid(total, 1), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, n, h, w, c, k, (float*)out);
+  else
+    avgpool_flatten_fwd_kernel<float><<<ew_grid(total, 1), 256, 0, as_stream(stream)>>>((const float*)x, n, h, w, c, k, (float*)out);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_avgpool_flatten_backward(const void* dout, int n, int h, int w, int c, int k, int dtype, void* dx, vg_stream_t stream) {
+  VG_CHECK_ARG(dout && dx && n >= 0 && h > 0 && w > 0 && c > 0 && k > 0, "bad args");
+  long long total = (long long)n * h * w * c;
+  if (total == 0) return VG_OK;
+  if (dtype == VG_BF16)
+    avgpool_flatten_bwd_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, as_stream(stream)>>>((const float*)dout, n, h, w, c, k, (__nv_bfloat16*)dx);
+  else
+    avgpool_flatten_bwd_kernel<float><<<ew_grid(total), 256, 0, as_stream(stream)>>>((const float*)dout, n, h, w, c, k, (float*)dx);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_spectral_norm_sigma(const float* w_orig, int rows, int cols, float* u, float* v, int training, float eps,
+                                      float* sigma, float* workspace, vg_stream_t stream) {
+  VG_CHECK_ARG(w_orig && u && v && sigma && workspace && rows > 0 && cols > 0, "bad args");
+  cudaStream_t s = as_stream(stream);
+  float* t = workspace;            // [cols]
+  float* sv = workspace + cols;    // [rows]
+  if (training) {
+    VG_CUDA(cudaMemsetAsync(t, 0, (size_t)cols * sizeof(float), s));
+    int slices = std::max(1, std::min(rows / 32, 16));
+    int rps = (int)cdiv(rows, slices);
+    dim3 g1((unsigned)cdiv(cols, 128), (unsigned)cdiv(rows, rps));
+    sn_wt_u_kernel<<<g1, 128, 0, s>>>(w_orig, u, rows, cols, rps, t);
+    VG_LAUNCHED();
+    sn_w_v_kernel<<<(unsigned)cdiv((long long)rows * 32, 256), 256, 0, s>>>(w_orig, t, rows, cols, 1, eps, v, sv);
+    VG_LAUNCHED();
+  } else {
+    sn_w_v_kernel<<<(unsigned)cdiv((long long)rows * 32, 256), 256, 0, s>>>(w_orig, v, rows, cols, 0, eps, nullptr, sv);
+    VG_LAUNCHED();
+  }
+  sn_finish_kernel<<<1, 256, 0, s>>>(sv, u, rows, training, eps, sigma);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_spectral_norm_backward(const float* dw_hat, const float* w_orig, const float* u, const float* v,
+                                         const float* sigma, int rows, int cols, float* dw_orig, float* workspace,
+                                         vg_stream_t stream) {
+  VG_CHECK_ARG(dw_hat && w_orig && u && v && sigma && dw_orig && workspace && rows > 0 && cols > 0, "bad args");
+  cudaStream_t s = as_stream(stream);
+  long long n = (long long)rows * cols;
+  VG_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float), s));
+  sn_bwd_dot_kernel<<<ew_grid(n), 256, 0, s>>>(dw_hat, w_orig, n, workspace);
+  VG_LAUNCHED();
+  sn_bwd_apply_kernel<<<ew_grid(n), 256, 0, s>>>(dw_hat, u, v, sigma, workspace, rows, cols, dw_orig);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_reparam_forward(const float* mu, const float* lv_raw, const float* eps, long long n, int training, int z_dtype,
+                                  void* z, float* lv_clamped, vg_stream_t stream) {
+  VG_CHECK_ARG(mu && lv_raw && z && lv_clamped && n >= 0 && (!training || eps), "bad args");
+  if (n == 0) return VG_OK;
+  if (z_dtype == VG_BF16)
+    reparam_fwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, as_stream(stream)>>>(mu, lv_raw, eps, n, training, (__nv_bfloat16*)z, lv_clamped);
+  else
+    reparam_fwd_kernel<float><<<ew_grid(n), 256, 0, as_stream(stream)>>>(mu, lv_raw, eps, n, training, (float*)z, lv_clamped);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_reparam_backward(const void* dz, const float* lv_raw, const float* eps, long long n, int training, int z_dtype,
+                                   float* d_mu, float* d_lv_raw, vg_stream_t stream) {
+  VG_CHECK_ARG(dz && lv_raw && d_mu && d_lv_raw && n >= 0 && (!training || eps), "bad args");
+  if (n == 0) return VG_OK;
+  if (z_dtype == VG_BF16)
+    reparam_bwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dz, lv_raw, eps, n, training, d_mu, d_lv_raw);
+  else
+    reparam_bwd_kernel<float><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const float*)dz, lv_raw, eps, n, training, d_mu, d_lv_raw);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_generator_loss(const void* xhat, const float* x, const float* mu, const float* lv, const float* logits,
+                                 const VgLossDesc* d, void* d_xhat, float* d_mu, float* d_lv, float* d_logits, double* losses,
+                                 vg_stream_t stream) {
+  VG_CHECK_ARG(d && xhat && x && mu && lv && d_xhat && d_mu && d_lv && losses, "null pointer");
+  VG_CHECK_ARG(d->n_logits == 0 || (logits && d_logits), "logits missing");
+  VG_CHECK_ARG(d->n_pix_global > 0 && (d->n_logits == 0 || d->n_logits_global > 0), "global counts must be positive");
+  long long work = std::max(d->n_pix, d->n_lat);
+  int grid = ew_grid(work, 8);
+  VgLossDesc dd = *d;
+  if (dd.n_logits_global <= 0) dd.n_logits_global = 1;
+  if (d->xhat_dtype == VG_BF16)
+    generator_loss_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)xhat, x, mu, lv, logits, dd,
+                                                                               (__nv_bfloat16*)d_xhat, d_mu, d_lv, d_logits, losses);
+  else
+    generator_loss_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)xhat, x, mu, lv, logits, dd, (float*)d_xhat, d_mu, d_lv,
+                                                                       d_logits, losses);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_discriminator_loss(const float* d_real, const float* d_fake, int n, int n_global, int adv_mode, float* g_real,
+                                     float* g_fake, double* losses, vg_stream_t stream) {
+  VG_CHECK_ARG(d_real && d_fake && g_real && g_fake && losses && n >= 0 && n_global > 0, "bad args");
+  discriminator_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(d_real, d_fake, n, n_global, adv_mode, g_real, g_fake, losses);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_optimizer_step(float* p, const float* g, float* m, float* v, long long n, const VgOptDesc* d, vg_stream_t stream) {
+  VG_CHECK_ARG(p && g && v && d && n >= 0, "null pointer");
+  VG_CHECK_ARG(d->kind == 0 || d->kind == 1, "unknown optimizer kind %d", d->kind);
+  VG_CHECK_ARG(d->kind != 0 || (m != nullptr && d->bias_corr1 > 0.f && d->bias_corr2 > 0.f), "Adam needs m and bias corrections");
+  if (n == 0) return VG_OK;
+  bool al = ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)v % 16 == 0) && (!m || (uintptr_t)m % 16 == 0);
+  long long n4 = al ? n / 4 : 0;
+  optimizer_kernel<<<ew_grid(n, 8), 256, 0, as_stream(stream)>>>(p, g, m, v, n4, n, *d);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, vg_stream_t stream) {
+  VG_CHECK_ARG(src && dst && n >= 0, "bad args");
+  if (n == 0) return VG_OK;
+  cudaStream_t s = as_stream(stream);
+  int grid = ew_grid(n);
+  if (src_dtype == VG_F32 && dst_dtype == VG_BF16) cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == VG_BF16 && dst_dtype == VG_F32) cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == VG_F32 && dst_dtype == VG_F32) cast_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src, (float*)dst, n);
+  else if (src_dtype == VG_BF16 && dst_dtype == VG_BF16) cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  else { set_error("bad dtypes %d -> %d", src_dtype, dst_dtype); return VG_EINVAL; }
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_nchw_to_nhwc(const float* src, int n, int c, int h, int w, int dst_dtype, void* dst, vg_stream_t stream) {
+  VG_CHECK_ARG(src && dst && n >= 0 && c > 0 && h > 0 && w > 0, "bad args");
+  if (n == 0) return VG_OK;
+  VG_CHECK_ARG(n <= 65535, "n too large for this helper");
+  dim3 grid((unsigned)cdiv(h * w, 32), (unsigned)cdiv(c, 32), (unsigned)n), block(32, 8);
+  if (dst_dtype == VG_BF16) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>(src, c, h * w, (__nv_bfloat16*)dst);
+  else nchw_to_nhwc_kernel<float><<<grid, block, 0, as_stream(stream)>>>(src, c, h * w, (float*)dst);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_nhwc_to_nchw(const void* src, int src_dtype, int n, int c, int h, int w, float* dst, vg_stream_t stream) {
+  VG_CHECK_ARG(src && dst && n >= 0 && c > 0 && h > 0 && w > 0, "bad args");
+  if (n == 0) return VG_OK;
+  VG_CHECK_ARG(n <= 65535, "n too large for this helper");
+  dim3 grid((unsigned)cdiv(h * w, 32), (unsigned)cdiv(c, 32), (unsigned)n), block(32, 8);
+  if (src_dtype == VG_BF16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, c, h * w, dst);
+  else nhwc_to_nchw_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)src, c, h * w, dst);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_fill_zero(void* p, size_t bytes, vg_stream_t stream) {
+  VG_CHECK_ARG(p || bytes == 0, "null pointer");
+  if (bytes == 0) return VG_OK;
+  VG_CUDA(cudaMemsetAsync(p, 0, bytes, as_stream(stream)));
+  return VG_OK;
+}

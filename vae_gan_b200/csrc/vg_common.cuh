@@ -1,0 +1,135 @@
+// Shared helpers for libvaegan_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/vaegan_b200.h"
+
+namespace vg {
+
+// ---- host-side error plumbing -------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+extern int g_num_sms;
+extern int g_force_simt;
+
+#define VG_CHECK_ARG(cond, ...)                  \
+  do {                                           \
+    if (!(cond)) {                               \
+      vg::set_error(__VA_ARGS__);                \
+      return VG_EINVAL;                          \
+    }                                            \
+  } while (0)
+
+#define VG_CUDA(expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      vg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return VG_ECUDA;                                                                   \
+    }                                                                                    \
+  } while (0)
+
+// call after every kernel launch
+#define VG_LAUNCHED()                                                                    \
+  do {                                                                                   \
+    vg::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+    cudaError_t _e = cudaPeekAtLastError();                                              \
+    if (_e != cudaSuccess) {                                                             \
+      cudaGetLastError();                                                                \
+      vg::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return VG_ECUDA;                                                                   \
+    }                                                                                    \
+  } while (0)
+
+static inline cudaStream_t as_stream(vg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline size_t dtype_size(int dt) { return dt == VG_BF16 ? 2 : 4; }
+static inline int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 8-element vector access (16 B for bf16, 32 B for f32)
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  float v[8];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- Philox4x32-10 (counter-based; restated on the CPU in oracle/vaegan_oracle.py) ---------
+struct Philox {
+  uint32_t k0, k1, c2, c3;
+  __device__ __forceinline__ Philox(unsigned long long seed, unsigned long long offset)
+      : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), c2((uint32_t)offset), c3((uint32_t)(offset >> 32)) {}
+  // 4 words for block index `blk` (= element index / 4)
+  __device__ __forceinline__ uint4 block(unsigned long long blk) const {
+    uint32_t c0 = (uint32_t)blk, c1 = (uint32_t)(blk >> 32), d2 = c2, d3 = c3, a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, d2), lo1 = 0xCD9E8D57u * d2;
+      uint32_t n0 = hi1 ^ c1 ^ a, n2 = hi0 ^ d3 ^ b;
+      c0 = n0; c1 = lo1; d2 = n2; d3 = lo0;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, d2, d3);
+  }
+  __device__ __forceinline__ uint32_t word(unsigned long long idx) const {
+    uint4 r = block(idx >> 2);
+    uint32_t l = (uint32_t)idx & 3u;
+    return l == 0 ? r.x : (l == 1 ? r.y : (l == 2 ? r.z : r.w));
+  }
+};
+__device__ __forceinline__ uint32_t drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+}
+
+}  // namespace vg
