@@ -97,6 +97,9 @@ typedef struct {
   unsigned long long offset;    /* Philox stream id (one per dropout site and step) */
   long long sample_offset;      /* global index of local sample 0 (partition invariance) */
   int training;                 /* 1: batch statistics; 0: running statistics (eval) */
+  /* Optional DEVICE step counter: effective Philox stream = offset + 65536 * (*step_ptr).
+   * Lets a captured CUDA graph draw fresh masks on every replay. */
+  const unsigned long long* step_ptr;
 } VgBnDesc;
 
 /* sums[0..c) += sum_x, sums[c..2c) += sum_x^2 over rows (double, caller zeroes). */
@@ -143,19 +146,24 @@ int vg_add(const void* a, const void* b, long long n, int dtype, void* out, vg_s
 int vg_dropout_mask(const VgBnDesc* d, uint8_t* mask, vg_stream_t stream);
 /* Dropout2d scale per (n, c): 0 or 1/(1-p); index = (sample_offset + n)*c + ch */
 int vg_dropout2d_scale(float* scale, int n, int c, float p, unsigned long long seed,
-                       unsigned long long offset, long long sample_offset, vg_stream_t stream);
+                       unsigned long long offset, const unsigned long long* step_ptr,
+                       long long sample_offset, vg_stream_t stream);
 /* standard normal noise, element i uses Philox index start+i */
 int vg_philox_normal(float* out, long long n, unsigned long long seed, unsigned long long offset,
-                     long long start, vg_stream_t stream);
+                     const unsigned long long* step_ptr, long long start, vg_stream_t stream);
+/* *counter += inc (device-side step counter used by the step_ptr arguments) */
+int vg_counter_add(unsigned long long* counter, unsigned long long inc, vg_stream_t stream);
 
 /* ---- avg_pool2d(k) + flatten in NCHW order (README.md:471-473) -------------------------- */
+/* x / dx are NHWC in `dtype`; the pooled, flattened features (out / dout) are fp32 */
 int vg_avgpool_flatten_forward(const void* x, int n, int h, int w, int c, int k, int dtype,
                                void* out, vg_stream_t stream);
 int vg_avgpool_flatten_backward(const void* dout, int n, int h, int w, int c, int k, int dtype,
                                 void* dx, vg_stream_t stream);
 
 /* ---- nn.Linear (+LeakyReLU 0.2) README.md:458-461,474-483 ------------------------------- */
-/* y[m][n] = lrelu(x[m][k] . w[n][k]^T + bias[n]); x,y,w in `dtype`, bias fp32; slope 1 = none */
+/* y[m][n] = lrelu(x[m][k] . w[n][k]^T + bias[n]).  The head's activations (x, y, dy, dx) are
+ * fp32 (they are tiny); only the weight w is stored in `dtype`.  slope 1 = no activation. */
 int vg_linear_forward(const void* x, const void* w, const float* bias, int m, int n, int k,
                       int dtype, float slope, void* y, vg_stream_t stream);
 int vg_linear_dgrad(const void* dy, const void* w, int m, int n, int k, int dtype, void* dx,
@@ -179,9 +187,11 @@ int vg_spectral_norm_backward(const float* dw_hat, const float* w_orig, const fl
 /* lv = clamp(lv_raw, -50, 50); z = mu + exp(0.5 lv) * eps (training) or mu (eval). z in z_dtype */
 int vg_reparam_forward(const float* mu, const float* lv_raw, const float* eps, long long n,
                        int training, int z_dtype, void* z, float* lv_clamped, vg_stream_t stream);
-/* d_mu = dz ; d_lv_raw = dz * 0.5*exp(0.5 lv)*eps inside the clamp, 0 outside */
-int vg_reparam_backward(const void* dz, const float* lv_raw, const float* eps, long long n,
-                        int training, int z_dtype, float* d_mu, float* d_lv_raw, vg_stream_t stream);
+/* d_mu = dz ; d_lv_raw = (dz * 0.5*exp(0.5 lv)*eps + dlv_in) inside the clamp, 0 outside.
+ * dlv_in (nullable): gradient arriving on the clamped log_var output (e.g. the KL term). */
+int vg_reparam_backward(const void* dz, const float* lv_raw, const float* eps, const float* dlv_in,
+                        long long n, int training, int z_dtype, float* d_mu, float* d_lv_raw,
+                        vg_stream_t stream);
 
 /* ---- fused generator loss + gradients (README.md:816-831) ------------------------------- */
 typedef struct {
@@ -213,8 +223,10 @@ typedef struct {
   float clamp;            /* > 0: clamp params to +-clamp after the update (README.md:805) */
   float grad_scale;       /* multiplies the gradient first (1/world_size after allreduce-sum) */
 } VgOptDesc;
+/* step_ptr (nullable, device): when given, Adam's bias corrections are computed on the device
+ * as 1 - beta^(*step_ptr) instead of taken from the descriptor (CUDA-graph replay). */
 int vg_optimizer_step(float* p, const float* g, float* m, float* v, long long n,
-                      const VgOptDesc* d, vg_stream_t stream);
+                      const VgOptDesc* d, const unsigned long long* step_ptr, vg_stream_t stream);
 
 /* ---- layout / dtype helpers at the module boundary --------------------------------------- */
 int vg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, vg_stream_t stream);

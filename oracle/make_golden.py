@@ -96,18 +96,35 @@ def d_blocks(D):
     return out
 
 
-def rand_masks_g(spec_g, B, S, gen):
+PHILOX_SEED = 0x5EED5EED     # = vae_gan_b200.functional.rng default seed
+
+
+def philox_mask_nchw(shape, offset, p=0.5, seed=PHILOX_SEED):
+    """Keep-mask a vae_gan_b200 dropout site (Philox stream `offset`) draws for an activation of
+    logical shape (N,C,H,W): the kernels index elements in NHWC order."""
+    n, c, h, w = shape
+    m = O.philox_keep_mask(n * h * w * c, seed, offset, p).reshape(n, h, w, c)
+    return torch.from_numpy(m).permute(0, 3, 1, 2).contiguous()
+
+
+def philox_keep2d(n, c, offset, p=0.5, seed=PHILOX_SEED):
+    sc = O.philox_keep_scale2d(n, c, seed, offset, p)
+    return torch.from_numpy((sc > 0).astype(np.uint8)).reshape(n, c, 1, 1)
+
+
+def rand_masks_g(spec_g, B, S, gen, first_site=0):
+    """Masks for the generator's dropout sites; site ids follow forward order (0,1,2,...)."""
     masks = {}
     h = S
-    for pre, cin, cout, mode in spec_g.encoder_blocks() + spec_g.decoder_blocks():
-        masks[pre] = (torch.rand(B, cin, h, h, generator=gen) >= 0.5).to(torch.uint8)
+    for i, (pre, cin, cout, mode) in enumerate(spec_g.encoder_blocks() + spec_g.decoder_blocks()):
+        masks[pre] = philox_mask_nchw((B, cin, h, h), first_site + i)
         h = h // 2 if mode == "downsample" else (h * 2 if mode == "upsample" else h)
     return masks
 
 
-def rand_masks_d(spec_d, B, gen):
-    return {pre: (torch.rand(B, cout, 1, 1, generator=gen) >= 0.5).to(torch.uint8)
-            for pre, cin, cout, st in spec_d.res_blocks()}
+def rand_masks_d(spec_d, B, gen, first_site=0):
+    return {pre: philox_keep2d(B, cout, first_site + i)
+            for i, (pre, cin, cout, st) in enumerate(spec_d.res_blocks())}
 
 
 def main():
@@ -143,7 +160,7 @@ def main():
     loss.backward()
     sd_after = G.state_dict()
     torch.save(dict(
-        spec=dict(depth=2, length=1, feature_size=fs), seed_g=11, B=B, S=S,
+        spec=dict(depth=2, length=1, feature_size=fs), seed_g=11, B=B, S=S, philox_seed=PHILOX_SEED,
         bn_perturb_seed=20240611, x=x, eps=eps, masks=gm,
         params={k: v.clone() for k, v in Pg.items() if "bn" in k or "shortcut.1" in k or k.endswith(".bias")},
         y=y.detach(), mu=mu.detach(), log_var=lv.detach(), loss=loss.detach(),
@@ -194,7 +211,7 @@ def main():
             xi = torch.randn(3, 6, 8, 8, generator=gen).requires_grad_(True)
             c_mask = 6 if res_mode == "pre-activation" else 10
             hm = 8 if (res_mode == "pre-activation" or mode == "level") else (4 if mode == "downsample" else 16)
-            keep = (torch.rand(3, c_mask, hm, hm, generator=gen) >= 0.5).to(torch.uint8)
+            keep = philox_mask_nchw((3, c_mask, hm, hm), 0)
             blk.dropout = MaskSeq([keep])
             blk.train()
             out = blk(xi)
@@ -214,7 +231,7 @@ def main():
                     m.bias.data.uniform_(-0.3, 0.3)
             sd0 = {k: v.clone() for k, v in blk.state_dict().items()}
             xi = torch.randn(3, cin, 8, 8, generator=gen).requires_grad_(True)
-            keep = (torch.rand(3, cout, 1, 1, generator=gen) >= 0.5).to(torch.uint8)
+            keep = philox_keep2d(3, cout, 0)
             blk.dropout = MaskSeq([keep])
             blk.train()
             out = blk(xi)

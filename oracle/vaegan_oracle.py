@@ -537,26 +537,47 @@ def philox4x32_10(counter, key):
     return c
 
 
+def _philox_blocks(blk, seed: int, offset: int):
+    import numpy as np
+
+    n = blk.shape[0]
+    ctr = [(blk & np.uint64(0xFFFFFFFF)).astype(np.uint32), (blk >> np.uint64(32)).astype(np.uint32),
+           np.full(n, offset & 0xFFFFFFFF, dtype=np.uint32),
+           np.full(n, (offset >> 32) & 0xFFFFFFFF, dtype=np.uint32)]
+    key = (np.full(n, seed & 0xFFFFFFFF, dtype=np.uint32),
+           np.full(n, (seed >> 32) & 0xFFFFFFFF, dtype=np.uint32))
+    return np.stack(philox4x32_10(ctr, key), axis=1)        # [n][4]
+
+
 def philox_uint32(n_elems: int, seed: int, offset: int, start: int = 0):
-    """uint32 word for each linear element index in [start, start+n_elems)."""
+    """32-bit word per linear element index e in [start, start+n): block e>>2, word e&3
+    (used by the Dropout2d per-(n,c) scale)."""
     import numpy as np
 
     idx = np.arange(start, start + n_elems, dtype=np.uint64)
-    blk = idx >> np.uint64(2)
-    lane = (idx & np.uint64(3)).astype(np.int64)
-    ctr = [(blk & np.uint64(0xFFFFFFFF)).astype(np.uint32), (blk >> np.uint64(32)).astype(np.uint32),
-           np.full(n_elems, offset & 0xFFFFFFFF, dtype=np.uint32),
-           np.full(n_elems, (offset >> 32) & 0xFFFFFFFF, dtype=np.uint32)]
-    key = (np.full(n_elems, seed & 0xFFFFFFFF, dtype=np.uint32),
-           np.full(n_elems, (seed >> 32) & 0xFFFFFFFF, dtype=np.uint32))
-    out = philox4x32_10(ctr, key)
-    words = np.stack(out, axis=1)
-    return words[np.arange(n_elems), lane]
+    words = _philox_blocks(idx >> np.uint64(2), seed, offset)
+    return words[np.arange(n_elems), (idx & np.uint64(3)).astype(np.int64)]
 
 
 def philox_keep_mask(n_elems: int, seed: int, offset: int, p: float, start: int = 0):
-    """Bernoulli(1-p) keep mask as uint8, identical to the CUDA dropout kernels."""
+    """Elementwise-dropout keep mask (uint8), identical to the CUDA kernels: element e uses the
+    16-bit half-word (e & 7) of Philox block (e >> 3); keep iff half-word >= floor(p * 65536)."""
     import numpy as np
 
-    thr = np.uint32(min(int(p * 4294967296.0), 0xFFFFFFFF))
-    return (philox_uint32(n_elems, seed, offset, start) >= thr).astype(np.uint8)
+    idx = np.arange(start, start + n_elems, dtype=np.uint64)
+    words = _philox_blocks(idx >> np.uint64(3), seed, offset)
+    j = (idx & np.uint64(7)).astype(np.int64)
+    w = words[np.arange(n_elems), j >> 1]
+    h = np.where((j & 1) == 1, w >> np.uint32(16), w & np.uint32(0xFFFF))
+    thr = min(int(float(np.float32(p)) * 65536.0), 65535)
+    return (h >= np.uint32(thr)).astype(np.uint8)
+
+
+def philox_keep_scale2d(n: int, c: int, seed: int, offset: int, p: float, sample_offset: int = 0):
+    """Dropout2d scale per (n, c): 0 or 1/(1-p); keep iff word >= floor(p * 2^32)."""
+    import numpy as np
+
+    w = philox_uint32(n * c, seed, offset, start=sample_offset * c)
+    thr = min(int(float(np.float32(p)) * 4294967296.0), 0xFFFFFFFF)
+    keep = (w >= np.uint32(thr)) if p > 0 else np.ones(n * c, dtype=bool)
+    return (keep.astype(np.float32) / np.float32(1.0 - p)).reshape(n, c)

@@ -1,0 +1,11 @@
+"""vae_gan_b200 - B200-native (sm_100a) VAE-GAN training step behind the reference notebook's
+nn.Module surface.  See DESIGN.md / INTEGRATION.md."""
+from . import functional
+from .functional import compute_dtype, config, rng
+from .modules import (Decoder, Discriminator, Encoder, ResBlockDiscriminator, ResBlockVAE,
+                      SpatialVAECodeProcessor, UnsupervisedGeneratorNetwork, build_vae_gan, init_weights)
+from .train import VaeGanTrainer
+
+__all__ = ["ResBlockVAE", "Encoder", "Decoder", "ResBlockDiscriminator", "Discriminator",
+           "SpatialVAECodeProcessor", "UnsupervisedGeneratorNetwork", "init_weights", "build_vae_gan",
+           "VaeGanTrainer", "functional", "compute_dtype", "config", "rng"]

@@ -1,0 +1,151 @@
+"""ctypes binding of libvaegan_sm100.so (include/vaegan_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, we raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libvaegan_sm100.so"
+
+VG_F32, VG_BF16 = 0, 1
+
+c_vp, c_int, c_ll, c_ull, c_f, c_d = C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.c_float, C.c_double
+
+
+class VgConvDesc(C.Structure):
+    _fields_ = [(n, c_int) for n in ("n", "h_in", "w_in", "c_in", "h_out", "w_out", "c_out", "kh", "kw",
+                                     "stride", "pad", "transposed", "act_dtype", "out_dtype")]
+
+
+class VgBnDesc(C.Structure):
+    _fields_ = [("rows", c_ll), ("c", c_int), ("hw", c_int), ("dtype", c_int), ("slope", c_f),
+                ("drop_p", c_f), ("seed", c_ull), ("offset", c_ull), ("sample_offset", c_ll),
+                ("training", c_int), ("step_ptr", c_vp)]
+
+
+class VgLossDesc(C.Structure):
+    _fields_ = [("n_pix", c_ll), ("n_pix_global", c_ll), ("n_lat", c_ll), ("n_logits", c_int),
+                ("n_logits_global", c_int), ("adv_mode", c_int), ("w_adv", c_f), ("w_recon", c_f),
+                ("w_kl", c_f), ("xhat_dtype", c_int)]
+
+
+class VgOptDesc(C.Structure):
+    _fields_ = [("kind", c_int), ("lr", c_f), ("beta1", c_f), ("beta2", c_f), ("alpha", c_f), ("eps", c_f),
+                ("weight_decay", c_f), ("bias_corr1", c_f), ("bias_corr2", c_f), ("clamp", c_f),
+                ("grad_scale", c_f)]
+
+
+_PROTOS = {
+    "vg_version": (c_int, []),
+    "vg_init": (c_int, [c_int]),
+    "vg_last_error": (C.c_char_p, []),
+    "vg_launch_count": (c_ull, []),
+    "vg_set_force_simt": (c_int, [c_int]),
+    "vg_conv_pack_weights": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vg_conv_forward": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vg_conv_dgrad": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vg_conv_wgrad": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vg_bn_stats": (c_int, [c_vp, C.POINTER(VgBnDesc), c_vp, c_vp]),
+    "vg_bn_finalize": (c_int, [c_vp, c_d, c_int, c_f, c_f, c_vp, c_vp, c_vp, c_vp]),
+    "vg_bn_eval_stats": (c_int, [c_vp, c_vp, c_int, c_f, c_vp, c_vp]),
+    "vg_bn_act_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, C.POINTER(VgBnDesc), c_vp, c_vp]),
+    "vg_bn_act_backward_reduce": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(VgBnDesc), c_vp, c_vp]),
+    "vg_bn_act_backward_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, C.POINTER(VgBnDesc), c_vp, c_vp, c_vp, c_vp]),
+    "vg_bn_param_grads": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp]),
+    "vg_bn_add_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(VgBnDesc), c_vp, c_vp, c_vp]),
+    "vg_lrelu_backward": (c_int, [c_vp, c_vp, c_ll, c_int, c_f, c_vp, c_vp]),
+    "vg_add": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_vp]),
+    "vg_dropout_mask": (c_int, [C.POINTER(VgBnDesc), c_vp, c_vp]),
+    "vg_dropout2d_scale": (c_int, [c_vp, c_int, c_int, c_f, c_ull, c_ull, c_vp, c_ll, c_vp]),
+    "vg_philox_normal": (c_int, [c_vp, c_ll, c_ull, c_ull, c_vp, c_ll, c_vp]),
+    "vg_counter_add": (c_int, [c_vp, c_ull, c_vp]),
+    "vg_avgpool_flatten_forward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "vg_avgpool_flatten_backward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "vg_linear_forward": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_vp, c_vp]),
+    "vg_linear_dgrad": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "vg_linear_wgrad": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "vg_spectral_norm_sigma": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_f, c_vp, c_vp, c_vp]),
+    "vg_spectral_norm_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    "vg_reparam_forward": (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp]),
+    "vg_reparam_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp]),
+    "vg_generator_loss": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(VgLossDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vg_discriminator_loss": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "vg_optimizer_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, C.POINTER(VgOptDesc), c_vp, c_vp]),
+    "vg_cast": (c_int, [c_vp, c_int, c_vp, c_int, c_ll, c_vp]),
+    "vg_nchw_to_nhwc": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "vg_nhwc_to_nchw": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "vg_fill_zero": (c_int, [c_vp, C.c_size_t, c_vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+_lib = None
+_inited_devices = set()
+
+
+class VgError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree shared library (no compute).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise VgError(
+            f"{LIB_PATH} not found: build it with `python -m vae_gan_b200.build` (or "
+            "`__graft_entry__.build()`).  There is no CPU / library fallback for this path.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ensure_device(device: torch.device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _inited_devices:
+        lib = load()
+        rc = lib.vg_init(idx)
+        if rc != 0:
+            raise VgError(f"vg_init({idx}) failed ({rc}): {lib.vg_last_error().decode()}")
+        _inited_devices.add(idx)
+
+
+def call(name: str, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise VgError(f"{name} failed ({rc}): {lib.vg_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(load().vg_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def vg_dtype(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return VG_F32
+    if dt == torch.bfloat16:
+        return VG_BF16
+    raise VgError(f"unsupported dtype {dt}")

@@ -193,17 +193,21 @@ struct BnK {
   float slope, drop_scale;
   uint32_t thr16;
   unsigned long long seed, offset;
+  const unsigned long long* step_ptr;
   long long sample_offset;
   int training;
   bool fold;
 };
+__device__ __forceinline__ unsigned long long eff_offset(unsigned long long offset, const unsigned long long* step_ptr) {
+  return step_ptr ? offset + 65536ull * (*step_ptr) : offset;
+}
 
 static inline BnK make_bnk(const VgBnDesc* d) {
   BnK k;
   k.rows = d->rows; k.c = d->c; k.hw = d->hw; k.slope = d->slope;
   k.drop_scale = d->drop_p > 0.f ? 1.0f / (1.0f - d->drop_p) : 1.0f;
   k.thr16 = d->drop_p > 0.f ? thr16_of(d->drop_p) : 0u;
-  k.seed = d->seed; k.offset = d->offset; k.sample_offset = d->sample_offset; k.training = d->training;
+  k.seed = d->seed; k.offset = d->offset; k.step_ptr = d->step_ptr; k.sample_offset = d->sample_offset; k.training = d->training;
   k.fold = false;
   return k;
 }
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_act_fwd_vec_kernel(const T* __r
     a[j] = aa;
     b[j] = beta[ch] - mean_rstd[ch] * aa;
   }
-  Philox ph(k.seed, k.offset);
+  Philox ph(k.seed, eff_offset(k.offset, k.step_ptr));
   const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
   const long long stride = (long long)gridDim.x * m.rpb;
   long long row = (long long)blockIdx.x * m.rpb + r0;
@@ -262,7 +266,7 @@ template <typename T>
 __global__ void bn_act_fwd_scalar_kernel(const T* __restrict__ x, const float* __restrict__ mean_rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, BnK k,
                                          T* __restrict__ y) {
-  Philox ph(k.seed, k.offset);
+  Philox ph(k.seed, eff_offset(k.offset, k.step_ptr));
   const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
   const long long total = k.rows * k.c;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_act_bwd_vec_kernel(const T* __r
         }
       }
     }
-    Philox ph(k.seed, k.offset);
+    Philox ph(k.seed, eff_offset(k.offset, k.step_ptr));
     const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
     const long long stride = (long long)gridDim.x * m.rpb;
     long long row = (long long)blockIdx.x * m.rpb + r0;
@@ -393,7 +397,7 @@ __global__ void bn_act_bwd_scalar_kernel(const T* __restrict__ dy, const T* __re
     for (int i = threadIdx.x; i < 2 * k.c; i += blockDim.x) dsm[i] = 0.0;
     __syncthreads();
   }
-  Philox ph(k.seed, k.offset);
+  Philox ph(k.seed, eff_offset(k.offset, k.step_ptr));
   const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
   const long long total = k.rows * k.c;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -541,7 +545,7 @@ __global__ void add_vec_kernel(const T* __restrict__ a, const T* __restrict__ b,
 }
 
 __global__ void dropout_mask_kernel(BnK k, uint8_t* __restrict__ mask) {
-  Philox ph(k.seed, k.offset);
+  Philox ph(k.seed, eff_offset(k.offset, k.step_ptr));
   const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
   const long long total = k.rows * k.c;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
@@ -549,8 +553,8 @@ __global__ void dropout_mask_kernel(BnK k, uint8_t* __restrict__ mask) {
 }
 
 __global__ void dropout2d_scale_kernel(float* __restrict__ scale, long long total, int c, float p, unsigned long long seed,
-                                       unsigned long long offset, long long sample_offset) {
-  Philox ph(seed, offset);
+                                       unsigned long long offset, const unsigned long long* step_ptr, long long sample_offset) {
+  Philox ph(seed, eff_offset(offset, step_ptr));
   uint32_t thr = drop_threshold(p);
   float sc = 1.0f / (1.0f - p);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -560,8 +564,8 @@ __global__ void dropout2d_scale_kernel(float* __restrict__ scale, long long tota
 }
 
 __global__ void philox_normal_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
-                                     long long start) {
-  Philox ph(seed, offset);
+                                     const unsigned long long* step_ptr, long long start) {
+  Philox ph(seed, eff_offset(offset, step_ptr));
   const long long nblk = (n + 3) / 4;
   for (long long bidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; bidx < nblk; bidx += (long long)gridDim.x * blockDim.x) {
     // element e = start + 4*bidx + l uses block (e >> 2) only when start % 4 == 0 (enforced by the host)
@@ -849,23 +853,32 @@ extern "C" int vg_dropout_mask(const VgBnDesc* d, uint8_t* mask, vg_stream_t str
 }
 
 extern "C" int vg_dropout2d_scale(float* scale, int n, int c, float p, unsigned long long seed, unsigned long long offset,
-                                  long long sample_offset, vg_stream_t stream) {
+                                  const unsigned long long* step_ptr, long long sample_offset, vg_stream_t stream) {
   VG_CHECK_ARG(scale && n >= 0 && c > 0 && p >= 0.f && p < 1.f, "bad args");
   long long total = (long long)n * c;
   if (total == 0) return VG_OK;
   int grid = (int)std::min<long long>(cdiv(total, 256), (long long)num_sms() * 4);
-  dropout2d_scale_kernel<<<grid, 256, 0, as_stream(stream)>>>(scale, total, c, p, seed, offset, sample_offset);
+  dropout2d_scale_kernel<<<grid, 256, 0, as_stream(stream)>>>(scale, total, c, p, seed, offset, step_ptr, sample_offset);
   VG_LAUNCHED();
   return VG_OK;
 }
 
-extern "C" int vg_philox_normal(float* out, long long n, unsigned long long seed, unsigned long long offset, long long start,
-                                vg_stream_t stream) {
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+
+extern "C" int vg_counter_add(unsigned long long* counter, unsigned long long inc, vg_stream_t stream) {
+  VG_CHECK_ARG(counter, "null pointer");
+  counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, inc);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_philox_normal(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                                const unsigned long long* step_ptr, long long start, vg_stream_t stream) {
   VG_CHECK_ARG(out && n >= 0 && start >= 0 && start % 4 == 0, "bad args (start must be a multiple of 4)");
   if (n == 0) return VG_OK;
   long long nblk = (n + 3) / 4;
   int grid = (int)std::min<long long>(cdiv(nblk, 256), (long long)num_sms() * 8);
-  philox_normal_kernel<<<grid, 256, 0, as_stream(stream)>>>(out, n, seed, offset, start);
+  philox_normal_kernel<<<grid, 256, 0, as_stream(stream)>>>(out, n, seed, offset, step_ptr, start);
   VG_LAUNCHED();
   return VG_OK;
 }

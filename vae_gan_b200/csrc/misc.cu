@@ -240,13 +240,17 @@ __global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __
 }
 template <typename T>
 __global__ void reparam_bwd_kernel(const T* __restrict__ dz, const float* __restrict__ lv_raw, const float* __restrict__ eps,
-                                   long long n, int training, float* __restrict__ d_mu, float* __restrict__ d_lv) {
+                                   const float* __restrict__ dlv_in, long long n, int training, float* __restrict__ d_mu,
+                                   float* __restrict__ d_lv) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float g = to_f32(dz[i]);
     d_mu[i] = g;
     float raw = lv_raw[i];
     float r = 0.f;
-    if (training && raw >= -50.f && raw <= 50.f) r = g * 0.5f * expf(0.5f * raw) * eps[i];
+    if (raw >= -50.f && raw <= 50.f) {
+      if (training) r = g * 0.5f * expf(0.5f * raw) * eps[i];
+      if (dlv_in != nullptr) r += dlv_in[i];
+    }
     d_lv[i] = r;
   }
 }
@@ -345,7 +349,13 @@ __global__ void discriminator_loss_kernel(const float* __restrict__ d_real, cons
 // fused optimizer
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) optimizer_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                         float* __restrict__ v, long long n4, long long n, VgOptDesc d) {
+                                                         float* __restrict__ v, long long n4, long long n, VgOptDesc d,
+                                                         const unsigned long long* __restrict__ step_ptr) {
+  if (step_ptr != nullptr && d.kind == 0) {
+    const float t = (float)(*step_ptr);
+    d.bias_corr1 = 1.f - powf(d.beta1, t);
+    d.bias_corr2 = 1.f - powf(d.beta2, t);
+  }
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     gg *= d.grad_scale;
     if (d.weight_decay != 0.f) gg = fmaf(d.weight_decay, pp, gg);
@@ -563,14 +573,14 @@ extern "C" int vg_reparam_forward(const float* mu, const float* lv_raw, const fl
   return VG_OK;
 }
 
-extern "C" int vg_reparam_backward(const void* dz, const float* lv_raw, const float* eps, long long n, int training, int z_dtype,
-                                   float* d_mu, float* d_lv_raw, vg_stream_t stream) {
+extern "C" int vg_reparam_backward(const void* dz, const float* lv_raw, const float* eps, const float* dlv_in, long long n,
+                                   int training, int z_dtype, float* d_mu, float* d_lv_raw, vg_stream_t stream) {
   VG_CHECK_ARG(dz && lv_raw && d_mu && d_lv_raw && n >= 0 && (!training || eps), "bad args");
   if (n == 0) return VG_OK;
   if (z_dtype == VG_BF16)
-    reparam_bwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dz, lv_raw, eps, n, training, d_mu, d_lv_raw);
+    reparam_bwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dz, lv_raw, eps, dlv_in, n, training, d_mu, d_lv_raw);
   else
-    reparam_bwd_kernel<float><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const float*)dz, lv_raw, eps, n, training, d_mu, d_lv_raw);
+    reparam_bwd_kernel<float><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const float*)dz, lv_raw, eps, dlv_in, n, training, d_mu, d_lv_raw);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -603,14 +613,15 @@ extern "C" int vg_discriminator_loss(const float* d_real, const float* d_fake, i
   return VG_OK;
 }
 
-extern "C" int vg_optimizer_step(float* p, const float* g, float* m, float* v, long long n, const VgOptDesc* d, vg_stream_t stream) {
+extern "C" int vg_optimizer_step(float* p, const float* g, float* m, float* v, long long n, const VgOptDesc* d,
+                                 const unsigned long long* step_ptr, vg_stream_t stream) {
   VG_CHECK_ARG(p && g && v && d && n >= 0, "null pointer");
   VG_CHECK_ARG(d->kind == 0 || d->kind == 1, "unknown optimizer kind %d", d->kind);
-  VG_CHECK_ARG(d->kind != 0 || (m != nullptr && d->bias_corr1 > 0.f && d->bias_corr2 > 0.f), "Adam needs m and bias corrections");
+  VG_CHECK_ARG(d->kind != 0 || (m != nullptr && (step_ptr != nullptr || (d->bias_corr1 > 0.f && d->bias_corr2 > 0.f))), "Adam needs m and bias corrections");
   if (n == 0) return VG_OK;
   bool al = ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)v % 16 == 0) && (!m || (uintptr_t)m % 16 == 0);
   long long n4 = al ? n / 4 : 0;
-  optimizer_kernel<<<ew_grid(n, 8), 256, 0, as_stream(stream)>>>(p, g, m, v, n4, n, *d);
+  optimizer_kernel<<<ew_grid(n, 8), 256, 0, as_stream(stream)>>>(p, g, m, v, n4, n, *d, step_ptr);
   VG_LAUNCHED();
   return VG_OK;
 }

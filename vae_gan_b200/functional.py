@@ -1,0 +1,691 @@
+"""torch.autograd.Functions over the C ABI (include/vaegan_b200.h).
+
+Activations are torch tensors of LOGICAL shape (N, C, H, W) stored channels_last (physically
+NHWC) in the compute dtype (bf16 tensor-core path, or fp32 parity path).  Every Function
+launches this library's kernels on torch's current CUDA stream; there is no torch/cuDNN/cuBLAS
+fallback - a missing library or an unsupported configuration raises.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import VgBnDesc, VgConvDesc, VgLossDesc, VgOptDesc, call, ptr, stream_ptr, vg_dtype
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+SN_EPS = 1e-12
+
+
+# ----------------------------------------------------------------------------------------------
+# global configuration / randomness
+# ----------------------------------------------------------------------------------------------
+class _Config:
+    compute_dtype = torch.bfloat16
+    process_group = None          # data-parallel group for SyncBN statistics (None = single GPU)
+    sample_offset = 0             # global index of this rank's first sample
+
+
+config = _Config()
+
+
+@contextlib.contextmanager
+def compute_dtype(dtype):
+    old = config.compute_dtype
+    config.compute_dtype = dtype
+    try:
+        yield
+    finally:
+        config.compute_dtype = old
+
+
+class PhiloxRng:
+    """Counter-based randomness: every dropout / noise site draws stream id `offset` (a host
+    counter, identical on every rank and every replay) + 65536 * step (a DEVICE counter), so a
+    captured CUDA graph produces fresh masks on each replay and tests can regenerate any mask."""
+
+    def __init__(self, seed: int = 0x5EED5EED):
+        self.seed = seed
+        self.site = 0
+        self._step = {}
+        self.record = False
+        self.trace = []
+
+    def reset_sites(self):
+        self.site = 0
+
+    def next_site(self, tag: str = "", shape=None) -> int:
+        s = self.site
+        self.site += 1
+        if self.record:
+            self.trace.append((tag, s, shape))
+        return s
+
+    def step_tensor(self, device) -> torch.Tensor:
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        if key not in self._step:
+            self._step[key] = torch.zeros(1, dtype=torch.int64, device=device)
+        return self._step[key]
+
+    def advance(self, device, inc: int = 1):
+        t = self.step_tensor(device)
+        call("vg_counter_add", ptr(t), inc, stream_ptr())
+
+
+rng = PhiloxRng()
+
+
+def _world():
+    pg = config.process_group
+    if pg is None:
+        return 1
+    return dist.get_world_size(pg)
+
+
+def _allreduce_sums(t: torch.Tensor):
+    if config.process_group is not None and _world() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=config.process_group)
+
+
+# ----------------------------------------------------------------------------------------------
+# tensor helpers
+# ----------------------------------------------------------------------------------------------
+def is_act(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.permute(0, 2, 3, 1).is_contiguous()
+
+
+def empty_act(n, c, h, w, dtype, device):
+    return torch.empty((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def as_act(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    """Make `t` an internal activation (channels_last, `dtype`) using our own kernels."""
+    dtype = dtype or t.dtype
+    _lib.ensure_device(t.device)
+    n, c, h, w = t.shape
+    if is_act(t):
+        if t.dtype == dtype:
+            return t
+        out = empty_act(n, c, h, w, dtype, t.device)
+        call("vg_cast", ptr(t), vg_dtype(t.dtype), ptr(out), vg_dtype(dtype), t.numel(), stream_ptr())
+        return out
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.dtype != torch.float32:
+        tmp = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+        call("vg_cast", ptr(t), vg_dtype(t.dtype), ptr(tmp), _lib.VG_F32, t.numel(), stream_ptr())
+        t = tmp
+    out = empty_act(n, c, h, w, dtype, t.device)
+    call("vg_nchw_to_nhwc", ptr(t), n, c, h, w, vg_dtype(dtype), ptr(out), stream_ptr())
+    return out
+
+
+def zeros_f64(n, device):
+    t = torch.empty(n, dtype=torch.float64, device=device)
+    call("vg_fill_zero", ptr(t), t.numel() * 8, stream_ptr())
+    return t
+
+
+def zeros_f32(shape, device):
+    t = torch.empty(shape, dtype=torch.float32, device=device)
+    call("vg_fill_zero", ptr(t), t.numel() * 4, stream_ptr())
+    return t
+
+
+class ToActFn(Function):
+    """Module-boundary conversion: any (N,C,H,W) tensor -> internal activation dtype/layout."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.in_dtype = x.dtype
+        ctx.in_cl = is_act(x)
+        return as_act(x, dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = as_act(g, ctx.in_dtype if ctx.in_dtype in (torch.float32, torch.bfloat16) else torch.float32)
+        return g, None
+
+
+def to_act(x, dtype=None):
+    dtype = dtype or config.compute_dtype
+    if is_act(x) and x.dtype == dtype:
+        return x
+    return ToActFn.apply(x, dtype)
+
+
+def from_act(y, dtype=torch.float32):
+    """Internal activation -> user-facing tensor (same logical NCHW shape, fp32)."""
+    if y.dtype == dtype:
+        return y
+    return ToActFn.apply(y, dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# convolution
+# ----------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class ConvGeom:
+    k: int
+    stride: int
+    pad: int
+    transposed: bool = False
+
+
+def _conv_desc(x_shape, c_out, g: ConvGeom, act_dtype, out_dtype):
+    n, c_in, h, w = x_shape
+    if g.transposed:
+        ho = (h - 1) * g.stride - 2 * g.pad + g.k
+        wo = (w - 1) * g.stride - 2 * g.pad + g.k
+    else:
+        ho = (h + 2 * g.pad - g.k) // g.stride + 1
+        wo = (w + 2 * g.pad - g.k) // g.stride + 1
+    d = VgConvDesc(n, h, w, c_in, ho, wo, c_out, g.k, g.k, g.stride, g.pad, int(g.transposed),
+                   vg_dtype(act_dtype), vg_dtype(out_dtype))
+    return d, ho, wo
+
+
+class ConvFn(Function):
+    """nn.Conv2d / nn.ConvTranspose2d (optionally spectral-normed, optionally followed by the
+    per-(n,c) Dropout2d scale) - README.md:148-170, 378-387, 441, 556-571.
+
+    weight is the fp32 parameter in torch layout.  With `sn=(u, v)` the legacy spectral-norm
+    hook semantics apply: one power iteration (training) updating u, v in place, weight/sigma.
+    `stats_out` (double[2*c_out], zeroed) receives sum / sum-of-squares of the output for the
+    BatchNorm that follows.  When `colscale` is given the matching BnActFn must be called with
+    out_colscale=colscale: it returns the gradient w.r.t. the UNSCALED conv output.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, sn_u, sn_v, colscale, geom, out_dtype, stats_out, training):
+        _lib.ensure_device(x.device)
+        assert is_act(x), "ConvFn expects a channels_last activation"
+        dev = x.device
+        c_out = weight.shape[1] if geom.transposed else weight.shape[0]
+        out_dtype = out_dtype or x.dtype
+        d, ho, wo = _conv_desc(x.shape, c_out, geom, x.dtype, out_dtype)
+        s = stream_ptr()
+        sigma = None
+        u_saved = v_saved = None
+        w = weight.detach()
+        if not w.is_contiguous():
+            w = w.contiguous()
+        if sn_u is not None:
+            rows, cols = w.shape[0], w.numel() // w.shape[0]
+            sigma = torch.empty(1, dtype=torch.float32, device=dev)
+            ws = torch.empty(rows + cols + 4, dtype=torch.float32, device=dev)
+            call("vg_spectral_norm_sigma", ptr(w), rows, cols, ptr(sn_u), ptr(sn_v), int(training), SN_EPS,
+                 ptr(sigma), ptr(ws), s)
+            u_saved, v_saved = sn_u.clone(), sn_v.clone()
+        numel = w.numel()
+        pack_kn = torch.empty(numel, dtype=x.dtype, device=dev)
+        pack_nk = torch.empty(numel, dtype=x.dtype, device=dev)
+        call("vg_conv_pack_weights", C.byref(d), ptr(w), ptr(sigma), ptr(pack_kn), ptr(pack_nk), s)
+        y = empty_act(x.shape[0], c_out, ho, wo, out_dtype, dev)
+        b = bias.detach() if bias is not None else None
+        call("vg_conv_forward", C.byref(d), ptr(x), ptr(pack_kn), ptr(pack_nk), ptr(b), ptr(colscale), ptr(y),
+             ptr(stats_out), s)
+        ctx.d = d
+        ctx.geom = geom
+        ctx.has_bias = bias is not None
+        ctx.has_sn = sn_u is not None
+        ctx.wshape = tuple(weight.shape)
+        ctx.wbuf = getattr(weight, "_vg_grad_buf", None)     # trainer's flat gradient view (fused accumulation)
+        ctx.bbuf = getattr(bias, "_vg_grad_buf", None) if bias is not None else None
+        ctx.save_for_backward(x, pack_kn, pack_nk, w if ctx.has_sn else None, sigma, u_saved, v_saved)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, pack_kn, pack_nk, w, sigma, u, v = ctx.saved_tensors
+        d = ctx.d
+        s = stream_ptr()
+        dy = as_act(dy, x.dtype)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_act(d.n, d.c_in, d.h_in, d.w_in, x.dtype, x.device)
+            call("vg_conv_dgrad", C.byref(d), ptr(dy), ptr(pack_kn), ptr(pack_nk), ptr(dx), s)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            fused = ctx.wbuf is not None
+            direct = fused and not ctx.has_sn
+            dwh = ctx.wbuf if direct else zeros_f32(ctx.wshape, x.device)
+            if ctx.has_bias:
+                db = ctx.bbuf if ctx.bbuf is not None else zeros_f32((d.c_out,), x.device)
+            call("vg_conv_wgrad", C.byref(d), ptr(x), ptr(dy), ptr(dwh), ptr(db), s)
+            if ctx.has_sn:
+                rows, cols = ctx.wshape[0], dwh.numel() // ctx.wshape[0]
+                dw = ctx.wbuf if fused else zeros_f32(ctx.wshape, x.device)
+                ws = torch.empty(4, dtype=torch.float32, device=x.device)
+                call("vg_spectral_norm_backward", ptr(dwh), ptr(w), ptr(u), ptr(v), ptr(sigma), rows, cols,
+                     ptr(dw), ptr(ws), s)
+            else:
+                dw = dwh
+            if fused:
+                dw = None
+            if ctx.bbuf is not None:
+                db = None
+        return dx, dw, db, None, None, None, None, None, None, None
+
+
+def conv(x, weight, bias=None, *, geom: ConvGeom, sn=None, colscale=None, out_dtype=None, stats_out=None,
+         training=True):
+    u, v = sn if sn is not None else (None, None)
+    return ConvFn.apply(x, weight, bias, u, v, colscale, geom, out_dtype, stats_out, training)
+
+
+# ----------------------------------------------------------------------------------------------
+# BatchNorm + LeakyReLU + Dropout
+# ----------------------------------------------------------------------------------------------
+def _bn_desc(x, slope=1.0, drop_p=0.0, offset=0, training=True):
+    n, c, h, w = x.shape
+    step_t = rng.step_tensor(x.device) if drop_p > 0 else None
+    d = VgBnDesc(n * h * w, c, h * w, vg_dtype(x.dtype), float(slope), float(drop_p), rng.seed, int(offset),
+                 int(config.sample_offset), int(training), ptr(step_t))
+    return d
+
+
+def bn_batch_stats(x, sums, running_mean, running_var, training, momentum=BN_MOMENTUM, eps=BN_EPS):
+    """Per-channel (mean, rstd) of `x` (float[2C]) - batch statistics (+ SyncBN all-reduce, +
+    running-stat update) in training, running statistics in eval."""
+    n, c, h, w = x.shape
+    s = stream_ptr()
+    mr = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+    if training:
+        if sums is None:
+            sums = zeros_f64(2 * c, x.device)
+            d = _bn_desc(x)
+            call("vg_bn_stats", ptr(x), C.byref(d), ptr(sums), s)
+        _allreduce_sums(sums)
+        count = float(n * h * w * _world())
+        call("vg_bn_finalize", ptr(sums), count, c, eps, momentum, ptr(running_mean), ptr(running_var), ptr(mr), s)
+    else:
+        call("vg_bn_eval_stats", ptr(running_mean), ptr(running_var), c, eps, ptr(mr), s)
+    return mr
+
+
+def _bn_backward(dy, x, mr, gamma, beta, d, out_colscale=None, addend=None, need_dx=True, need_params=True,
+                 gbuf=None, bbuf=None):
+    """Shared BN(+act+dropout) backward: returns dx, dgamma, dbeta (None when accumulated into the
+    trainer's flat gradient views gbuf / bbuf)."""
+    s = stream_ptr()
+    c = d.c
+    sums = zeros_f64(2 * c, x.device)
+    call("vg_bn_act_backward_reduce", ptr(dy), ptr(x), ptr(mr), ptr(gamma), ptr(beta), C.byref(d), ptr(sums), s)
+    if d.training:
+        _allreduce_sums(sums)          # SyncBN: global sums enter dx; param grads get reduced again
+    dx = None
+    if need_dx:
+        dx = torch.empty_like(x)
+        count = float(d.rows * _world())
+        call("vg_bn_act_backward_apply", ptr(dy), ptr(x), ptr(mr), ptr(gamma), ptr(beta), ptr(sums), count,
+             C.byref(d), ptr(out_colscale), ptr(addend), ptr(dx), s)
+    if not need_params:
+        return dx, None, None
+    fused = gbuf is not None and bbuf is not None
+    dgamma = gbuf if fused else zeros_f32((c,), x.device)
+    dbeta = bbuf if fused else zeros_f32((c,), x.device)
+    if d.training and _world() > 1:
+        # the parameter gradients are all-reduced (summed) later with the flat gradient buffer,
+        # so each rank must contribute 1/world of the already-global sums
+        sums = sums / _world()
+    call("vg_bn_param_grads", ptr(sums), c, ptr(dgamma), ptr(dbeta), s)
+    if fused:
+        return dx, None, None
+    return dx, dgamma, dbeta
+
+
+class BnActFn(Function):
+    """y = dropout(leaky_relu(batch_norm(x)))  - README.md:188-190, 192-193, 410-411, 414-415,
+    467-468.  `sums`: optional pre-accumulated double[2C] statistics from the producer."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, sums, slope, drop_p, offset, training,
+                out_colscale):
+        _lib.ensure_device(x.device)
+        assert is_act(x)
+        g, b = gamma.detach(), beta.detach()
+        mr = bn_batch_stats(x, sums, running_mean, running_var, training)
+        d = _bn_desc(x, slope, drop_p if training else 0.0, offset, training)
+        y = torch.empty_like(x)
+        call("vg_bn_act_forward", ptr(x), ptr(mr), ptr(g), ptr(b), C.byref(d), ptr(y), stream_ptr())
+        ctx.d = d
+        ctx.gbuf = getattr(gamma, "_vg_grad_buf", None)
+        ctx.bbuf = getattr(beta, "_vg_grad_buf", None)
+        ctx.save_for_backward(x, mr, g, b, out_colscale)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, mr, g, b, ocs = ctx.saved_tensors
+        dy = as_act(dy, x.dtype)
+        dx, dgamma, dbeta = _bn_backward(dy, x, mr, g, b, ctx.d, out_colscale=ocs,
+                                         need_dx=ctx.needs_input_grad[0], need_params=ctx.needs_input_grad[1],
+                                         gbuf=ctx.gbuf, bbuf=ctx.bbuf)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
+def bn_act(x, bn, *, slope=1.0, drop_p=0.0, training=True, sums=None, out_colscale=None, tag=""):
+    """`bn` is an nn.BatchNorm2d used as a parameter/buffer container."""
+    offset = rng.next_site(tag, tuple(x.shape)) if (training and drop_p > 0) else 0
+    if training and bn.track_running_stats:
+        bn.num_batches_tracked += 1
+    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, sums, slope, drop_p, offset,
+                         training, out_colscale)
+
+
+class BnAddFn(Function):
+    """out = leaky_relu(bnA(a) + bnB(b)), either BN optional: the residual add of
+    README.md:183-184, 195, 405-406, 417 fused with the shortcut's BatchNorm."""
+
+    @staticmethod
+    def forward(ctx, a, b, ga, ba, rma, rva, sums_a, gb, bb, rmb, rvb, sums_b, slope, training, stats_out):
+        _lib.ensure_device(a.device)
+        assert is_act(a) and is_act(b) and a.shape == b.shape and a.dtype == b.dtype
+        mra = mrb = None
+        ga_p, ba_p, gb_p, bb_p = ga, ba, gb, bb
+        if ga is not None:
+            ga, ba = ga.detach(), ba.detach()
+            mra = bn_batch_stats(a, sums_a, rma, rva, training)
+        if gb is not None:
+            gb, bb = gb.detach(), bb.detach()
+            mrb = bn_batch_stats(b, sums_b, rmb, rvb, training)
+        d = _bn_desc(a, slope, 0.0, 0, training)
+        out = torch.empty_like(a)
+        call("vg_bn_add_forward", ptr(a), ptr(mra), ptr(ga), ptr(ba), ptr(b), ptr(mrb), ptr(gb), ptr(bb),
+             C.byref(d), ptr(out), ptr(stats_out), stream_ptr())
+        ctx.d = d
+        ctx.slope = slope
+        ctx.bufs_a = (getattr(ga_p, "_vg_grad_buf", None), getattr(ba_p, "_vg_grad_buf", None))
+        ctx.bufs_b = (getattr(gb_p, "_vg_grad_buf", None), getattr(bb_p, "_vg_grad_buf", None))
+        ctx.save_for_backward(a if mra is not None else None, mra, ga, ba, b if mrb is not None else None, mrb, gb, bb,
+                              out if slope != 1.0 else None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        a, mra, ga, ba, b, mrb, gb, bb, out = ctx.saved_tensors
+        ref = a if a is not None else (b if b is not None else out)
+        dtype = ref.dtype if ref is not None else dout.dtype
+        dout = as_act(dout, dtype)
+        s = stream_ptr()
+        if ctx.slope != 1.0:
+            dpre = torch.empty_like(dout)
+            call("vg_lrelu_backward", ptr(dout), ptr(out), dout.numel(), vg_dtype(dout.dtype), float(ctx.slope),
+                 ptr(dpre), s)
+        else:
+            dpre = dout
+        d = VgBnDesc.from_buffer_copy(ctx.d)
+        d.slope = 1.0
+        da = db = dga = dba = dgb = dbb = None
+        if mra is not None:
+            da, dga, dba = _bn_backward(dpre, a, mra, ga, ba, d, need_dx=ctx.needs_input_grad[0],
+                                        need_params=ctx.needs_input_grad[2], gbuf=ctx.bufs_a[0], bbuf=ctx.bufs_a[1])
+        elif ctx.needs_input_grad[0]:
+            da = dpre
+        if mrb is not None:
+            db, dgb, dbb = _bn_backward(dpre, b, mrb, gb, bb, d, need_dx=ctx.needs_input_grad[1],
+                                        need_params=ctx.needs_input_grad[7], gbuf=ctx.bufs_b[0], bbuf=ctx.bufs_b[1])
+        elif ctx.needs_input_grad[1]:
+            db = dpre
+        return da, db, dga, dba, None, None, None, dgb, dbb, None, None, None, None, None, None
+
+
+def bn_add(a, b, bn_a=None, bn_b=None, *, slope=1.0, training=True, sums_a=None, sums_b=None, stats_out=None):
+    def unpack(bn):
+        if bn is None:
+            return None, None, None, None
+        if training and bn.track_running_stats:
+            bn.num_batches_tracked += 1
+        return bn.weight, bn.bias, bn.running_mean, bn.running_var
+
+    ga, ba, rma, rva = unpack(bn_a)
+    gb, bb, rmb, rvb = unpack(bn_b)
+    return BnAddFn.apply(a, b, ga, ba, rma, rva, sums_a, gb, bb, rmb, rvb, sums_b, slope, training, stats_out)
+
+
+class AddFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        out = torch.empty_like(a)
+        call("vg_add", ptr(a), ptr(b), a.numel(), vg_dtype(a.dtype), ptr(out), stream_ptr())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+# ----------------------------------------------------------------------------------------------
+# randomness helpers
+# ----------------------------------------------------------------------------------------------
+def dropout2d_scale(n, c, p, device, tag="dropout2d"):
+    """Per-(n,c) Dropout2d scale (0 or 1/(1-p)) from Philox - nn.Dropout2d, README.md:381."""
+    _lib.ensure_device(device)
+    offset = rng.next_site(tag, (n, c))
+    out = torch.empty((n, c), dtype=torch.float32, device=device)
+    call("vg_dropout2d_scale", ptr(out), n, c, float(p), rng.seed, offset, ptr(rng.step_tensor(device)),
+         int(config.sample_offset), stream_ptr())
+    return out
+
+
+def philox_normal(shape, device, tag="randn"):
+    """Standard-normal noise in NHWC element order of a (N,C,H,W) activation (fp32)."""
+    _lib.ensure_device(device)
+    n, c, h, w = shape
+    offset = rng.next_site(tag, tuple(shape))
+    out = empty_act(n, c, h, w, torch.float32, device)
+    start = int(config.sample_offset) * c * h * w
+    call("vg_philox_normal", ptr(out), out.numel(), rng.seed, offset, ptr(rng.step_tensor(device)), start,
+         stream_ptr())
+    return out
+
+
+def export_dropout_mask(shape, drop_p, offset, device, step=None, sample_offset=0, seed=None):
+    """Keep-mask bytes (logical NCHW view) for a BnActFn dropout site - used by the tests to feed
+    the oracle the very same mask."""
+    _lib.ensure_device(device)
+    n, c, h, w = shape
+    st = None
+    if step is not None:
+        st = torch.full((1,), int(step), dtype=torch.int64, device=device)
+    d = VgBnDesc(n * h * w, c, h * w, _lib.VG_F32, 1.0, float(drop_p), seed if seed is not None else rng.seed,
+                 int(offset), int(sample_offset), 1, ptr(st))
+    m = torch.empty((n, h, w, c), dtype=torch.uint8, device=device)
+    call("vg_dropout_mask", C.byref(d), ptr(m), stream_ptr())
+    return m.permute(0, 3, 1, 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# discriminator head
+# ----------------------------------------------------------------------------------------------
+class AvgPoolFlattenFn(Function):
+    """F.avg_pool2d(x, k) + view(B, -1) in NCHW order (README.md:471-473); output fp32."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        _lib.ensure_device(x.device)
+        assert is_act(x)
+        n, c, h, w = x.shape
+        out = torch.empty((n, c * (h // k) * (w // k)), dtype=torch.float32, device=x.device)
+        call("vg_avgpool_flatten_forward", ptr(x), n, h, w, c, k, vg_dtype(x.dtype), ptr(out), stream_ptr())
+        ctx.shape, ctx.k, ctx.dtype = (n, c, h, w), k, x.dtype
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        n, c, h, w = ctx.shape
+        g = g.contiguous().float()
+        dx = empty_act(n, c, h, w, ctx.dtype, g.device)
+        call("vg_avgpool_flatten_backward", ptr(g), n, h, w, c, ctx.k, vg_dtype(ctx.dtype), ptr(dx), stream_ptr())
+        return dx, None
+
+
+class LinearFn(Function):
+    """leaky_relu(nn.Linear(x)) (README.md:474-483).  Activations fp32; the weight is streamed in
+    the compute dtype (bf16 halves the 75 MB linear_1 read)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, slope, wdtype):
+        _lib.ensure_device(x.device)
+        x = x.contiguous()
+        m, k = x.shape
+        n = weight.shape[0]
+        s = stream_ptr()
+        w = weight.detach()
+        if wdtype != torch.float32:
+            wq = torch.empty(w.shape, dtype=wdtype, device=w.device)
+            call("vg_cast", ptr(w), _lib.VG_F32, ptr(wq), vg_dtype(wdtype), w.numel(), s)
+            w = wq
+        y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+        b = bias.detach() if bias is not None else None
+        call("vg_linear_forward", ptr(x), ptr(w), ptr(b), m, n, k, vg_dtype(wdtype), float(slope), ptr(y), s)
+        ctx.dims, ctx.slope, ctx.wdtype, ctx.has_bias = (m, n, k), slope, wdtype, bias is not None
+        ctx.wbuf = getattr(weight, "_vg_grad_buf", None)
+        ctx.bbuf = getattr(bias, "_vg_grad_buf", None) if bias is not None else None
+        ctx.save_for_backward(x, w, y if slope != 1.0 else None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        m, n, k = ctx.dims
+        s = stream_ptr()
+        dy = dy.contiguous().float()
+        if ctx.slope != 1.0:
+            dpre = torch.empty_like(dy)
+            call("vg_lrelu_backward", ptr(dy), ptr(y), dy.numel(), _lib.VG_F32, float(ctx.slope), ptr(dpre), s)
+            dy = dpre
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((m, k), dtype=torch.float32, device=dy.device)
+            call("vg_linear_dgrad", ptr(dy), ptr(w), m, n, k, vg_dtype(ctx.wdtype), ptr(dx), s)
+        if ctx.needs_input_grad[1]:
+            fused = ctx.wbuf is not None and (not ctx.has_bias or ctx.bbuf is not None)
+            dw = ctx.wbuf if fused else zeros_f32((n, k), dy.device)
+            db = (ctx.bbuf if fused else zeros_f32((n,), dy.device)) if ctx.has_bias else None
+            call("vg_linear_wgrad", ptr(x), ptr(dy), m, n, k, vg_dtype(ctx.wdtype), ptr(dw), ptr(db), s)
+            if fused:
+                dw = db = None
+        return dx, dw, db, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# reparameterisation and losses
+# ----------------------------------------------------------------------------------------------
+class ReparamFn(Function):
+    """README.md:575-582: log_var = clamp(raw, -50, 50); z = mu + exp(0.5 log_var) * eps."""
+
+    @staticmethod
+    def forward(ctx, mu, lv_raw, eps, training, z_dtype):
+        _lib.ensure_device(mu.device)
+        assert is_act(mu) and is_act(lv_raw) and mu.dtype == torch.float32 and lv_raw.dtype == torch.float32
+        n, c, h, w = mu.shape
+        z = empty_act(n, c, h, w, z_dtype, mu.device)
+        lv = torch.empty_like(lv_raw)
+        call("vg_reparam_forward", ptr(mu), ptr(lv_raw), ptr(eps), mu.numel(), int(training), vg_dtype(z_dtype),
+             ptr(z), ptr(lv), stream_ptr())
+        ctx.training, ctx.z_dtype = training, z_dtype
+        ctx.save_for_backward(lv_raw, eps)
+        return z, lv
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dz, dlv):
+        lv_raw, eps = ctx.saved_tensors
+        d_mu = torch.empty_like(lv_raw)
+        d_lv = torch.empty_like(lv_raw)
+        if dz is None:
+            dz = zeros_f32(lv_raw.shape, lv_raw.device).permute(0, 1, 2, 3)
+            dz = as_act(dz, ctx.z_dtype)
+        else:
+            dz = as_act(dz, ctx.z_dtype)
+        if dlv is not None:
+            dlv = as_act(dlv, torch.float32)
+        call("vg_reparam_backward", ptr(dz), ptr(lv_raw), ptr(eps), ptr(dlv), lv_raw.numel(), int(ctx.training),
+             vg_dtype(ctx.z_dtype), ptr(d_mu), ptr(d_lv), stream_ptr())
+        return d_mu, d_lv, None, None, None
+
+
+class GeneratorLossFn(Function):
+    """One fused kernel for the generator objective AND its gradients (README.md:816-831):
+    adv (BCE-with-logits vs 1, or -mean D) + w_recon*(L1+MSE) + w_kl*KL.  Returns
+    (total, recon, kl, adv) as fp32 scalars; backward only scales the stored gradients."""
+
+    @staticmethod
+    def forward(ctx, xhat, x, mu, lv, logits, adv_mode, w_adv, w_recon, w_kl):
+        _lib.ensure_device(xhat.device)
+        dev = xhat.device
+        assert is_act(xhat) and is_act(mu) and is_act(lv)
+        xf = x if (x.dtype == torch.float32 and is_act(x)) else as_act(x, torch.float32)
+        world = _world()
+        nlog = logits.numel() if logits is not None else 0
+        d = VgLossDesc(xhat.numel(), xhat.numel() * world, mu.numel(), nlog, nlog * world, int(adv_mode),
+                       float(w_adv), float(w_recon), float(w_kl), vg_dtype(xhat.dtype))
+        d_xhat = torch.empty_like(xhat)
+        d_mu = torch.empty_like(mu)
+        d_lv = torch.empty_like(lv)
+        d_log = torch.empty_like(logits) if logits is not None else None
+        losses = zeros_f64(4, dev)
+        lg = logits.detach().contiguous() if logits is not None else None
+        call("vg_generator_loss", ptr(xhat), ptr(xf), ptr(mu), ptr(lv), ptr(lg), C.byref(d), ptr(d_xhat), ptr(d_mu),
+             ptr(d_lv), ptr(d_log), ptr(losses), stream_ptr())
+        ctx.save_for_backward(d_xhat, d_mu, d_lv, d_log)
+        out = losses.to(torch.float32)
+        return out[0], out[1], out[2], out[3]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_total, g_recon, g_kl, g_adv):
+        d_xhat, d_mu, d_lv, d_log = ctx.saved_tensors
+        # the trainer calls backward with grad 1 on `total`; keep exactly that contract
+        return d_xhat, None, d_mu, d_lv, d_log, None, None, None, None
+
+
+class DiscriminatorLossFn(Function):
+    """README.md:792-793 (critic) or BCE-with-logits (north_star): returns (total, real, fake)."""
+
+    @staticmethod
+    def forward(ctx, d_real, d_fake, adv_mode):
+        _lib.ensure_device(d_real.device)
+        n = d_real.numel()
+        g_real = torch.empty_like(d_real)
+        g_fake = torch.empty_like(d_fake)
+        losses = zeros_f64(3, d_real.device)
+        call("vg_discriminator_loss", ptr(d_real.detach().contiguous()), ptr(d_fake.detach().contiguous()), n,
+             n * _world(), int(adv_mode), ptr(g_real), ptr(g_fake), ptr(losses), stream_ptr())
+        ctx.save_for_backward(g_real, g_fake)
+        out = losses.to(torch.float32)
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_total, g_r, g_f):
+        g_real, g_fake = ctx.saved_tensors
+        return g_real, g_fake, None
+
+
+# ----------------------------------------------------------------------------------------------
+# fused optimizer over flat buffers
+# ----------------------------------------------------------------------------------------------
+def optimizer_step(p, g, m, v, *, kind="adam", lr=3e-4, betas=(0.9, 0.999), alpha=0.99, eps=1e-8, weight_decay=0.0,
+                   step=1, clamp=0.0, grad_scale=1.0, step_tensor: Optional[torch.Tensor] = None):
+    _lib.ensure_device(p.device)
+    k = 0 if kind == "adam" else 1
+    d = VgOptDesc(k, lr, betas[0], betas[1], alpha, eps, weight_decay, 1 - betas[0] ** max(step, 1),
+                  1 - betas[1] ** max(step, 1), clamp, grad_scale)
+    call("vg_optimizer_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), C.byref(d), ptr(step_tensor), stream_ptr())

@@ -1,0 +1,162 @@
+"""The VAE-GAN training iteration (README.md:775-834) on this package's kernels.
+
+Order follows the reference exactly (it is result-affecting): G forward -> D(real), D(fake.detach)
+-> D backward -> D optimizer step [-> clamp in WGAN mode] -> D(fake) with the UPDATED D -> G
+backward (D dgrad only) -> G optimizer step.  Differences, all result-neutral or named by
+BASELINE.json north_star: BCE-with-logits adversarial loss and Adam are the default (the
+reference's critic loss / RMSprop+clamp are `loss_mode="wgan"`, `optimizer="rmsprop"`); the unused
+D weight gradients of the G step are not computed; losses stay on the device (no per-step sync).
+
+Parameters, gradients and optimizer state of each network live in ONE flat fp32 buffer: weight
+gradients are accumulated by the wgrad kernels straight into the flat gradient buffer, the
+data-parallel all-reduce is one NCCL call per network, and the optimizer is one fused kernel.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import functional as VF
+from . import modules as M
+
+
+class FlatParams:
+    """Re-homes a module's parameters into one flat buffer (+ flat grad, + optimizer state)."""
+
+    ALIGN = 64
+
+    def __init__(self, net: nn.Module):
+        params = [p for p in net.parameters()]
+        assert params, "module has no parameters"
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.params, self.offsets, self.total = params, offs, total
+        self.p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                view = self.p[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                gview = self.g[o:o + p.numel()].view(p.shape)
+                p.grad = gview
+                p._vg_grad_buf = gview       # wgrad kernels accumulate here directly
+
+    def zero_grad(self):
+        VF.call("vg_fill_zero", VF.ptr(self.g), self.g.numel() * 4, VF.stream_ptr())
+
+    def set_requires_grad(self, flag: bool):
+        for p in self.params:
+            p.requires_grad_(flag)
+
+
+class VaeGanTrainer:
+    def __init__(self, generator: nn.Module, discriminator: nn.Module, *, loss_mode: str = "bce",
+                 optimizer: str = "adam", lr: float = 3e-4, weights=(1.0, 10.0, 0.1), clip_value: float = 0.01,
+                 weight_decay: Optional[float] = None, betas=(0.9, 0.999), process_group=None,
+                 local_batch: Optional[int] = None):
+        assert loss_mode in ("bce", "wgan"), "wgan_gp (double backward) is not built yet - see DESIGN.md"
+        assert optimizer in ("adam", "rmsprop")
+        self.G, self.D = generator, discriminator
+        self.loss_mode, self.opt_kind, self.lr, self.weights = loss_mode, optimizer, lr, tuple(weights)
+        self.clip = clip_value if loss_mode == "wgan" else 0.0
+        self.weight_decay = weight_decay if weight_decay is not None else (1e-5 if optimizer == "rmsprop" else 0.0)
+        self.betas = betas
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if process_group is not None else 1
+        self.rank = dist.get_rank(process_group) if process_group is not None else 0
+        self.device = next(generator.parameters()).device
+        VF._lib.ensure_device(self.device)
+        self.fg = FlatParams(generator)
+        self.fd = FlatParams(discriminator)
+        self.opt_step = torch.zeros(1, dtype=torch.int64, device=self.device)   # device-side Adam t
+        self.losses: Dict[str, torch.Tensor] = {}
+        self.graph = None
+        self.static_real = None
+        self.local_batch = local_batch
+        if process_group is not None:
+            VF.config.process_group = process_group
+
+    # ------------------------------------------------------------------------------------------
+    def _opt(self, flat: FlatParams, clamp: float):
+        VF.optimizer_step(flat.p, flat.g, flat.m, flat.v, kind=self.opt_kind, lr=self.lr, betas=self.betas,
+                          weight_decay=self.weight_decay, clamp=clamp, step_tensor=self.opt_step)
+
+    def _allreduce(self, flat: FlatParams):
+        if self.world > 1:
+            dist.all_reduce(flat.g, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _step_impl(self, real: torch.Tensor):
+        dev = self.device
+        if self.world > 1:
+            VF.config.sample_offset = self.rank * real.shape[0]
+        adv_mode = 0 if self.loss_mode == "bce" else 1
+        VF.rng.reset_sites()
+        VF.rng.advance(dev)
+        VF.call("vg_counter_add", VF.ptr(self.opt_step), 1, VF.stream_ptr())
+        with M._scope():
+            with M._scope():          # depth >= 1 everywhere: modules hand over internal activations
+                # ---- generator forward (graph kept for the G step) ----
+                gen, mu, log_var = self.G(real)
+                # ---- discriminator step ----
+                self.fd.set_requires_grad(True)
+                self.fd.zero_grad()
+                d_real = self.D(real)
+                d_fake = self.D(gen.detach())
+                d_total, d_rl, d_fl = VF.DiscriminatorLossFn.apply(d_real, d_fake, adv_mode)
+                d_total.backward()
+                self._allreduce(self.fd)
+                self._opt(self.fd, self.clip)
+                # ---- generator step ----
+                self.fd.set_requires_grad(False)
+                self.fg.zero_grad()
+                d_gen = self.D(gen)
+                g_total, recon, kl, adv = VF.GeneratorLossFn.apply(gen, real, mu, log_var, d_gen, adv_mode,
+                                                                   self.weights[0], self.weights[1], self.weights[2])
+                g_total.backward()
+                self._allreduce(self.fg)
+                self._opt(self.fg, 0.0)
+                self.fd.set_requires_grad(True)
+        self.losses = dict(d_loss=d_total.detach(), real_loss=d_rl.detach(), fake_loss=d_fl.detach(),
+                           g_loss=g_total.detach(), recon=recon.detach(), kl=kl.detach(), adv=adv.detach())
+        self.last = dict(gen=gen.detach(), mu=mu.detach(), log_var=log_var.detach(), d_real=d_real.detach(),
+                         d_fake=d_fake.detach(), d_gen=d_gen.detach())
+        return self.losses
+
+    # ------------------------------------------------------------------------------------------
+    def capture(self, real_example: torch.Tensor, warmup: int = 3):
+        """Capture the whole iteration (fwd + bwd + collectives + optimizers) in one CUDA graph."""
+        self.static_real = real_example.clone()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_impl(self.static_real)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step_impl(self.static_real)
+        return self
+
+    def step(self, real: torch.Tensor):
+        if self.graph is not None:
+            if real is not self.static_real:
+                self.static_real.copy_(real, non_blocking=True)
+            self.graph.replay()
+            return self.losses
+        return self._step_impl(real)
+
+    def read_losses(self) -> Dict[str, float]:
+        """One device->host read of the last step's scalars."""
+        keys = list(self.losses)
+        vals = torch.stack([self.losses[k].float() for k in keys]).cpu().tolist()
+        return dict(zip(keys, vals))
