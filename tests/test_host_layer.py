@@ -1,0 +1,84 @@
+"""CPU-only checks of the host layer: the C-ABI library loads and exports every symbol the header
+declares (no compute calls), ctypes struct layouts match the C structs, and the drop-in modules keep
+the reference's state-dict keys."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from vae_gan_b200 import _lib
+    from vae_gan_b200.build import build
+    build()
+    lib = _lib.load()
+    hdr = (ROOT / "include" / "vaegan_b200.h").read_text()
+    declared = sorted(set(re.findall(r"\b(vg_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 38
+    missing = [n for n in declared if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+    assert lib.vg_version() == 100
+
+
+def test_ctypes_struct_layouts_match_header():
+    """Compile a tiny C program against the header and compare sizeof / offsetof."""
+    import subprocess, tempfile, json
+    from vae_gan_b200 import _lib
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "vaegan_b200.h"
+int main(void){
+  printf("{\"VgConvDesc\":%zu,\"VgBnDesc\":%zu,\"VgLossDesc\":%zu,\"VgOptDesc\":%zu,"
+         "\"bn_step_ptr\":%zu,\"bn_seed\":%zu,\"loss_xhat_dtype\":%zu,\"opt_grad_scale\":%zu}\n",
+         sizeof(VgConvDesc), sizeof(VgBnDesc), sizeof(VgLossDesc), sizeof(VgOptDesc),
+         offsetof(VgBnDesc, step_ptr), offsetof(VgBnDesc, seed), offsetof(VgLossDesc, xhat_dtype),
+         offsetof(VgOptDesc, grad_scale));
+  return 0; }
+'''
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "t.c"
+        p.write_text(src)
+        subprocess.check_call(["gcc", "-I", str(ROOT / "include"), str(p), "-o", str(Path(td) / "t")])
+        got = json.loads(subprocess.check_output([str(Path(td) / "t")]))
+    assert got["VgConvDesc"] == C.sizeof(_lib.VgConvDesc)
+    assert got["VgBnDesc"] == C.sizeof(_lib.VgBnDesc)
+    assert got["VgLossDesc"] == C.sizeof(_lib.VgLossDesc)
+    assert got["VgOptDesc"] == C.sizeof(_lib.VgOptDesc)
+    assert got["bn_step_ptr"] == _lib.VgBnDesc.step_ptr.offset
+    assert got["bn_seed"] == _lib.VgBnDesc.seed.offset
+    assert got["loss_xhat_dtype"] == _lib.VgLossDesc.xhat_dtype.offset
+    assert got["opt_grad_scale"] == _lib.VgOptDesc.grad_scale.offset
+
+
+def test_modules_keep_reference_state_dict_keys(golden_dir):
+    from vae_gan_b200 import build_vae_gan
+    s = torch.load(golden_dir / "structure_96.pt")
+    G, D = build_vae_gan(image_size=96)
+    assert sorted((k, tuple(v.shape)) for k, v in G.state_dict().items()) == sorted(s["g_keys"])
+    assert sorted((k, tuple(v.shape)) for k, v in D.state_dict().items()) == sorted(s["d_keys"])
+    assert sum(p.numel() for p in G.parameters()) == s["g_params"]
+    assert sum(p.numel() for p in D.parameters()) == s["d_params"]
+    # reference hard-codes 256x256 (README.md:435): the default input_size reproduces linear_len
+    from vae_gan_b200 import Discriminator, ResBlockDiscriminator
+    D256 = Discriminator(ResBlockDiscriminator, 1, 64, [1, 1, 1], [1, 2, 2], [128, 256, 512])
+    assert D256.linear_len == 131072
+
+
+def test_product_never_imports_the_oracle():
+    for p in (ROOT / "vae_gan_b200").glob("*.py"):
+        txt = p.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt, p
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from vae_gan_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
+    import pytest
+    with pytest.raises(_lib.VgError):
+        _lib.load()
