@@ -48,9 +48,9 @@ extern "C" int vg_conv_forward(const VgConvDesc* d, const void* x, const void* p
                                const float* colscale, void* y, double* stats, vg_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
+  if (d->n == 0) return VG_OK;   // empty batch: nothing to do (pointers of empty tensors may be null)
   VG_CHECK_ARG(x && y && pack_kn && pack_nk, "null pointer");
   cudaStream_t s = as_stream(stream);
-  if (d->n == 0) return VG_OK;
   if (tc_conv_supported(d, false))
     rc = tc_conv_run(d, false, x, pack_kn, bias, colscale, y, d->out_dtype, s);
   else
@@ -72,8 +72,8 @@ extern "C" int vg_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pa
                              vg_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
-  VG_CHECK_ARG(dy && dx && pack_kn && pack_nk, "null pointer");
   if (d->n == 0) return VG_OK;
+  VG_CHECK_ARG(dy && dx && pack_kn && pack_nk, "null pointer");
   cudaStream_t s = as_stream(stream);
   if (tc_conv_supported(d, true)) return tc_conv_run(d, true, dy, pack_nk, nullptr, nullptr, dx, d->act_dtype, s);
   return simt_conv_dgrad(d, dy, pack_kn, dx, s);
@@ -82,8 +82,8 @@ extern "C" int vg_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pa
 extern "C" int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias, vg_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
-  VG_CHECK_ARG(x && dy && dw, "null pointer");
   if (d->n == 0) return VG_OK;
+  VG_CHECK_ARG(x && dy && dw, "null pointer");
   cudaStream_t s = as_stream(stream);
   if (tc_wgrad_supported(d))
     rc = tc_wgrad_run(d, x, dy, dw, s);

@@ -354,6 +354,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static std::once_flag g_encode_once;
 
+// cuTensorMapEncodeTiled is a DRIVER entry point and needs a current context on the calling
+// thread.  torch's autograd worker threads only select a runtime device; a (cheap, once per
+// thread) runtime call binds the primary context before the first encode.
+static void bind_context_once() {
+  static thread_local bool done = false;
+  if (!done) {
+    cudaFree(0);
+    done = true;
+  }
+}
+
 static EncodeTiledFn get_encode() {
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
@@ -374,6 +385,7 @@ static int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, i
     set_error("cuTensorMapEncodeTiled entry point unavailable");
     return VG_ECUDA;
   }
+  bind_context_once();
   const int hs = (h - py + s - 1) / s, ws = (w - px + s - 1) / s;
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)std::max(ws, 1), (cuuint64_t)std::max(hs, 1), (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)s * c * 2, (cuuint64_t)s * w * c * 2, (cuuint64_t)h * w * c * 2};
@@ -395,6 +407,7 @@ static int make_weight_map(CUtensorMap* m, const void* base, long long rows, int
     set_error("cuTensorMapEncodeTiled entry point unavailable");
     return VG_ECUDA;
   }
+  bind_context_once();
   cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)k * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
