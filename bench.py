@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the VAE-GAN training iteration (BASELINE.json metric: train images/s at 96x96,
+global batch 256, on 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--global-batch B] [--impl ours|reference]
+
+One "step" = one full training iteration (G fwd, D(real), D(fake), D bwd + Adam, D(fake) again,
+G bwd + Adam) on one synthetic batch.  N > 1 is launched by torchrun (one rank per GPU, NCCL):
+the global batch is split over the ranks (strong scaling), BatchNorm statistics and gradients are
+all-reduced.  Prints ONE JSON line on rank 0.
+
+`value`  : whole-job images/s with the batch already resident in HBM (CUDA-graph replay).
+`e2e`    : same metric through the public API with HOST batches: pinned H2D copy of every batch and a
+           D2H read of the step's losses inside the timed region.
+`roofline`: the dominant kernel (tcgen05 implicit-GEMM conv) on the hottest layer shape, timed alone
+           with CUDA events: algorithmic FLOPs / duration vs the measured bf16 peak.
+`cpu_baseline`: the oracle (a port of the reference's PyTorch CPU path) on the host cores, bounded.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import torch
+
+IMAGE = 96
+FEATURE = 64
+GFLOP_PER_IMG_STEP = 127.59        # 3*G + 8*D forward GFLOPs, SURVEY.md section 8d / BASELINE.md
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(bf16=d.get("bf16_tflops", 1590.0), bf16_sustained=d.get("bf16_tflops_sustained", 1400.0),
+                    hbm=d.get("hbm_gbs", 6650.0), source="measured")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_baseline(budget_s: float = 20.0, batch: int = 4):
+    """The reference's CPU path (oracle port: same modules, BCE + Adam step the GPU parity tests use)
+    on the host cores, bounded to ~budget_s.  TEST/CHECKER code: reported, never shipped."""
+    from oracle import vaegan_oracle as O
+    spec_g = O.GeneratorSpec(depth=2, length=1, feature_size=FEATURE)
+    spec_d = O.DiscriminatorSpec(input_size=IMAGE)
+    Pg, Pd = O.make_generator_params(spec_g, 0), O.make_discriminator_params(spec_d, 1)
+    og, od = O.OptState(), O.OptState()
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(batch, 1, IMAGE, IMAGE, generator=g)
+    O.train_step(Pg, Pd, og, od, x, spec_g, spec_d)            # warm-up
+    t0, n = time.time(), 0
+    while True:
+        O.train_step(Pg, Pd, og, od, x, spec_g, spec_d)
+        n += 1
+        if time.time() - t0 > budget_s or n >= 8:
+            break
+    dt = time.time() - t0
+    return {"value": round(batch * n / dt, 4), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} iterations of oracle.train_step (BCE + Adam, dropout/noise from torch RNG) at batch {batch}, "
+                      f"1x{IMAGE}x{IMAGE}, after 1 warm-up; {dt / n:.2f} s/iteration"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port; the
+    notebook itself is not present on the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import vaegan_oracle as O
+    batch = 4
+    spec_g = O.GeneratorSpec(depth=2, length=1, feature_size=FEATURE)
+    spec_d = O.DiscriminatorSpec(input_size=IMAGE)
+    Pg, Pd = O.make_generator_params(spec_g, 0), O.make_discriminator_params(spec_d, 1)
+    og, od = O.OptState(), O.OptState()
+    g = torch.Generator().manual_seed(1234)
+    xs = [torch.rand(batch, 1, IMAGE, IMAGE, generator=g) for _ in range(2)]
+    steps = max(1, min(args.steps, 6))
+    warm = max(1, min(args.warmup, 1))
+    for i in range(warm):
+        O.train_step(Pg, Pd, og, od, xs[i % 2], spec_g, spec_d)
+    t0 = time.time()
+    for i in range(steps):
+        O.train_step(Pg, Pd, og, od, xs[i % 2], spec_g, spec_d)
+    dt = time.time() - t0
+    val = batch * steps / dt
+    sample = (f"each step = one oracle.train_step (BCE + Adam) on a bounded sample of {batch} images of the "
+              f"global-batch-{args.global_batch} workload; {steps} steps after {warm} warm-up")
+    print(json.dumps({
+        "impl": "reference", "metric": "train_images_per_sec", "value": round(val, 4), "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": round(1000 * dt / steps, 2),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"VAE-GAN train step 1x{IMAGE}x{IMAGE}, depth 2 / length 1 / feature_size {FEATURE}, "
+                               f"global batch {args.global_batch} (CPU arm: {batch}-image sample per step)",
+                   "global_batch": args.global_batch, "parallelism": "cpu"},
+        "cpu_baseline": {"value": round(val, 4), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": round(val, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------
+def roofline_probe(dev, batch: int, peaks):
+    """Dominant kernel = tc_conv_kernel.  Hottest layer of the step: D res0.conv2, Conv2d 128->128
+    3x3 s1 at 96x96 (2.718 GFLOP/img forward).  Timed alone, CUDA events on the
+    launching stream; the 128-channel activation is batch*96*96*128*2 B (>= 150 MB at batch 64) so
+    every launch streams its input from HBM, not from the 126 MB L2."""
+    import vae_gan_b200.functional as VF
+    cin = cout = 128
+    g = torch.Generator().manual_seed(0)
+    nbuf = 3
+    xs = [VF.as_act(torch.randn(batch, cin, IMAGE, IMAGE, generator=g).to(dev), torch.bfloat16) for _ in range(nbuf)]
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / 34.0).to(dev)
+    geom = VF.ConvGeom(3, 1, 1, False)
+    with torch.no_grad():
+        for i in range(3):
+            VF.conv(xs[i % nbuf], w, None, geom=geom)
+        torch.cuda.synchronize(dev)
+        # time ONLY the conv kernel: pack once, call the C ABI directly
+        import ctypes as C
+        from vae_gan_b200 import _lib
+        d, ho, wo = VF._conv_desc(xs[0].shape, cout, geom, torch.bfloat16, torch.bfloat16)
+        pk = torch.empty(w.numel(), dtype=torch.bfloat16, device=dev)
+        pn = torch.empty(w.numel(), dtype=torch.bfloat16, device=dev)
+        _lib.call("vg_conv_pack_weights", C.byref(d), w.data_ptr(), None, pk.data_ptr(), pn.data_ptr(), _lib.stream_ptr())
+        y = VF.empty_act(batch, cout, ho, wo, torch.bfloat16, dev)
+        iters = 12
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for i in range(iters):
+            evs[i][0].record()
+            _lib.call("vg_conv_forward", C.byref(d), xs[i % nbuf].data_ptr(), pk.data_ptr(), pn.data_ptr(), None, None,
+                      y.data_ptr(), None, _lib.stream_ptr())
+            evs[i][1].record()
+        torch.cuda.synchronize(dev)
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    avg = sum(ms[1:-1]) / (len(ms) - 2)
+    flops = 2.0 * batch * IMAGE * IMAGE * cout * cin * 9
+    achieved = flops / (avg * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["bf16"], "unit": "TFLOP/s",
+            "frac": round(achieved / peaks["bf16"], 4), "traffic": None,
+            "kernel": "tc_conv_kernel<128,3> (tcgen05 implicit GEMM), Conv2d 128->128 3x3 s1 @96x96",
+            "batch": batch, "ms_per_launch": round(avg, 4), "flop_per_launch": flops,
+            "peak_source": f"{peaks['source']} bf16 burst (kernel timed alone)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--global-batch", type=int, default=256)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--fp32", action="store_true", help="run the fp32 parity path instead of bf16")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch.distributed as dist
+    import vae_gan_b200 as V
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product path has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    assert args.global_batch % world == 0
+    local_b = args.global_batch // world
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+    peaks = measured_peaks()
+    cdt = torch.float32 if args.fp32 else torch.bfloat16
+
+    torch.manual_seed(0)
+    with V.compute_dtype(cdt):
+        G, D = V.build_vae_gan(feature_size=FEATURE, image_size=IMAGE)
+        G, D = G.to(dev).train(), D.to(dev).train()
+        tr = V.VaeGanTrainer(G, D, loss_mode="bce", optimizer="adam", lr=3e-4, process_group=pg)
+        V.config.sample_offset = rank * local_b
+        g = torch.Generator().manual_seed(1234 + rank)
+        n_host = 4
+        host = [torch.rand(local_b, 1, IMAGE, IMAGE, generator=g).pin_memory() for _ in range(n_host)]
+        x_dev = host[0].to(dev)
+        if world > 1:
+            t = torch.ones(1, device=dev)
+            dist.all_reduce(t)          # initialise the NCCL communicator before any capture
+        torch.cuda.synchronize(dev)
+
+        mode = "eager"
+        launches_per_step = None
+        if not args.no_graph:
+            try:
+                for _ in range(2):
+                    tr._step_impl(x_dev)
+                torch.cuda.synchronize(dev)
+                l0 = V._lib.launch_count()
+                tr.capture(x_dev, warmup=1)
+                mode = "cuda_graph"
+                # capture() ran 1 eager step + 1 captured step
+                launches_per_step = (V._lib.launch_count() - l0) // 2
+            except Exception as e:      # pragma: no cover
+                if rank == 0:
+                    print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+                tr.graph = None
+                torch.cuda.synchronize(dev)
+        if launches_per_step is None:
+            l0 = V._lib.launch_count()
+            tr._step_impl(x_dev)
+            launches_per_step = V._lib.launch_count() - l0
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        # ---------------- device-resident throughput ----------------
+        for _ in range(W):
+            tr.step(x_dev if tr.graph is None else tr.static_real)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            tr.step(x_dev if tr.graph is None else tr.static_real)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        ms_per_step = ms / K
+        value = args.global_batch * K / (ms * 1e-3)
+        losses = tr.read_losses()
+
+        # ---------------- end to end: host batches in, losses out, every step ----------------
+        for i in range(2):
+            tr.step(host[i % n_host].to(dev, non_blocking=True))
+            tr.read_losses()
+        barrier()
+        Ke = max(5, min(K, 20))
+        e0.record()
+        for i in range(Ke):
+            xb = host[i % n_host].to(dev, non_blocking=True)     # pinned H2D copy of this step's batch
+            tr.step(xb)
+            tr.read_losses()                                      # D2H read of this step's scalars
+        e1.record()
+        barrier()
+        ms_e = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t)
+        e2e_value = args.global_batch * Ke / (ms_e * 1e-3)
+
+        roof = cpu = None
+        # drop the captured graph (it holds NCCL work) on EVERY rank before any teardown
+        tr.graph = None
+        torch.cuda.synchronize(dev)
+        barrier()
+        if rank == 0:
+            torch.cuda.empty_cache()
+            roof = roofline_probe(dev, min(local_b, 64), peaks)
+            if world == 1 and not args.skip_cpu_baseline:
+                cpu = cpu_baseline()
+
+    if rank == 0:
+        step_tflops = GFLOP_PER_IMG_STEP * 1e9 * args.global_batch / (ms_per_step * 1e-3) / 1e12 / world
+        out = {
+            "metric": "train_images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32" if args.fp32 else "bf16", "data": "synthetic",
+            "config": {
+                "workload": f"full VAE-GAN train step (encoder+decoder+discriminator, KL + L1/MSE + adversarial BCE, Adam), "
+                            f"1x{IMAGE}x{IMAGE} images, depth 2 / length 1 / feature_size {FEATURE}, global batch "
+                            f"{args.global_batch} ({local_b}/GPU), SyncBN + gradient all-reduce" + ("" if world > 1 else " (1 GPU: no collectives)"),
+                "global_batch": args.global_batch, "per_gpu_batch": local_b, "parallelism": f"dp{world}", "mode": mode,
+                "l2_note": "activations of one step (several GB) far exceed the 126 MB L2; no flush needed",
+            },
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": local_b * IMAGE * IMAGE * 4 * world,
+                    "d2h_bytes_per_step": 7 * 4 * world, "steps": Ke, "ms_per_step": round(ms_e / Ke, 3)},
+            "gpu_launches": int(launches_per_step * K),
+            "launches_per_step": int(launches_per_step),
+            "step_model_tflops_per_gpu": round(step_tflops, 1),
+            "step_frac_of_tensor_peak": round(step_tflops / peaks["bf16_sustained"], 4),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "losses_last_step": {k: round(v, 4) for k, v in losses.items()},
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)       # skip NCCL/graph teardown ordering issues at interpreter exit
+
+
+if __name__ == "__main__":
+    main()

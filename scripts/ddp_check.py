@@ -1,0 +1,86 @@
+"""Data-parallel equivalence check (run under torchrun, one rank per GPU):
+the N-rank trainer (SyncBN statistics + gradient all-reduce, batch split over ranks) must reproduce
+the single-process trainer on the GLOBAL batch.  Prints one JSON line on rank 0
+and exits non-zero on mismatch."""
+import json
+import os
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch
+import torch.distributed as dist
+
+import vae_gan_b200 as V
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    results = {}
+    ok = True
+    for cdt, tol in ((torch.float32, 2e-4), (torch.bfloat16, 3e-2)):
+        B, S, fs, steps = 4 * world, 32, 64, 2
+        gen = torch.Generator().manual_seed(5)
+        xs = [torch.rand(B, 1, S, S, generator=gen).to(dev) for _ in range(steps)]
+
+        def make(pg):
+            torch.manual_seed(0)
+            G, D = V.build_vae_gan(feature_size=fs, image_size=S)
+            G, D = G.to(dev).train(), D.to(dev).train()
+            V.rng.seed = 77
+            V.rng.step_tensor(dev).zero_()
+            V.config.process_group = None
+            V.config.sample_offset = 0
+            return V.VaeGanTrainer(G, D, process_group=pg)
+
+        with V.compute_dtype(cdt):
+            single = make(None)
+            ref = []
+            for x in xs:
+                single.step(x)
+                ref.append(single.read_losses())
+            p_ref_g, p_ref_d = single.fg.p.clone(), single.fd.p.clone()
+            dp = make(dist.group.WORLD)
+            got = []
+            lb = B // world
+            for x in xs:
+                dp.step(x[rank * lb:(rank + 1) * lb].contiguous())
+                got.append(dp.read_losses())
+            V.config.process_group = None
+            # step-1 quantities computed BEFORE any optimizer update must agree tightly; everything
+            # after an update inherits Adam's lr*sign(g) amplification of summation-order noise
+            pre = ("d_loss", "real_loss", "fake_loss", "recon", "kl")
+            worst = worst_pre = 0.0
+            for i, (a, b) in enumerate(zip(got, ref)):
+                for k in b:
+                    e = abs(a[k] - b[k]) / max(1.0, abs(b[k]))
+                    if i == 0 and k in pre:
+                        worst_pre = max(worst_pre, e)
+                    else:
+                        worst = max(worst, e)
+            lr = 3e-4
+            frac_g = float(((dp.fg.p - p_ref_g).abs() > 0.5 * lr).float().mean())
+            frac_d = float(((dp.fd.p - p_ref_d).abs() > 0.5 * lr).float().mean())
+            # all ranks must hold identical parameters
+            chk = torch.stack([dp.fg.p.double().sum(), dp.fd.p.double().sum()])
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            same = bool(((hi - lo).abs() <= 1e-6 * hi.abs().clamp_min(1)).all())
+        results[str(cdt)] = dict(worst_pre_update_loss_rel=worst_pre, worst_loss_rel=worst, frac_params_off_g=frac_g, frac_params_off_d=frac_d, replicas_identical=same)
+        lim = 2e-3 if cdt == torch.float32 else 0.08
+        tol_pre = 2e-5 if cdt == torch.float32 else 2e-2
+        tol_post = 5e-3 if cdt == torch.float32 else 5e-2
+        ok = ok and worst_pre <= tol_pre and worst <= tol_post and frac_g <= lim and frac_d <= lim and same
+    if rank == 0:
+        print(json.dumps(dict(world=world, ok=ok, **results)))
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

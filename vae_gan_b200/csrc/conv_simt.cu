@@ -44,15 +44,15 @@ template <typename TI, typename TO, bool SCATTER, int CO_T>
 __global__ void __launch_bounds__(256) conv_direct_kernel(const TI* __restrict__ in, const TI* __restrict__ W,
                                                           const float* __restrict__ bias, const float* __restrict__ colscale,
                                                           ConvGeom g, TO* __restrict__ out) {
-  const int cog = g.co / CO_T;
-  const long long total = (long long)g.n * g.ho * g.wo * cog;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  const unsigned cog = (unsigned)(g.co / CO_T);
+  const unsigned total = (unsigned)g.n * g.ho * g.wo * cog;      // host guarantees < 2^31
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int cg = (int)(idx % cog);
-    long long pix = idx / cog;
-    const int ox = (int)(pix % g.wo);
-    long long t = pix / g.wo;
-    const int oy = (int)(t % g.ho);
-    const int n = (int)(t / g.ho);
+    const unsigned pix = idx / cog;
+    const int ox = (int)(pix % (unsigned)g.wo);
+    const unsigned t = pix / (unsigned)g.wo;
+    const int oy = (int)(t % (unsigned)g.ho);
+    const int n = (int)(t / (unsigned)g.ho);
     const int co0 = cg * CO_T;
     float acc[CO_T];
 #pragma unroll
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const TI* __restrict__
         }
       }
     }
-    TO* op = out + pix * g.co + co0;
+    TO* op = out + (long long)pix * g.co + co0;
 #pragma unroll
     for (int j = 0; j < CO_T; ++j) {
       float v = acc[j];
@@ -129,6 +129,224 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const TI* __restrict__
 #pragma unroll
       for (int j = 0; j < CO_T; ++j) op[j] = from_f32<TO>(acc[j]);
     }
+  }
+}
+
+// ---- degenerate layers (one side has a single channel) --------------------------------------
+// reduce1: out[p] = sum_taps sum_c in[p (+) tap][c] * W[tap][c]     (Conv2d C->1 forward, Conv2d 1->C dgrad)
+// 8 threads cooperate on one output pixel, each owning 8 channels of every tap; the weights of
+// a thread (taps x 8) live in registers for the whole kernel.  cr == 64 only (8 lanes x 8 ch).
+template <typename TI, typename TO, bool SCATTER, int TAPS>
+__global__ void __launch_bounds__(256) conv_reduce1_kernel(const TI* __restrict__ in, const TI* __restrict__ W,
+                                                           const float* __restrict__ bias, ConvGeom g, TO* __restrict__ out) {
+  const int sub = threadIdx.x & 7;            // channel group within the pixel
+  float w[TAPS][8];
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) {
+    Vec8<TI> wv;
+    wv.load(W + (long long)t * g.cr + sub * 8);   // W is [tap][cr][1]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[t][j] = wv.v[j];
+  }
+  const unsigned npix = (unsigned)g.n * g.ho * g.wo;
+  for (unsigned pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < npix; pix += (gridDim.x * blockDim.x) >> 3) {
+    const int ox = (int)(pix % (unsigned)g.wo);
+    const unsigned t0 = pix / (unsigned)g.wo;
+    const int oy = (int)(t0 % (unsigned)g.ho);
+    const int n = (int)(t0 / (unsigned)g.ho);
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      if (ky >= g.kh) break;
+      int iy;
+      if (SCATTER) { int ty = oy + g.pad - ky; if (ty < 0 || ty % g.stride != 0) continue; iy = ty / g.stride; }
+      else iy = oy * g.stride - g.pad + ky;
+      if (iy < 0 || iy >= g.hi) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        if (kx >= g.kw) break;
+        int ix;
+        if (SCATTER) { int tx = ox + g.pad - kx; if (tx < 0 || tx % g.stride != 0) continue; ix = tx / g.stride; }
+        else ix = ox * g.stride - g.pad + kx;
+        if (ix < 0 || ix >= g.wi) continue;
+        Vec8<TI> xv;
+        xv.load(in + (((long long)n * g.hi + iy) * g.wi + ix) * g.cr + sub * 8);
+        const int tp = ky * 3 + kx;   // kw == 3 (dispatch guarantees it): compile-time register index
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(xv.v[j], w[tp][j], acc);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (sub == 0) {
+      if (bias) acc += bias[0];
+      out[pix] = from_f32<TO>(acc);
+    }
+  }
+}
+
+// expand1: out[p][c] = sum_taps in[p (+) tap] * W[tap][c]   (Conv2d 1->C forward, Conv2d C->1 dgrad).
+// A thread owns 8 output channels for its whole life (its 9x8 weights stay in registers) and walks
+// pixels with a grid stride: 9 scalar loads (L1-resident single-channel image) per 16 B stored.
+template <typename TI, typename TO, bool SCATTER>
+__global__ void __launch_bounds__(256) conv_expand1_kernel(const TI* __restrict__ in, const TI* __restrict__ W,
+                                                           const float* __restrict__ bias, const float* __restrict__ colscale,
+                                                           ConvGeom g, TO* __restrict__ out) {
+  const unsigned cog = (unsigned)g.co / 8;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned nthr = gridDim.x * blockDim.x;          // multiple of cog (host guarantees)
+  const int cg = (int)(tid % cog);
+  float w[9][8], b[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    Vec8<TI> wv;
+    wv.load(W + (long long)t * g.co + cg * 8);            // W is [tap][1][co]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[t][j] = wv.v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = bias ? bias[cg * 8 + j] : 0.f;
+  const unsigned npix = (unsigned)g.n * g.ho * g.wo;
+  for (unsigned pix = tid / cog; pix < npix; pix += nthr / cog) {
+    const int ox = (int)(pix % (unsigned)g.wo);
+    const unsigned t0 = pix / (unsigned)g.wo;
+    const int oy = (int)(t0 % (unsigned)g.ho);
+    const int n = (int)(t0 / (unsigned)g.ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = b[j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      int iy;
+      if (SCATTER) { int ty = oy + g.pad - ky; if (ty < 0 || ty % g.stride != 0) continue; iy = ty / g.stride; }
+      else iy = oy * g.stride - g.pad + ky;
+      if (iy < 0 || iy >= g.hi) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        int ix;
+        if (SCATTER) { int tx = ox + g.pad - kx; if (tx < 0 || tx % g.stride != 0) continue; ix = tx / g.stride; }
+        else ix = ox * g.stride - g.pad + kx;
+        if (ix < 0 || ix >= g.wi) continue;
+        const float xs = to_f32(in[((long long)n * g.hi + iy) * g.wi + ix]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xs, w[ky * 3 + kx][j], acc[j]);
+      }
+    }
+    if (colscale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= colscale[(long long)n * g.co + cg * 8 + j];
+    }
+    Vec8<TO> ov;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ov.v[j] = acc[j];
+    ov.store(out + (long long)pix * g.co + cg * 8);
+  }
+}
+
+// wgrad with a single-channel side: dw[c*taps + tap] += sum_q V[q][c] * S[shift(q, tap)]
+//   a_mode = true : V on the coarse/output grid (Conv2d 1->C: V = dy, S = x),   S index = q*stride - pad + k
+//   a_mode = false: V on the input grid         (Conv2d C->1: V = x,  S = dy),  S index = (q + pad - k)/stride
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) wgrad_degenerate_kernel(const T* __restrict__ V, const T* __restrict__ S, int n, int hv,
+                                                               int wv, int c, int hs, int ws, int kh, int kw, int stride, int pad,
+                                                               bool a_mode, unsigned pix_per_block, float* __restrict__ dw) {
+  extern __shared__ float sacc[];   // [taps * c]
+  const int taps = kh * kw;
+  for (int i = threadIdx.x; i < taps * c; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int groups = c / VEC;                 // channel groups per pixel
+  const int lanes = blockDim.x / groups;      // pixels processed concurrently
+  const int grp = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const unsigned npix = (unsigned)n * hv * wv;
+  const unsigned p0 = blockIdx.x * pix_per_block;
+  const unsigned p1 = min(npix, p0 + pix_per_block);
+  float acc[9][VEC];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[t][j] = 0.f;
+  if (lane < lanes) {
+    constexpr int U = 4;
+    for (unsigned qb = p0 + lane; qb < p1; qb += U * lanes) {
+      float v[U][VEC];
+      // issue all the streaming loads of this batch first (memory-level parallelism)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned q = qb + u * lanes;
+        if (q < p1) {
+          if (VEC == 8) {
+            Vec8<T> vv;
+            vv.load(V + (long long)q * c + grp * 8);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[u][j] = vv.v[j];
+          } else {
+            v[u][0] = to_f32(V[(long long)q * c + grp]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned q = qb + u * lanes;
+        if (q >= p1) break;
+        const int xq = (int)(q % (unsigned)wv);
+        const unsigned t0 = q / (unsigned)wv;
+        const int yq = (int)(t0 % (unsigned)hv);
+        const int nn = (int)(t0 / (unsigned)hv);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          if (ky >= kh) break;
+          int sy;
+          if (a_mode) sy = yq * stride - pad + ky;
+          else { int ty = yq + pad - ky; if (ty < 0 || ty % stride != 0) continue; sy = ty / stride; }
+          if (sy < 0 || sy >= hs) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            if (kx >= kw) break;
+            int sx;
+            if (a_mode) sx = xq * stride - pad + kx;
+            else { int tx = xq + pad - kx; if (tx < 0 || tx % stride != 0) continue; sx = tx / stride; }
+            if (sx < 0 || sx >= ws) continue;
+            const float sv = to_f32(S[((long long)nn * hs + sy) * ws + sx]);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[ky * 3 + kx][j] = fmaf(v[u][j], sv, acc[ky * 3 + kx][j]);
+          }
+        }
+      }
+    }
+    // reduce across the threads of this warp that own the same channel group (register shuffles),
+    // then ONE plain shared store per (warp, tap, channel): no contended shared atomics
+    const int lid = threadIdx.x & 31;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float a = acc[t][j];
+        for (int off = groups; off < 32; off <<= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        acc[t][j] = a;
+      }
+    if (lid < groups || groups >= 32) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          if (ky >= kh || kx >= kw) continue;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            float* dst = &sacc[(ky * kw + kx) * c + grp * VEC + j];
+            if (groups >= 32) atomicAdd(dst, acc[ky * 3 + kx][j]);        // wide layers: few threads per group
+            else atomicAdd(dst, acc[ky * 3 + kx][j]);                     // <= 8 warps contend per address
+          }
+        }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < taps * c; i += blockDim.x) {
+    const int tap = i / c, ch = i % c;
+    atomicAdd(&dw[(long long)ch * taps + tap], sacc[i]);
   }
 }
 
@@ -218,6 +436,22 @@ static int launch_direct(bool scatter, const TI* in, const TI* W, const float* b
   const bool v8 = (g.co % 8 == 0);
   const long long total = (long long)g.n * g.ho * g.wo * (v8 ? g.co / 8 : g.co);
   if (total == 0) return VG_OK;
+  VG_CHECK_ARG(total < (1LL << 31) && (long long)g.n * g.hi * g.wi * g.cr < (1LL << 40), "tensor too large for the CUDA-core conv path");
+  if (g.co == 1 && g.cr == 64 && g.kh == 3 && g.kw == 3 && colscale == nullptr) {
+    const long long thr = (long long)g.n * g.ho * g.wo * 8;
+    int grid1 = (int)std::min<long long>(cdiv(thr, 256), (long long)num_sms() * 16);
+    if (scatter) conv_reduce1_kernel<TI, TO, true, 9><<<grid1, 256, 0, s>>>(in, W, bias, g, out);
+    else         conv_reduce1_kernel<TI, TO, false, 9><<<grid1, 256, 0, s>>>(in, W, bias, g, out);
+    VG_LAUNCHED();
+    return VG_OK;
+  }
+  if (g.cr == 1 && v8 && g.kh == 3 && g.kw == 3 && 256 % (g.co / 8) == 0) {
+    int grid1 = (int)std::min<long long>(cdiv(total, 256 * 2), (long long)num_sms() * 16);
+    if (scatter) conv_expand1_kernel<TI, TO, true><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
+    else         conv_expand1_kernel<TI, TO, false><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
+    VG_LAUNCHED();
+    return VG_OK;
+  }
   int grid = (int)std::min<long long>(cdiv(total, 256), (long long)num_sms() * 32);
   if (scatter) {
     if (v8) conv_direct_kernel<TI, TO, true, 8><<<grid, 256, 0, s>>>(in, W, bias, colscale, g, out);
@@ -266,6 +500,35 @@ int simt_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* d
   }
   const long long qtot = (long long)g.n * g.hu * g.wu;
   if (qtot == 0) return VG_OK;
+  const int dg_c = (d->c_in == 1) ? d->c_out : d->c_in;
+  const int dg_groups = (dg_c % 8 == 0) ? dg_c / 8 : dg_c;
+  if (!d->transposed && d->kh <= 3 && d->kw <= 3 && (d->c_in == 1 || d->c_out == 1) && dg_groups <= 256 &&
+      (dg_groups & (dg_groups - 1)) == 0 &&
+      (long long)d->n * d->h_in * d->w_in < (1LL << 31) && std::max(d->c_in, d->c_out) * d->kh * d->kw * 4 <= 40000) {
+    // one side has a single channel: memory-bound streaming kernel
+    const bool a_mode = (d->c_in == 1);           // V = dy on the output grid, S = x
+    const void* V = a_mode ? dy : x;
+    const void* Sx = a_mode ? x : dy;
+    const int c = a_mode ? d->c_out : d->c_in;
+    const int hv = a_mode ? d->h_out : d->h_in, wv = a_mode ? d->w_out : d->w_in;
+    const int hs = a_mode ? d->h_in : d->h_out, ws = a_mode ? d->w_in : d->w_out;
+    const long long npix = (long long)d->n * hv * wv;
+    const int vec = (c % 8 == 0 && c / 8 <= 256) ? 8 : 1;
+    VG_CHECK_ARG(c / vec <= 256, "degenerate wgrad supports up to 256 channel groups");
+    long long blocks = std::min<long long>(cdiv(npix, 1024), (long long)num_sms() * 2);
+    unsigned ppb = (unsigned)cdiv(npix, blocks);
+    blocks = cdiv(npix, ppb);
+    size_t sm = (size_t)d->kh * d->kw * c * sizeof(float);
+    if (d->act_dtype == VG_BF16) {
+      if (vec == 8) wgrad_degenerate_kernel<__nv_bfloat16, 8><<<(unsigned)blocks, 256, sm, s>>>((const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
+      else          wgrad_degenerate_kernel<__nv_bfloat16, 1><<<(unsigned)blocks, 256, sm, s>>>((const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
+    } else {
+      if (vec == 8) wgrad_degenerate_kernel<float, 8><<<(unsigned)blocks, 256, sm, s>>>((const float*)V, (const float*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
+      else          wgrad_degenerate_kernel<float, 1><<<(unsigned)blocks, 256, sm, s>>>((const float*)V, (const float*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
+    }
+    VG_LAUNCHED();
+    return VG_OK;
+  }
   const int tiles = ((g.cu + 31) / 32) * ((g.cs + 31) / 32);
   const int taps = g.kh * g.kw;
   long long want = std::max<long long>(1, (long long)num_sms() * 4 / ((long long)tiles * taps));

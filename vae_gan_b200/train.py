@@ -158,5 +158,9 @@ class VaeGanTrainer:
     def read_losses(self) -> Dict[str, float]:
         """One device->host read of the last step's scalars."""
         keys = list(self.losses)
-        vals = torch.stack([self.losses[k].float() for k in keys]).cpu().tolist()
-        return dict(zip(keys, vals))
+        vals = torch.stack([self.losses[k].float() for k in keys])
+        if self.world > 1:
+            # each rank holds its share (means are normalised by the GLOBAL count, KL is a sum)
+            vals = vals.clone()
+            dist.all_reduce(vals, op=dist.ReduceOp.SUM, group=self.pg)
+        return dict(zip(keys, vals.cpu().tolist()))
