@@ -135,6 +135,8 @@ int vg_bn_add_forward(const void* a, const float* mean_rstd_a, const float* gamm
                       const float* beta_a, const void* b, const float* mean_rstd_b,
                       const float* gamma_b, const float* beta_b, const VgBnDesc* d, void* out,
                       double* stats, vg_stream_t stream);
+/* y = leaky_relu(x) on a flat fp32 tensor (discriminator head, README.md:475-481) */
+int vg_lrelu_forward(const void* x, long long n, int dtype, float slope, void* y, vg_stream_t stream);
 /* dx = dy * (y_ref > 0 ? 1 : slope) */
 int vg_lrelu_backward(const void* dy, const void* y_ref, long long n, int dtype, float slope,
                       void* dx, vg_stream_t stream);

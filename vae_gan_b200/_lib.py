@@ -59,6 +59,7 @@ _PROTOS = {
     "vg_bn_act_backward_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, C.POINTER(VgBnDesc), c_vp, c_vp, c_vp, c_vp]),
     "vg_bn_param_grads": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp]),
     "vg_bn_add_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(VgBnDesc), c_vp, c_vp, c_vp]),
+    "vg_lrelu_forward": (c_int, [c_vp, c_ll, c_int, c_f, c_vp, c_vp]),
     "vg_lrelu_backward": (c_int, [c_vp, c_vp, c_ll, c_int, c_f, c_vp, c_vp]),
     "vg_add": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_vp]),
     "vg_dropout_mask": (c_int, [C.POINTER(VgBnDesc), c_vp, c_vp]),

@@ -48,6 +48,7 @@ struct alignas(64) TcConvParams {
   int n_out;             // output channels
   int OH, OW, os;        // output tensor spatial dims and phase stride
   int out_f32;
+  int ksplit, k_per_split;   // split-K over blockIdx.z (only with a single phase, fp32 atomics)
   void* out;
   const float* bias;
   const float* colscale;
@@ -89,9 +90,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TcPhase& ph = p.phases[blockIdx.z];
+  const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : blockIdx.z];
   const int ntaps = ph.ntaps;
-  const int num_k = ntaps * p.k_chunks;
+  const int kb0 = p.ksplit > 1 ? (int)blockIdx.z * p.k_per_split : 0;
+  const int kb1 = p.ksplit > 1 ? min(ntaps * p.k_chunks, kb0 + p.k_per_split) : ntaps * p.k_chunks;
+  const int num_k = max(0, kb1 - kb0);
   int t = blockIdx.x;
   const int tx = t % p.tiles_x; t /= p.tiles_x;
   const int ty = t % p.tiles_y;
@@ -122,16 +125,16 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int tp = 0; tp < ntaps; ++tp) {
+        int tp = kb0 / p.k_chunks, kc = kb0 % p.k_chunks;
+        for (int i = kb0; i < kb1; ++i) {
           const TcTap tap = ph.taps[tp];
           const CUtensorMap* im = &p.in_maps[tap.map];
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
-            ptx::mbar_wait(&empty[stage], phase ^ 1u);
-            ptx::mbar_arrive_expect_tx(&full[stage], kABytes + kBBytes);
-            ptx::tma_load_4d(sA + stage * kABytes, im, &full[stage], kc * 64, x0 + tap.dx, y0 + tap.dy, n0);
-            ptx::tma_load_2d(sB + stage * kBBytes, &p.w_map, &full[stage], kc * 64, tap.wrow + ncol0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          }
+          ptx::mbar_wait(&empty[stage], phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full[stage], kABytes + kBBytes);
+          ptx::tma_load_4d(sA + stage * kABytes, im, &full[stage], kc * 64, x0 + tap.dx, y0 + tap.dy, n0);
+          ptx::tma_load_2d(sB + stage * kBBytes, &p.w_map, &full[stage], kc * 64, tap.wrow + ncol0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++kc == p.k_chunks) { kc = 0; ++tp; }
         }
       }
     } else if (warp == 1) {
@@ -181,11 +184,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      if (valid) {
+      if (valid && !(p.ksplit > 1 && num_k == 0)) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
+        if (p.bias != nullptr && (p.ksplit <= 1 || blockIdx.z == 0)) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + ncol0 + c0 + j);
         }
@@ -194,7 +197,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
         }
-        if (p.out_f32) {
+        if (p.ksplit > 1) {
+          float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
+        } else if (p.out_f32) {
           float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -585,6 +592,23 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   if ((rc = make_weight_map(&p.w_map, wpack, (long long)k * k * n_out, in_c, BN))) return rc;
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.tiles_n), (unsigned)(n_out / BN), (unsigned)nphase);
   if (grid.x == 0) return VG_OK;
+  p.ksplit = 1;
+  p.k_per_split = p.phases[0].ntaps * p.k_chunks;
+  {
+    // few output tiles but a long reduction (the discriminator's Linear layers run here as 1x1
+    // convolutions on [B,1,1,C] tensors): split K over blockIdx.z, fp32 atomics into a zeroed output
+    const long long ctas = (long long)grid.x * grid.y;
+    const int total_kb = p.phases[0].ntaps * p.k_chunks;
+    if (nphase == 1 && p.out_f32 && colscale == nullptr && ctas * 2 <= num_sms() && total_kb >= 16) {
+      int ks = (int)std::min<long long>(cdiv(2LL * num_sms(), ctas), total_kb / 4);
+      if (ks > 1) {
+        p.k_per_split = (int)cdiv(total_kb, ks);
+        p.ksplit = (int)cdiv(total_kb, p.k_per_split);
+        grid.z = (unsigned)p.ksplit;
+        VG_CUDA(cudaMemsetAsync(out, 0, (size_t)d->n * out_h * out_w * n_out * sizeof(float), s));
+      }
+    }
+  }
   switch (BN) {
     case 64: return launch_conv<64, 4>(p, grid, s);
     case 128: return launch_conv<128, 3>(p, grid, s);

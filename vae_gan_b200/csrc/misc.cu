@@ -473,6 +473,16 @@ extern "C" int vg_linear_forward(const void* x, const void* w, const float* bias
   return VG_OK;
 }
 
+extern "C" int vg_lrelu_forward(const void* x, long long n, int dtype, float slope, void* y, vg_stream_t stream) {
+  VG_CHECK_ARG(x && y && n >= 0, "bad args");
+  VG_CHECK_ARG(dtype == VG_F32, "vg_lrelu_forward: fp32 only (head activations)");
+  if (n == 0) return VG_OK;
+  if (x != y) VG_CUDA(cudaMemcpyAsync(y, x, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
+  bias_lrelu_kernel<<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>((float*)y, nullptr, n, 1, slope);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
 extern "C" int vg_linear_dgrad(const void* dy, const void* w, int m, int n, int k, int dtype, void* dx, vg_stream_t stream) {
   VG_CHECK_ARG(dy && w && dx && m >= 0 && n > 0 && k > 0, "bad args");
   if (m == 0) return VG_OK;

@@ -584,6 +584,48 @@ class LinearFn(Function):
         return dx, dw, db, None, None
 
 
+class LeakyReluFn(Function):
+    """nn.LeakyReLU on the discriminator head's fp32 activations (README.md:475-481)."""
+
+    @staticmethod
+    def forward(ctx, x, slope):
+        x = x.contiguous() if not (x.is_contiguous() or is_act(x)) else x
+        y = torch.empty_like(x)
+        call("vg_lrelu_forward", ptr(x), x.numel(), _lib.VG_F32, float(slope), ptr(y), stream_ptr())
+        ctx.slope = slope
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        if dy.stride() != y.stride():
+            dy = dy.contiguous() if y.is_contiguous() else as_act(dy, torch.float32)
+        dx = torch.empty_like(y)
+        call("vg_lrelu_backward", ptr(dy), ptr(y), y.numel(), _lib.VG_F32, float(ctx.slope), ptr(dx), stream_ptr())
+        return dx, None
+
+
+def linear(x, weight, bias, slope, wdtype):
+    """leaky_relu(nn.Linear(x)).  On the bf16 path, layers whose sizes fit the tensor-core tiles run
+    as 1x1 convolutions on [B, C, 1, 1] activations through the tcgen05 kernels (forward with
+    split-K, dgrad, wgrad); everything else takes the CUDA-core GEMM."""
+    m, k = x.shape
+    n = weight.shape[0]
+    if wdtype == torch.bfloat16 and k % 64 == 0 and n % 64 == 0:
+        xa = to_act(x.view(m, k, 1, 1), torch.bfloat16)
+        wv = weight.view(n, k, 1, 1)
+        gb = getattr(weight, "_vg_grad_buf", None)
+        if gb is not None:
+            wv._vg_grad_buf = gb.view(n, k, 1, 1)      # wgrad accumulates straight into the flat buffer
+        y = conv(xa, wv, bias, geom=ConvGeom(1, 1, 0, False), out_dtype=torch.float32)
+        if slope != 1.0:
+            y = LeakyReluFn.apply(y, slope)
+        return y.view(m, n)
+    return LinearFn.apply(x, weight, bias, slope, wdtype)
+
+
 # ----------------------------------------------------------------------------------------------
 # reparameterisation and losses
 # ----------------------------------------------------------------------------------------------

@@ -319,10 +319,10 @@ class Discriminator(nn.Module):
             out = self.res_layers(out)
             out = VF.AvgPoolFlattenFn.apply(out, 4)
             wd = VF.config.compute_dtype
-            out = VF.LinearFn.apply(out, self.linear_1.weight, self.linear_1.bias, slope, wd)
-            out = VF.LinearFn.apply(out, self.linear_2.weight, self.linear_2.bias, slope, wd)
-            out = VF.LinearFn.apply(out, self.linear_3.weight, self.linear_3.bias, slope, wd)
-            out = VF.LinearFn.apply(out, self.linear_4.weight, self.linear_4.bias, 1.0, wd)
+            out = VF.linear(out, self.linear_1.weight, self.linear_1.bias, slope, wd)
+            out = VF.linear(out, self.linear_2.weight, self.linear_2.bias, slope, wd)
+            out = VF.linear(out, self.linear_3.weight, self.linear_3.bias, slope, wd)
+            out = VF.linear(out, self.linear_4.weight, self.linear_4.bias, 1.0, wd)
             return out
 
 
