@@ -32,13 +32,17 @@ __host__ __device__ inline RowMap make_rowmap(int c) {
 
 static inline bool vec_ok(int c) { return c % 8 == 0 && c / 8 <= kBnThreads; }
 
-static inline int grid_for(long long rows, int rpb, int iters_target = kUnroll * 2) {
+static inline int grid_for(long long rows, int rpb, int iters_target = kUnroll * 2, int blocks_per_sm = 8) {
   long long blocks = cdiv(rows, (long long)rpb * iters_target);
-  long long cap = (long long)num_sms() * 8;
+  long long cap = (long long)num_sms() * blocks_per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
+// kernels that end in a per-channel reduction: every block issues 2C same-address fp64 atomics, which
+// serialise in L2 - keep the block count at a small multiple of the SM count and give each block
+// more rows instead.
+constexpr int kReduceBlocksPerSm = 3;
 
 // 16-bit Philox keep decisions for 8 consecutive elements starting at linear index e0 (e0 % 8 == 0)
 __device__ __forceinline__ void keep8(const Philox& ph, unsigned long long e0, uint32_t thr16, bool keep[8]) {
@@ -283,7 +287,7 @@ __global__ void bn_act_fwd_scalar_kernel(const T* __restrict__ x, const float* _
 // backward: g = dy * drop' * lrelu'(a*x+b);  reduce: sum g, sum g*xhat;  apply: dx
 // ------------------------------------------------------------------------------------------
 template <typename T, bool DROP, bool APPLY>
-__global__ void __launch_bounds__(kBnThreads) bn_act_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(kBnThreads, 3) bn_act_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                                      const float* __restrict__ mean_rstd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                      BnK k, double* __restrict__ sums_out /* reduce */,
@@ -431,7 +435,7 @@ __global__ void bn_act_bwd_scalar_kernel(const T* __restrict__ dy, const T* __re
 // residual add: out = lrelu(bnA(a) + bnB(b)) (+ stats of out)
 // ------------------------------------------------------------------------------------------
 template <typename T, bool STATS>
-__global__ void __launch_bounds__(kBnThreads) bn_add_vec_kernel(const T* __restrict__ A, const float* __restrict__ mrA,
+__global__ void __launch_bounds__(kBnThreads, 3) bn_add_vec_kernel(const T* __restrict__ A, const float* __restrict__ mrA,
                                                                  const float* __restrict__ gA, const float* __restrict__ bA,
                                                                  const T* __restrict__ B, const float* __restrict__ mrB,
                                                                  const float* __restrict__ gB, const float* __restrict__ bB, BnK k,
@@ -624,7 +628,7 @@ extern "C" int vg_bn_stats(const void* x, const VgBnDesc* d, double* sums, vg_st
     long long rows = fold ? d->rows / 8 : d->rows;
     int cv = fold ? 8 : d->c;
     RowMap m = make_rowmap(cv);
-    int grid = grid_for(rows, m.rpb);
+    int grid = grid_for(rows, m.rpb, kUnroll * 2, kReduceBlocksPerSm);
     if (d->dtype == VG_BF16)
       bn_stats_vec_kernel<__nv_bfloat16><<<grid, kBnThreads, vec_smem(), s>>>((const __nv_bfloat16*)x, rows, d->c, fold, sums);
     else
@@ -714,7 +718,7 @@ static int bn_act_backward_t(const T* dy, const T* x, const float* mr, const flo
     long long rows = k.fold ? d->rows / 8 : d->rows;
     k.rows = rows;
     RowMap m = make_rowmap(k.fold ? 8 : d->c);
-    int grid = grid_for(rows, m.rpb, kUnroll);
+    int grid = grid_for(rows, m.rpb, kUnroll, APPLY ? 8 : kReduceBlocksPerSm);
     size_t sm = APPLY ? 0 : vec_smem();
     if (k.thr16)
       bn_act_bwd_vec_kernel<T, true, APPLY><<<grid, kBnThreads, sm, s>>>(dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
@@ -770,7 +774,7 @@ static int bn_add_t(const T* a, const float* mra, const float* ga, const float* 
     long long rows = k.fold ? d->rows / 8 : d->rows;
     k.rows = rows;
     RowMap m = make_rowmap(k.fold ? 8 : d->c);
-    int grid = grid_for(rows, m.rpb, kUnroll);
+    int grid = grid_for(rows, m.rpb, kUnroll, stats ? kReduceBlocksPerSm : 8);
     if (stats)
       bn_add_vec_kernel<T, true><<<grid, kBnThreads, vec_smem(), s>>>(a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
     else

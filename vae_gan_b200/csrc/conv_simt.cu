@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) conv_expand1_kernel(const TI* __restrict_
 //   a_mode = true : V on the coarse/output grid (Conv2d 1->C: V = dy, S = x),   S index = q*stride - pad + k
 //   a_mode = false: V on the input grid         (Conv2d C->1: V = x,  S = dy),  S index = (q + pad - k)/stride
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) wgrad_degenerate_kernel(const T* __restrict__ V, const T* __restrict__ S, int n, int hv,
+__global__ void __launch_bounds__(256, 2) wgrad_degenerate_kernel(const T* __restrict__ V, const T* __restrict__ S, int n, int hv,
                                                                int wv, int c, int hs, int ws, int kh, int kw, int stride, int pad,
                                                                bool a_mode, unsigned pix_per_block, float* __restrict__ dw) {
   extern __shared__ float sacc[];   // [taps * c]
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) wgrad_degenerate_kernel(const T* __restri
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[t][j] = 0.f;
   if (lane < lanes) {
-    constexpr int U = 4;
+    constexpr int U = 2;
     for (unsigned qb = p0 + lane; qb < p1; qb += U * lanes) {
       float v[U][VEC];
       // issue all the streaming loads of this batch first (memory-level parallelism)
@@ -515,7 +515,7 @@ int simt_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* d
     const long long npix = (long long)d->n * hv * wv;
     const int vec = (c % 8 == 0 && c / 8 <= 256) ? 8 : 1;
     VG_CHECK_ARG(c / vec <= 256, "degenerate wgrad supports up to 256 channel groups");
-    long long blocks = std::min<long long>(cdiv(npix, 1024), (long long)num_sms() * 2);
+    long long blocks = std::min<long long>(cdiv(npix, 1024), (long long)num_sms() * 4);
     unsigned ppb = (unsigned)cdiv(npix, blocks);
     blocks = cdiv(npix, ppb);
     size_t sm = (size_t)d->kh * d->kw * c * sizeof(float);

@@ -67,23 +67,27 @@ struct alignas(64) TcWgradParams {
 constexpr int kTcThreads = 256;
 constexpr int kABytes = 128 * 128;   // 128 rows x 64 bf16
 
-template <int BN, int STAGES>
+template <int BN, int MT, int STAGES>
 struct ConvSmem {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kBytes = STAGES * (kABytes + kBBytes) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 1) * 8 + 16 + 1024;
 };
 
 // ------------------------------------------------------------------------------------------
 // forward / dgrad implicit GEMM
 // ------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+// MT pixel tiles (128 rows each) per CTA share every weight tile: B traffic per FLOP drops by MT
+// (the implicit GEMM re-reads its operands from L2 for every tap, so it is L2-bandwidth bound
+// unless each staged byte feeds enough MMAs).
+template <int BN, int MT, int STAGES>
 __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int kBBytes = BN * 128;
+  constexpr int kAStage = MT * kABytes;
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * kABytes;
+  uint8_t* sB = smem + STAGES * kAStage;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * kBBytes);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
@@ -95,11 +99,18 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
   const int kb0 = p.ksplit > 1 ? (int)blockIdx.z * p.k_per_split : 0;
   const int kb1 = p.ksplit > 1 ? min(ntaps * p.k_chunks, kb0 + p.k_per_split) : ntaps * p.k_chunks;
   const int num_k = max(0, kb1 - kb0);
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x; t /= p.tiles_x;
-  const int ty = t % p.tiles_y;
-  const int tn = t / p.tiles_y;
-  const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int tile0 = blockIdx.x * MT;
+  const int nvalid = min(MT, total_tiles - tile0);
+  int x0s[MT], y0s[MT], n0s[MT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    int t = min(tile0 + i, total_tiles - 1);
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int tn = t / p.tiles_y;
+    x0s[i] = tx * p.TW; y0s[i] = ty * p.TH; n0s[i] = tn * p.TN;
+  }
   const int ncol0 = blockIdx.y * BN;
 
   if (warp == 0 && lane == 0) {
@@ -114,7 +125,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
     ptx::mbar_init(tmem_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc<BN>(tmem_slot);
+  constexpr int kTmemCols = (MT * BN < 32) ? 32 : MT * BN;
+  if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -130,8 +142,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
           const TcTap tap = ph.taps[tp];
           const CUtensorMap* im = &p.in_maps[tap.map];
           ptx::mbar_wait(&empty[stage], phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(&full[stage], kABytes + kBBytes);
-          ptx::tma_load_4d(sA + stage * kABytes, im, &full[stage], kc * 64, x0 + tap.dx, y0 + tap.dy, n0);
+          ptx::mbar_arrive_expect_tx(&full[stage], nvalid * kABytes + kBBytes);
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            if (m < nvalid)
+              ptx::tma_load_4d(sA + stage * kAStage + m * kABytes, im, &full[stage], kc * 64, x0s[m] + tap.dx, y0s[m] + tap.dy, n0s[m]);
           ptx::tma_load_2d(sB + stage * kBBytes, &p.w_map, &full[stage], kc * 64, tap.wrow + ncol0);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           if (++kc == p.k_chunks) { kc = 0; ++tp; }
@@ -145,13 +160,18 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
         for (int i = 0; i < num_k; ++i) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(sA + stage * kABytes);
+          const uint32_t a_addr = ptx::smem_u32(sA + stage * kAStage);
           const uint32_t b_addr = ptx::smem_u32(sB + stage * kBBytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
-            ptx::mma_bf16_ss(tmem_base, ad, bd, idesc, (i | k) != 0);
+          for (int m = 0; m < MT; ++m) {
+            if (m < nvalid) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = ptx::make_smem_desc(a_addr + m * kABytes + k * 32, 16, 1024);
+                const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
+                ptx::mma_bf16_ss(tmem_base + (uint32_t)(m * BN), ad, bd, idesc, (i | k) != 0);
+              }
+            }
           }
           ptx::mma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -167,55 +187,58 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
     const int xl = row & (p.TW - 1);
     const int yl = (row >> p.tw_log2) & (p.TH - 1);
     const int nl = row >> (p.tw_log2 + p.th_log2);
-    const int gx = x0 + xl, gy = y0 + yl, gn = n0 + nl;
-    const bool valid = gx < p.gw && gy < p.gh && gn < p.gn;
-    const long long opix = ((long long)gn * p.OH + (long long)gy * p.os + ph.oy_off) * p.OW + (long long)gx * p.os + ph.ox_off;
     if (num_k > 0) {
       ptx::mbar_wait(tmem_full, 0);
       ptx::tc_fence_after();
     }
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      if (num_k > 0) {
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        ptx::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-      if (valid && !(p.ksplit > 1 && num_k == 0)) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr && (p.ksplit <= 1 || blockIdx.z == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + ncol0 + c0 + j);
-        }
-        if (p.colscale != nullptr) {
-          const float* cs = p.colscale + (long long)gn * p.n_out + ncol0 + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
-        }
-        if (p.ksplit > 1) {
-          float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
-        } else if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int m = 0; m < nvalid; ++m) {
+      const int gx = x0s[m] + xl, gy = y0s[m] + yl, gn = n0s[m] + nl;
+      const bool valid = gx < p.gw && gy < p.gh && gn < p.gn;
+      const long long opix = ((long long)gn * p.OH + (long long)gy * p.os + ph.oy_off) * p.OW + (long long)gx * p.os + ph.ox_off;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        if (num_k > 0) {
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * BN + c0), r);
+          ptx::tmem_ld_wait();
         } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.n_out + ncol0 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t w[4];
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (valid && !(p.ksplit > 1 && num_k == 0)) {
+          float v[32];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * i], v[j + 2 * i + 1]);
-              w[i] = *reinterpret_cast<uint32_t*>(&h);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr && (p.ksplit <= 1 || blockIdx.z == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + ncol0 + c0 + j);
+          }
+          if (p.colscale != nullptr) {
+            const float* cs = p.colscale + (long long)gn * p.n_out + ncol0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
+          }
+          if (p.ksplit > 1) {
+            float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
+          } else if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.n_out + ncol0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t w[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * i], v[j + 2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(o + j) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            *reinterpret_cast<uint4*>(o + j) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }
@@ -223,7 +246,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc<BN>(tmem_base);
+  if (warp == 2) ptx::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -473,14 +496,16 @@ bool tc_wgrad_supported(const VgConvDesc* d) {
   return get_encode() != nullptr;
 }
 
-template <int BN, int STAGES>
+template <int BN, int MT, int STAGES>
 static int launch_conv(const TcConvParams& p, dim3 grid, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    VG_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<BN, STAGES>::kBytes));
+    VG_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 ConvSmem<BN, MT, STAGES>::kBytes));
     attr_done = true;
   }
-  tc_conv_kernel<BN, STAGES><<<grid, kTcThreads, ConvSmem<BN, STAGES>::kBytes, s>>>(p);
+  grid.x = (unsigned)cdiv(grid.x, MT);
+  tc_conv_kernel<BN, MT, STAGES><<<grid, kTcThreads, ConvSmem<BN, MT, STAGES>::kBytes, s>>>(p);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -542,6 +567,7 @@ static int pick_bn(int n_out) {
     forced = e ? atoi(e) : 0;
   }
   if (forced && n_out % forced == 0) return forced;
+  if (n_out % 256 == 0) return 256;
   if (n_out % 128 == 0) return 128;
   return 64;
 }
@@ -609,10 +635,20 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
       }
     }
   }
+  // several pixel tiles per CTA (sharing the weight tile) when there are enough tiles to keep
+  // every SM busy; single-tile CTAs (two resident per SM) for small problems and split-K
+  // Measured on B200 (scripts/sweep_conv.py, batch 64): with one CTA per SM the epilogue of a
+  // multi-tile CTA is no longer hidden behind a co-resident CTA's main loop, and 128->128 @96 drops
+  // from 897 to 769 TFLOP/s.  Kept opt-in (VG_TC_MT=1) until the kernel is persistent with a
+  // double-buffered TMEM accumulator.
+  static int mt_on = -1;
+  if (mt_on < 0) { const char* e = getenv("VG_TC_MT"); mt_on = (e && atoi(e)) ? 1 : 0; }
+  const long long ctas1 = (long long)grid.x * grid.y * grid.z;
+  const bool big = mt_on && p.ksplit == 1 && ctas1 >= 6LL * num_sms();
   switch (BN) {
-    case 64: return launch_conv<64, 4>(p, grid, s);
-    case 128: return launch_conv<128, 3>(p, grid, s);
-    case 256: return launch_conv<256, 4>(p, grid, s);
+    case 64: return big ? launch_conv<64, 4, 3>(p, grid, s) : launch_conv<64, 1, 4>(p, grid, s);
+    case 128: return big ? launch_conv<128, 2, 4>(p, grid, s) : launch_conv<128, 1, 3>(p, grid, s);
+    case 256: return launch_conv<256, 1, 4>(p, grid, s);
     default: set_error("unsupported BN %d", BN); return VG_EUNSUPPORTED;
   }
 }
@@ -649,8 +685,22 @@ int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, 
   const int m_tiles = (p.ntaps * p.cs_chunks + 1) / 2;
   const int n_tiles = cu / (NB * 64);
   if (p.n_boxes == 0) return VG_OK;
-  long long want = std::max<long long>(1, cdiv(2LL * num_sms(), (long long)m_tiles * n_tiles));
-  long long splits = std::min<long long>(want, std::max<long long>(1, p.n_boxes / 4));
+  // one CTA per SM (160-192 KB of smem): pick the split count that fills whole waves
+  const long long tiles = (long long)m_tiles * n_tiles;
+  long long splits = 1;
+  {
+    double best = -1.0;
+    const long long max_splits = std::max<long long>(1, p.n_boxes / 4);
+    for (long long waves = 1; waves <= 4; ++waves) {
+      long long sp = std::max<long long>(1, std::min<long long>((waves * num_sms()) / tiles, max_splits));
+      long long bps = cdiv(p.n_boxes, sp);
+      sp = cdiv(p.n_boxes, bps);
+      const long long ctas = tiles * sp;
+      const double eff = (double)ctas / (double)(cdiv(ctas, num_sms()) * num_sms());   // wave quantisation
+      const double score = eff - 0.02 * (double)sp / (double)max_splits - (ctas < num_sms() ? 0.5 : 0.0);
+      if (score > best) { best = score; splits = sp; }
+    }
+  }
   p.boxes_per_split = (int)cdiv(p.n_boxes, splits);
   splits = cdiv(p.n_boxes, p.boxes_per_split);
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
