@@ -80,9 +80,13 @@ int vg_conv_forward(const VgConvDesc* d, const void* x, const void* pack_kn, con
 int vg_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pack_kn, const void* pack_nk,
                   void* dx, vg_stream_t stream);
 /* dw += x (*) dy in torch's weight layout, fp32 (caller zeroes dw for a fresh gradient);
- * dbias (nullable) += per-channel sum of dy. */
+ * dbias (nullable) += per-channel sum of dy.
+ * workspace (nullable): float[kh*kw*c_in*c_out] scratch.  When given, the tensor-core kernel
+ * accumulates its split-K partial sums into it with coalesced 16-byte vector reductions and a
+ * second kernel adds the result into dw; without it the partial sums go straight into dw with
+ * scalar atomics (slower).  Its contents are undefined afterwards. */
 int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias,
-                  vg_stream_t stream);
+                  float* workspace, vg_stream_t stream);
 
 /* ---- BatchNorm2d (+LeakyReLU +Dropout) fused family: README.md:143,152,159,166,169,172,
  *      144/180/190 (nn.Dropout), 376,382,388,394,442 --------------------------------------- */

@@ -52,10 +52,11 @@ for name, cin, cout, h, k, st, pad, tr in SHAPES:
     dy = VF.as_act(torch.randn(B, cout, ho, wo, generator=g).to(dev), torch.bfloat16)
     dx = torch.empty_like(x)
     dw = torch.zeros_like(w)
+    wsb = torch.empty(w.numel(), dtype=torch.float32, device=dev)
     flops = 2.0 * B * (h * h if tr else ho * wo) * cin * cout * k * k
     t_f = timeit(lambda: _lib.call("vg_conv_forward", C.byref(d), x.data_ptr(), pk.data_ptr(), pn.data_ptr(), None, None, y.data_ptr(), None, s))
     t_d = timeit(lambda: _lib.call("vg_conv_dgrad", C.byref(d), dy.data_ptr(), pk.data_ptr(), pn.data_ptr(), dx.data_ptr(), s))
-    t_w = timeit(lambda: _lib.call("vg_conv_wgrad", C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), None, s))
+    t_w = timeit(lambda: _lib.call("vg_conv_wgrad", C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), None, wsb.data_ptr(), s))
     tot["fwd"] += t_f; tot["dgrad"] += t_d; tot["wgrad"] += t_w
     print(f"{name:26s} {flops/1e9:7.1f} GF  fwd {t_f*1e3:7.1f} us {flops/t_f/1e9:7.0f} TF/s | dgrad {t_d*1e3:7.1f} us {flops/t_d/1e9:7.0f} | wgrad {t_w*1e3:7.1f} us {flops/t_w/1e9:7.0f}")
 print("sum ms", {k: round(v, 3) for k, v in tot.items()})

@@ -50,7 +50,7 @@ _PROTOS = {
     "vg_conv_pack_weights": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "vg_conv_forward": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "vg_conv_dgrad": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "vg_conv_wgrad": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vg_conv_wgrad": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "vg_bn_stats": (c_int, [c_vp, C.POINTER(VgBnDesc), c_vp, c_vp]),
     "vg_bn_finalize": (c_int, [c_vp, c_d, c_int, c_f, c_f, c_vp, c_vp, c_vp, c_vp]),
     "vg_bn_eval_stats": (c_int, [c_vp, c_vp, c_int, c_f, c_vp, c_vp]),

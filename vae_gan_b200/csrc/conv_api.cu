@@ -13,7 +13,7 @@ bool tc_conv_supported(const VgConvDesc*, bool dgrad);
 bool tc_wgrad_supported(const VgConvDesc*);
 int tc_conv_run(const VgConvDesc*, bool dgrad, const void* in, const void* wpack, const float* bias, const float* colscale, void* out,
                 int out_dtype, cudaStream_t);
-int tc_wgrad_run(const VgConvDesc*, const void* x, const void* dy, float* dw, cudaStream_t);
+int tc_wgrad_run(const VgConvDesc*, const void* x, const void* dy, float* dw, float* workspace, cudaStream_t);
 }  // namespace vg
 
 using namespace vg;
@@ -79,14 +79,15 @@ extern "C" int vg_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pa
   return simt_conv_dgrad(d, dy, pack_kn, dx, s);
 }
 
-extern "C" int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias, vg_stream_t stream) {
+extern "C" int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias, float* workspace,
+                             vg_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
   if (d->n == 0) return VG_OK;
   VG_CHECK_ARG(x && dy && dw, "null pointer");
   cudaStream_t s = as_stream(stream);
   if (tc_wgrad_supported(d))
-    rc = tc_wgrad_run(d, x, dy, dw, s);
+    rc = tc_wgrad_run(d, x, dy, dw, workspace, s);
   else
     rc = simt_conv_wgrad(d, x, dy, dw, s);
   if (rc) return rc;

@@ -61,6 +61,7 @@ struct alignas(64) TcWgradParams {
   int ntaps, cs_chunks, cs, cu;
   int tiles_x, tiles_y, tiles_n, TW, TH, TN;
   int n_boxes, boxes_per_split;
+  int packed;    // 1: dw is the packed scratch [tap][c_s][c_u] (vector reductions); 0: torch layout [c_u][c_s][tap]
   float* dw;
 };
 
@@ -250,6 +251,249 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// persistent variant: one CTA per SM loops over work items (phase|k-split, N tile, group of MT
+// pixel tiles); the TMEM accumulator is double-buffered so the epilogue of item i overlaps the
+// main loop of item i+1, and the MT pixel tiles of an item share every staged weight tile.
+// ------------------------------------------------------------------------------------------
+template <int BN, int MT, int STAGES>
+struct ConvPersistSmem {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <int BN, int MT, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __grid_constant__ TcConvParams p, int n_ntiles,
+                                                                         int n_groups, int n_z, int n_work) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int kBBytes = BN * 128;
+  constexpr int kAStage = MT * kABytes;
+  constexpr int kAccCols = MT * BN;
+  constexpr int kTmemCols = 2 * kAccCols;
+  static_assert(kTmemCols <= 512 && kTmemCols >= 32, "TMEM budget");
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kAStage;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * kBBytes);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;       // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.w_map);
+    ptx::prefetch_tmap(&p.in_maps[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&acc_full[a], 1);
+      ptx::mbar_init(&acc_empty[a], 4);      // one arrival per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> (z, n tile, pixel-tile group); groups vary fastest so that concurrently running
+  // CTAs stream the same weight tile (L2 reuse) over neighbouring pixels
+  auto decode = [&](int w, int& z, int& nt, int& g) {
+    const int per_z = n_ntiles * n_groups;
+    z = w / per_z;
+    const int r = w - z * per_z;
+    nt = r / n_groups;
+    g = r - nt * n_groups;
+  };
+  auto k_range = [&](int z, const TcPhase& ph, int& kb0, int& kb1) {
+    const int total = ph.ntaps * p.k_chunks;
+    if (p.ksplit > 1) { kb0 = z * p.k_per_split; kb1 = min(total, kb0 + p.k_per_split); }
+    else { kb0 = 0; kb1 = total; }
+    if (kb1 < kb0) kb1 = kb0;
+  };
+  auto tile_origin = [&](int t, int& x0, int& y0, int& n0) {
+    t = min(t, total_tiles - 1);
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int tn = t / p.tiles_y;
+    x0 = tx * p.TW; y0 = ty * p.TH; n0 = tn * p.TN;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        int z, nt, g;
+        decode(w, z, nt, g);
+        const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : z];
+        int kb0, kb1;
+        k_range(z, ph, kb0, kb1);
+        if (kb1 == kb0) continue;
+        const int tile0 = g * MT;
+        const int nvalid = min(MT, total_tiles - tile0);
+        int x0s[MT], y0s[MT], n0s[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) tile_origin(tile0 + m, x0s[m], y0s[m], n0s[m]);
+        const int ncol0 = nt * BN;
+        int tp = kb0 / p.k_chunks, kc = kb0 % p.k_chunks;
+        for (int i = kb0; i < kb1; ++i) {
+          const TcTap tap = ph.taps[tp];
+          const CUtensorMap* im = &p.in_maps[tap.map];
+          ptx::mbar_wait(&empty[stage], phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full[stage], nvalid * kABytes + kBBytes);
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            if (m < nvalid)
+              ptx::tma_load_4d(sA + stage * kAStage + m * kABytes, im, &full[stage], kc * 64, x0s[m] + tap.dx, y0s[m] + tap.dy, n0s[m]);
+          ptx::tma_load_2d(sB + stage * kBBytes, &p.w_map, &full[stage], kc * 64, tap.wrow + ncol0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++kc == p.k_chunks) { kc = 0; ++tp; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;                       // number of accumulator uses so far
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        int z, nt, g;
+        decode(w, z, nt, g);
+        const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : z];
+        int kb0, kb1;
+        k_range(z, ph, kb0, kb1);
+        if (kb1 == kb0) continue;
+        const int nvalid = min(MT, total_tiles - g * MT);
+        const int as = it & 1;
+        ptx::mbar_wait(&acc_empty[as], (uint32_t)(((it >> 1) & 1) ^ 1));
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(as * kAccCols);
+        for (int i = kb0; i < kb1; ++i) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(sA + stage * kAStage);
+          const uint32_t b_addr = ptx::smem_u32(sB + stage * kBBytes);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            if (m < nvalid) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = ptx::make_smem_desc(a_addr + m * kABytes + k * 32, 16, 1024);
+                const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
+                ptx::mma_bf16_ss(acc + (uint32_t)(m * BN), ad, bd, idesc, (i > kb0) || (k > 0));
+              }
+            }
+          }
+          ptx::mma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(&acc_full[as]);
+        ++it;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int xl = row & (p.TW - 1);
+    const int yl = (row >> p.tw_log2) & (p.TH - 1);
+    const int nl = row >> (p.tw_log2 + p.th_log2);
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      int z, nt, g;
+      decode(w, z, nt, g);
+      const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : z];
+      int kb0, kb1;
+      k_range(z, ph, kb0, kb1);
+      const bool has_k = kb1 > kb0;
+      if (!has_k && p.ksplit > 1) continue;          // empty k-split: contributes nothing
+      const int tile0 = g * MT;
+      const int nvalid = min(MT, total_tiles - tile0);
+      const int ncol0 = nt * BN;
+      const int as = it & 1;
+      if (has_k) {
+        ptx::mbar_wait(&acc_full[as], (uint32_t)((it >> 1) & 1));
+        ptx::tc_fence_after();
+      }
+      const uint32_t acc = tmem_base + (uint32_t)(as * kAccCols) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int m = 0; m < nvalid; ++m) {
+        int x0, y0, n0;
+        tile_origin(tile0 + m, x0, y0, n0);
+        const int gx = x0 + xl, gy = y0 + yl, gn = n0 + nl;
+        const bool valid = gx < p.gw && gy < p.gh && gn < p.gn;
+        const long long opix = ((long long)gn * p.OH + (long long)gy * p.os + ph.oy_off) * p.OW + (long long)gx * p.os + ph.ox_off;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          if (has_k) {
+            ptx::tmem_ld_32x32(acc + (uint32_t)(m * BN + c0), r);
+            ptx::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias != nullptr && (p.ksplit <= 1 || z == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + ncol0 + c0 + j);
+            }
+            if (p.colscale != nullptr) {
+              const float* cs = p.colscale + (long long)gn * p.n_out + ncol0 + c0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
+            }
+            if (p.ksplit > 1) {
+              float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
+            } else if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.n_out + ncol0 + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t wv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * i], v[j + 2 * i + 1]);
+                  wv[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(o + j) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+              }
+            }
+          }
+        }
+      }
+      if (has_k) {
+        // this warp is done reading accumulator stage `as`: hand it back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
+        ++it;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
 // weight gradient
 // ------------------------------------------------------------------------------------------
 template <int NB, int STAGES>
@@ -362,10 +606,20 @@ __global__ void __launch_bounds__(kTcThreads) tc_wgrad_kernel(const __grid_const
       ptx::tmem_ld_wait();
       if (row_valid) {
         const int cu0 = blockIdx.y * BN + c0;
+        if (p.packed) {
+          // 32 consecutive c_u of one (tap, c_s) row: eight 16-byte vector reductions
+          float* dst = p.dw + ((long long)tap * p.cs + cs) * p.cu + cu0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float* dst = p.dw + ((long long)(cu0 + j) * p.cs + cs) * p.ntaps + tap;
-          atomicAdd(dst, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+                         "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float* dst = p.dw + ((long long)(cu0 + j) * p.cs + cs) * p.ntaps + tap;
+            atomicAdd(dst, __uint_as_float(r[j]));
+          }
         }
       }
     }
@@ -373,6 +627,28 @@ __global__ void __launch_bounds__(kTcThreads) tc_wgrad_kernel(const __grid_const
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+}
+
+// dw[cu][cs][tap] += ws[tap][cs][cu]  (32x32 smem-tile transpose between cu and r = cs*taps+tap)
+__global__ void __launch_bounds__(256) wgrad_unpack_kernel(const float* __restrict__ ws, int cu_n, int cs_n, int taps, float* __restrict__ dw) {
+  __shared__ float tile[32][33];
+  const int R = cs_n * taps;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, cu = c0 + tx;
+    float v = 0.f;
+    if (r < R && cu < cu_n) {
+      const int cs = r / taps, tap = r - cs * taps;
+      v = ws[((long long)tap * cs_n + cs) * cu_n + cu];
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int cu = c0 + i, r = r0 + tx;
+    if (cu < cu_n && r < R) dw[(long long)cu * R + r] += tile[tx][i];
+  }
 }
 
 // ==========================================================================================
@@ -506,6 +782,25 @@ static int launch_conv(const TcConvParams& p, dim3 grid, cudaStream_t s) {
   }
   grid.x = (unsigned)cdiv(grid.x, MT);
   tc_conv_kernel<BN, MT, STAGES><<<grid, kTcThreads, ConvSmem<BN, MT, STAGES>::kBytes, s>>>(p);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+template <int BN, int MT, int STAGES>
+static int launch_conv_persist(const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    VG_CUDA(cudaFuncSetAttribute(tc_conv_persist_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 ConvPersistSmem<BN, MT, STAGES>::kBytes));
+    attr_done = true;
+  }
+  const int n_groups = (int)cdiv(grid.x, MT);
+  const int n_ntiles = (int)grid.y;
+  const int n_z = (int)grid.z;
+  const long long n_work = (long long)n_groups * n_ntiles * n_z;
+  const int ctas = (int)std::min<long long>(n_work, num_sms());
+  tc_conv_persist_kernel<BN, MT, STAGES><<<ctas, kTcThreads, ConvPersistSmem<BN, MT, STAGES>::kBytes, s>>>(p, n_ntiles, n_groups, n_z,
+                                                                                                          (int)n_work);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -645,6 +940,22 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   if (mt_on < 0) { const char* e = getenv("VG_TC_MT"); mt_on = (e && atoi(e)) ? 1 : 0; }
   const long long ctas1 = (long long)grid.x * grid.y * grid.z;
   const bool big = mt_on && p.ksplit == 1 && ctas1 >= 6LL * num_sms();
+  static int persist = -1;
+  if (persist < 0) { const char* e = getenv("VG_TC_PERSIST"); persist = e ? atoi(e) : 1; }
+  static int mt_min = -1;
+  if (mt_min < 0) { const char* e = getenv("VG_TC_MT_MIN"); mt_min = e ? atoi(e) : 6; }
+  if (persist && ctas1 >= 2LL * num_sms()) {
+    // enough work for several items per SM: persistent CTAs with a double-buffered accumulator; for
+    // N tiles below 256 only when there is enough work to let MT pixel tiles share each staged
+    // weight tile (measured: a persistent single-tile CTA loses to two co-resident one-shot CTAs)
+    const bool mt = ctas1 >= (long long)mt_min * num_sms();
+    switch (BN) {
+      case 64: if (mt) return launch_conv_persist<64, 4, 3>(p, grid, s); break;
+      case 128: if (mt) return launch_conv_persist<128, 2, 4>(p, grid, s); break;
+      case 256: return launch_conv_persist<256, 1, 4>(p, grid, s);
+      default: break;
+    }
+  }
   switch (BN) {
     case 64: return big ? launch_conv<64, 4, 3>(p, grid, s) : launch_conv<64, 1, 4>(p, grid, s);
     case 128: return big ? launch_conv<128, 2, 4>(p, grid, s) : launch_conv<128, 1, 3>(p, grid, s);
@@ -653,7 +964,7 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   }
 }
 
-int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, cudaStream_t s) {
+int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* workspace, cudaStream_t s) {
   TcWgradParams p;
   memset(&p, 0, sizeof(p));
   // dw[cu][cs][tap] += sum_q U[q][cu] * S[q*stride - pad + k][cs]
@@ -670,7 +981,10 @@ int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, 
   choose_box(wu, hu, d->n, 64, &p.TW, &p.TH, &p.TN);
   p.tiles_x = (int)cdiv(wu, p.TW); p.tiles_y = (int)cdiv(hu, p.TH); p.tiles_n = (int)cdiv(d->n, p.TN);
   p.n_boxes = p.tiles_x * p.tiles_y * p.tiles_n;
-  p.dw = dw;
+  p.packed = workspace != nullptr;
+  p.dw = p.packed ? workspace : dw;
+  const size_t welems = (size_t)k * k * cs * cu;
+  if (p.packed) VG_CUDA(cudaMemsetAsync(workspace, 0, welems * sizeof(float), s));
   int rc;
   if (st == 2) {
     for (int py = 0; py < 2; ++py)
@@ -705,10 +1019,15 @@ int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, 
   splits = cdiv(p.n_boxes, p.boxes_per_split);
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
   switch (NB) {
-    case 1: return launch_wgrad<1, 6>(p, grid, s);
-    case 2: return launch_wgrad<2, 5>(p, grid, s);
-    default: return launch_wgrad<4, 4>(p, grid, s);
+    case 1: rc = launch_wgrad<1, 6>(p, grid, s); break;
+    case 2: rc = launch_wgrad<2, 5>(p, grid, s); break;
+    default: rc = launch_wgrad<4, 4>(p, grid, s); break;
   }
+  if (rc || !p.packed) return rc;
+  dim3 ug((unsigned)cdiv((long long)cs * p.ntaps, 32), (unsigned)cdiv(cu, 32));
+  wgrad_unpack_kernel<<<ug, 256, 0, s>>>(workspace, cu, cs, p.ntaps, dw);
+  VG_LAUNCHED();
+  return VG_OK;
 }
 
 }  // namespace vg

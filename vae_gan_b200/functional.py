@@ -33,6 +33,7 @@ class _Config:
     compute_dtype = torch.bfloat16
     process_group = None          # data-parallel group for SyncBN statistics (None = single GPU)
     sample_offset = 0             # global index of this rank's first sample
+    defer_num_batches_tracked = False   # the trainer bumps every BN's counter with ONE foreach kernel per step
 
 
 config = _Config()
@@ -91,8 +92,12 @@ def _world():
     return dist.get_world_size(pg)
 
 
+import os as _os
+_DIAG_NO_SYNCBN = bool(int(_os.environ.get("VG_DIAG_NO_SYNCBN", "0")))      # timing diagnosis only (wrong numerics)
+
+
 def _allreduce_sums(t: torch.Tensor):
-    if config.process_group is not None and _world() > 1:
+    if config.process_group is not None and _world() > 1 and not _DIAG_NO_SYNCBN:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=config.process_group)
 
 
@@ -262,7 +267,8 @@ class ConvFn(Function):
             dwh = ctx.wbuf if direct else zeros_f32(ctx.wshape, x.device)
             if ctx.has_bias:
                 db = ctx.bbuf if ctx.bbuf is not None else zeros_f32((d.c_out,), x.device)
-            call("vg_conv_wgrad", C.byref(d), ptr(x), ptr(dy), ptr(dwh), ptr(db), s)
+            ws = torch.empty(dwh.numel(), dtype=torch.float32, device=x.device) if x.dtype == torch.bfloat16 else None
+            call("vg_conv_wgrad", C.byref(d), ptr(x), ptr(dy), ptr(dwh), ptr(db), ptr(ws), s)
             if ctx.has_sn:
                 rows, cols = ctx.wshape[0], dwh.numel() // ctx.wshape[0]
                 dw = ctx.wbuf if fused else zeros_f32(ctx.wshape, x.device)
@@ -379,7 +385,7 @@ class BnActFn(Function):
 def bn_act(x, bn, *, slope=1.0, drop_p=0.0, training=True, sums=None, out_colscale=None, tag=""):
     """`bn` is an nn.BatchNorm2d used as a parameter/buffer container."""
     offset = rng.next_site(tag, tuple(x.shape)) if (training and drop_p > 0) else 0
-    if training and bn.track_running_stats:
+    if training and bn.track_running_stats and not config.defer_num_batches_tracked:
         bn.num_batches_tracked += 1
     return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, sums, slope, drop_p, offset,
                          training, out_colscale)
@@ -447,7 +453,7 @@ def bn_add(a, b, bn_a=None, bn_b=None, *, slope=1.0, training=True, sums_a=None,
     def unpack(bn):
         if bn is None:
             return None, None, None, None
-        if training and bn.track_running_stats:
+        if training and bn.track_running_stats and not config.defer_num_batches_tracked:
             bn.num_batches_tracked += 1
         return bn.weight, bn.bias, bn.running_mean, bn.running_var
 

@@ -84,6 +84,9 @@ class VaeGanTrainer:
         self.local_batch = local_batch
         if process_group is not None:
             VF.config.process_group = process_group
+        # num_batches_tracked of every BatchNorm: G's are used once per iteration, D's three times
+        self._nbt_g = [m.num_batches_tracked for m in generator.modules() if isinstance(m, nn.BatchNorm2d)]
+        self._nbt_d = [m.num_batches_tracked for m in discriminator.modules() if isinstance(m, nn.BatchNorm2d)]
 
     # ------------------------------------------------------------------------------------------
     def _opt(self, flat: FlatParams, clamp: float):
@@ -91,6 +94,9 @@ class VaeGanTrainer:
                           weight_decay=self.weight_decay, clamp=clamp, step_tensor=self.opt_step)
 
     def _allreduce(self, flat: FlatParams):
+        import os
+        if os.environ.get("VG_DIAG_NO_GRAD_AR", "0") == "1":     # timing diagnosis only (wrong numerics)
+            return
         if self.world > 1:
             dist.all_reduce(flat.g, op=dist.ReduceOp.SUM, group=self.pg)
 
@@ -102,6 +108,17 @@ class VaeGanTrainer:
         VF.rng.reset_sites()
         VF.rng.advance(dev)
         VF.call("vg_counter_add", VF.ptr(self.opt_step), 1, VF.stream_ptr())
+        if self.G.training and self._nbt_g:
+            torch._foreach_add_(self._nbt_g, 1)
+        if self.D.training and self._nbt_d:
+            torch._foreach_add_(self._nbt_d, 3)
+        VF.config.defer_num_batches_tracked = True
+        try:
+            return self._iteration(real, adv_mode)
+        finally:
+            VF.config.defer_num_batches_tracked = False
+
+    def _iteration(self, real, adv_mode):
         with M._scope():
             with M._scope():          # depth >= 1 everywhere: modules hand over internal activations
                 # ---- generator forward (graph kept for the G step) ----
