@@ -201,6 +201,43 @@ def roofline_probe(dev, batch: int, peaks):
             "peak_source": f"{peaks['source']} bf16 burst (kernel timed alone)"}
 
 
+def run_decode_sweep(args):
+    """BASELINE.json config 5: decoder-only sampling, z ~ N(0, I) of shape (B, 256, 24, 24) -> 96x96 image,
+    eval mode (BatchNorm running statistics, no dropout), batch 1..4096 on one GPU, CUDA-graph replay."""
+    import vae_gan_b200 as V
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    rows = []
+    with V.compute_dtype(torch.bfloat16), torch.no_grad():
+        G, _ = V.build_vae_gan(feature_size=FEATURE, image_size=IMAGE)
+        G = G.to(dev).eval()
+        G.set_is_training(False)
+        for B in (1, 4, 16, 64, 256, 1024, 4096):
+            z = torch.randn(B, 256, IMAGE // 4, IMAGE // 4, device=dev)
+            for _ in range(3):
+                y = G.decode(z)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                y = G.decode(z)
+            for _ in range(3):
+                graph.replay()
+            iters = 20 if B <= 1024 else 8
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            rows.append({"batch": B, "ms": round(ms, 4), "images_per_s": round(B / ms * 1e3, 1),
+                         "tflops": round(3.796e9 * B / (ms * 1e-3) / 1e12, 1)})
+            del graph
+    print(json.dumps({"metric": "decode_images_per_sec", "unit": "images/s", "n_gpus": 1, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": "decoder-only sampling sweep, latent (B,256,24,24) -> 1x96x96, eval mode"},
+                      "sweep": rows, "value": max(r["images_per_s"] for r in rows), "higher_is_better": True}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,10 +248,20 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--fp32", action="store_true", help="run the fp32 parity path instead of bf16")
+    ap.add_argument("--workload", default="train", choices=["train", "cfg4", "decode"],
+                    help="train: BASELINE metric (96x96, fs 64); cfg4: 256x256, widths x2; decode: config-5 sampling sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.workload == "decode":
+        run_decode_sweep(args)
+        return
+    global IMAGE, FEATURE, GFLOP_PER_IMG_STEP
+    if args.workload == "cfg4":
+        IMAGE, FEATURE, GFLOP_PER_IMG_STEP = 256, 128, 3621.5
+        if args.global_batch == 256:
+            args.global_batch = 16 * max(1, int(os.environ.get("WORLD_SIZE", "1")))
 
     import torch.distributed as dist
     import vae_gan_b200 as V

@@ -184,6 +184,9 @@ CONV_CASES_F32 = [
     (8, 16, 1, 2, 0, False, 2, 8),
     (16, 8, 1, 1, 0, False, 2, 7),
     (16, 24, 3, 1, 1, False, 2, 6),
+    (1, 64, 3, 1, 1, False, 2, 16),        # width % 8 == 0: strip kernels
+    (64, 1, 3, 1, 1, False, 2, 16),
+    (1, 16, 3, 1, 1, False, 3, 8),
 ]
 CONV_CASES_TC = [
     (64, 64, 3, 1, 1, False, 2, 16),
@@ -197,6 +200,8 @@ CONV_CASES_TC = [
     (128, 256, 1, 2, 0, False, 2, 16),
     (256, 256, 3, 1, 1, False, 1, 12),
     (512, 512, 3, 1, 1, False, 2, 6),
+    (64, 1, 3, 1, 1, False, 2, 16),        # single output channel through the tensor-core kernel
+    (64, 1, 3, 1, 1, False, 3, 24),
 ]
 
 

@@ -51,7 +51,7 @@ extern "C" int vg_conv_forward(const VgConvDesc* d, const void* x, const void* p
   if (d->n == 0) return VG_OK;   // empty batch: nothing to do (pointers of empty tensors may be null)
   VG_CHECK_ARG(x && y && pack_kn && pack_nk, "null pointer");
   cudaStream_t s = as_stream(stream);
-  if (tc_conv_supported(d, false))
+  if (tc_conv_supported(d, false) && !(d->c_out == 1 && colscale != nullptr))
     rc = tc_conv_run(d, false, x, pack_kn, bias, colscale, y, d->out_dtype, s);
   else
     rc = simt_conv_forward(d, x, pack_nk, bias, colscale, y, s);

@@ -244,6 +244,144 @@ __global__ void __launch_bounds__(256) conv_expand1_kernel(const TI* __restrict_
   }
 }
 
+// ---- strip variants (3x3, stride 1, pad 1, width % 8 == 0): a thread walks 8 consecutive pixels of a
+// row and keeps the 3x10 window of the single-channel tensor in registers, so per pixel it issues the
+// 72 FMAs it must plus ~10 other instructions (the per-pixel kernels above spend ~4x that on index math,
+// bounds checks and reloading the window).
+template <typename T>
+__device__ __forceinline__ void load_window_3x10(const T* __restrict__ S, int n, int h, int w, int oy, int ox0, float (&win)[3][10]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = oy - 1 + r;
+    const bool rowok = iy >= 0 && iy < h;
+    const T* rp = S + ((long long)n * h + (rowok ? iy : 0)) * w;
+#pragma unroll
+    for (int c = 0; c < 10; ++c) {
+      const int ix = ox0 - 1 + c;
+      win[r][c] = (rowok && ix >= 0 && ix < w) ? to_f32(rp[ix]) : 0.f;
+    }
+  }
+}
+
+template <typename TI, typename TO, bool FLIP>
+__global__ void __launch_bounds__(256) conv_expand1_strip_kernel(const TI* __restrict__ in, const TI* __restrict__ W,
+                                                                 const float* __restrict__ bias, const float* __restrict__ colscale,
+                                                                 ConvGeom g, TO* __restrict__ out) {
+  const unsigned cog = (unsigned)g.co / 8;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned nthr = gridDim.x * blockDim.x;
+  const int cg = (int)(tid % cog);
+  float w[9][8], b[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    Vec8<TI> wv;
+    wv.load(W + (long long)(FLIP ? 8 - t : t) * g.co + cg * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[t][j] = wv.v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = bias ? bias[cg * 8 + j] : 0.f;
+  const unsigned spr = (unsigned)g.wo / 8;
+  const unsigned nstrips = (unsigned)g.n * g.ho * spr;
+  for (unsigned st = tid / cog; st < nstrips; st += nthr / cog) {
+    const int sx = (int)(st % spr);
+    const unsigned t0 = st / spr;
+    const int oy = (int)(t0 % (unsigned)g.ho);
+    const int n = (int)(t0 / (unsigned)g.ho);
+    float win[3][10];
+    load_window_3x10(in, n, g.hi, g.wi, oy, sx * 8, win);
+    float cs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = colscale ? colscale[(long long)n * g.co + cg * 8 + j] : 1.f;
+    TO* op = out + (((long long)n * g.ho + oy) * g.wo + sx * 8) * g.co + cg * 8;
+#pragma unroll
+    for (int px = 0; px < 8; ++px) {
+      Vec8<TO> ov;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ov.v[j] = b[j];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float xs = win[r][px + c];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ov.v[j] = fmaf(xs, w[r * 3 + c][j], ov.v[j]);
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ov.v[j] *= cs[j];
+      ov.store(op + (long long)px * g.co);
+    }
+  }
+}
+
+template <typename T, bool FLIP>
+__global__ void __launch_bounds__(256) wgrad_degenerate_strip_kernel(const T* __restrict__ V, const T* __restrict__ S, int n, int h,
+                                                                     int w, int c, unsigned strips_per_block, float* __restrict__ dw) {
+  extern __shared__ float sacc[];   // [9 * c]
+  for (int i = threadIdx.x; i < 9 * c; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int groups = c / 8;
+  const int lanes = blockDim.x / groups;
+  const int grp = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const unsigned spr = (unsigned)w / 8;
+  const unsigned nstrips = (unsigned)n * h * spr;
+  const unsigned s0 = blockIdx.x * strips_per_block;
+  const unsigned s1 = min(nstrips, s0 + strips_per_block);
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  for (unsigned st = s0 + lane; st < s1; st += lanes) {
+    const int sx = (int)(st % spr);
+    const unsigned t0 = st / spr;
+    const int oy = (int)(t0 % (unsigned)h);
+    const int nn = (int)(t0 / (unsigned)h);
+    float win[3][10];
+    load_window_3x10(S, nn, h, w, oy, sx * 8, win);
+    const T* vp = V + (((long long)nn * h + oy) * w + sx * 8) * c + grp * 8;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      Vec8<T> v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u].load(vp + (long long)(half * 4 + u) * c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int px = half * 4 + u;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            const float sv = win[r][px + cc];
+            const int t = FLIP ? 8 - (r * 3 + cc) : (r * 3 + cc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(v[u].v[j], sv, acc[t][j]);
+          }
+      }
+    }
+  }
+  const int lid = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = acc[t][j];
+      for (int off = groups; off < 32; off <<= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      acc[t][j] = a;
+    }
+  if (lid < groups || groups >= 32) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sacc[t * c + grp * 8 + j], acc[t][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * c; i += blockDim.x) {
+    const int tap = i / c, ch = i % c;
+    atomicAdd(&dw[(long long)ch * 9 + tap], sacc[i]);
+  }
+}
+
 // wgrad with a single-channel side: dw[c*taps + tap] += sum_q V[q][c] * S[shift(q, tap)]
 //   a_mode = true : V on the coarse/output grid (Conv2d 1->C: V = dy, S = x),   S index = q*stride - pad + k
 //   a_mode = false: V on the input grid         (Conv2d C->1: V = x,  S = dy),  S index = (q + pad - k)/stride
@@ -445,6 +583,15 @@ static int launch_direct(bool scatter, const TI* in, const TI* W, const float* b
     VG_LAUNCHED();
     return VG_OK;
   }
+  if (g.cr == 1 && v8 && g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.wo % 8 == 0 && g.ho == g.hi && g.wo == g.wi &&
+      256 % (g.co / 8) == 0) {
+    const long long thr = (long long)g.n * g.ho * (g.wo / 8) * (g.co / 8);
+    int grid1 = (int)std::min<long long>(cdiv(thr, 256), (long long)num_sms() * 8);
+    if (scatter) conv_expand1_strip_kernel<TI, TO, true><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
+    else         conv_expand1_strip_kernel<TI, TO, false><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
+    VG_LAUNCHED();
+    return VG_OK;
+  }
   if (g.cr == 1 && v8 && g.kh == 3 && g.kw == 3 && 256 % (g.co / 8) == 0) {
     int grid1 = (int)std::min<long long>(cdiv(total, 256 * 2), (long long)num_sms() * 16);
     if (scatter) conv_expand1_kernel<TI, TO, true><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
@@ -513,6 +660,23 @@ int simt_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* d
     const int hv = a_mode ? d->h_out : d->h_in, wv = a_mode ? d->w_out : d->w_in;
     const int hs = a_mode ? d->h_in : d->h_out, ws = a_mode ? d->w_in : d->w_out;
     const long long npix = (long long)d->n * hv * wv;
+    if (c % 8 == 0 && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && wv % 8 == 0 && hv == hs && wv == ws &&
+        256 % (c / 8) == 0 && (size_t)9 * c * sizeof(float) <= 40000) {
+      const long long nstrips = npix / 8;
+      long long blocks = std::min<long long>(cdiv(nstrips, 64), (long long)num_sms() * 4);
+      unsigned spb = (unsigned)cdiv(nstrips, blocks);
+      blocks = cdiv(nstrips, spb);
+      size_t sm2 = (size_t)9 * c * sizeof(float);
+      if (d->act_dtype == VG_BF16) {
+        if (a_mode) wgrad_degenerate_strip_kernel<__nv_bfloat16, false><<<(unsigned)blocks, 256, sm2, s>>>((const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, spb, dw);
+        else        wgrad_degenerate_strip_kernel<__nv_bfloat16, true><<<(unsigned)blocks, 256, sm2, s>>>((const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, spb, dw);
+      } else {
+        if (a_mode) wgrad_degenerate_strip_kernel<float, false><<<(unsigned)blocks, 256, sm2, s>>>((const float*)V, (const float*)Sx, d->n, hv, wv, c, spb, dw);
+        else        wgrad_degenerate_strip_kernel<float, true><<<(unsigned)blocks, 256, sm2, s>>>((const float*)V, (const float*)Sx, d->n, hv, wv, c, spb, dw);
+      }
+      VG_LAUNCHED();
+      return VG_OK;
+    }
     const int vec = (c % 8 == 0 && c / 8 <= 256) ? 8 : 1;
     VG_CHECK_ARG(c / vec <= 256, "degenerate wgrad supports up to 256 channel groups");
     long long blocks = std::min<long long>(cdiv(npix, 1024), (long long)num_sms() * 4);

@@ -46,6 +46,7 @@ struct alignas(64) TcConvParams {
   int gw, gh, gn;        // GEMM pixel grid of one phase
   int k_chunks;          // reduction channels / 64
   int n_out;             // output channels
+  int n_store;           // columns actually stored per N tile (== BN except for single-channel outputs)
   int OH, OW, os;        // output tensor spatial dims and phase stride
   int out_f32;
   int ksplit, k_per_split;   // split-K over blockIdx.z (only with a single phase, fp32 atomics)
@@ -213,14 +214,22 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (p.bias != nullptr && (p.ksplit <= 1 || blockIdx.z == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + ncol0 + c0 + j);
+            for (int j = 0; j < 32; ++j)
+              if (ncol0 + c0 + j < p.n_out) v[j] += __ldg(p.bias + ncol0 + c0 + j);
           }
           if (p.colscale != nullptr) {
             const float* cs = p.colscale + (long long)gn * p.n_out + ncol0 + c0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
           }
-          if (p.ksplit > 1) {
+          if (p.n_store == 1) {
+            // single-channel output (Conv2d C->1 forward / Conv2d 1->C dgrad): only column 0 is real
+            // (static register index - a dynamic one would push v[] into local memory)
+            if (c0 == 0) {
+              if (p.out_f32) reinterpret_cast<float*>(p.out)[opix] = v[0];
+              else reinterpret_cast<__nv_bfloat16*>(p.out)[opix] = __float2bfloat16_rn(v[0]);
+            }
+          } else if (p.ksplit > 1) {
             float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
@@ -448,14 +457,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             if (p.bias != nullptr && (p.ksplit <= 1 || z == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + ncol0 + c0 + j);
+              for (int j = 0; j < 32; ++j)
+                if (ncol0 + c0 + j < p.n_out) v[j] += __ldg(p.bias + ncol0 + c0 + j);
             }
             if (p.colscale != nullptr) {
               const float* cs = p.colscale + (long long)gn * p.n_out + ncol0 + c0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
             }
-            if (p.ksplit > 1) {
+            if (p.n_store == 1) {
+              // single-channel output (Conv2d C->1 forward / Conv2d 1->C dgrad): only column 0 is real
+              // (static register index - a dynamic one would push v[] into local memory)
+              if (c0 == 0) {
+                if (p.out_f32) reinterpret_cast<float*>(p.out)[opix] = v[0];
+                else reinterpret_cast<__nv_bfloat16*>(p.out)[opix] = __float2bfloat16_rn(v[0]);
+              }
+            } else if (p.ksplit > 1) {
               float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
@@ -756,9 +773,10 @@ bool tc_conv_supported(const VgConvDesc* d, bool dgrad) {
   if (d->kh != d->kw || d->kh * d->kw > 16) return false;
   const int c_red = dgrad ? d->c_out : d->c_in;
   const int n_out = dgrad ? d->c_in : d->c_out;
-  if (c_red % 64 != 0 || n_out % 64 != 0) return false;
+  // n_out == 1: the N tile is filled with the neighbouring taps' weight rows (finite garbage) and only
+  // column 0 is stored - the reduction over 64+ input channels still runs on the tensor cores
+  if (c_red % 64 != 0 || (n_out % 64 != 0 && n_out != 1)) return false;
   if (d->stride == 2 && ((d->transposed ? d->h_out : d->h_in) % 2 != 0 || (d->transposed ? d->w_out : d->w_in) % 2 != 0)) return false;
-  if (dgrad && d->out_dtype != VG_BF16 && false) return false;
   return get_encode() != nullptr;
 }
 
@@ -909,9 +927,10 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
     if ((rc = make_act_map(&p.in_maps[0], in, d->n, in_h, in_w, in_c, 1, 0, 0, p.TW, p.TH, p.TN))) return rc;
     p.in_maps[1] = p.in_maps[2] = p.in_maps[3] = p.in_maps[0];
   }
-  const int BN = pick_bn(n_out);
+  const int BN = (n_out == 1) ? 64 : pick_bn(n_out);
+  p.n_store = (n_out == 1) ? 1 : BN;
   if ((rc = make_weight_map(&p.w_map, wpack, (long long)k * k * n_out, in_c, BN))) return rc;
-  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.tiles_n), (unsigned)(n_out / BN), (unsigned)nphase);
+  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.tiles_n), (unsigned)std::max(1, n_out / BN), (unsigned)nphase);
   if (grid.x == 0) return VG_OK;
   p.ksplit = 1;
   p.k_per_split = p.phases[0].ntaps * p.k_chunks;

@@ -113,11 +113,33 @@ __global__ void avgpool_flatten_fwd_kernel(const T* __restrict__ x, int n, int h
     out[(long long)nn * c * ph * pw + (long long)ch * ph * pw + py * pw + px] = s * inv;
   }
 }
+// one thread per 8 consecutive channels of an input pixel: 16-byte stores, 32-bit index math
 template <typename T>
 __global__ void avgpool_flatten_bwd_kernel(const float* __restrict__ dout, int n, int h, int w, int c, int k, T* __restrict__ dx) {
   const int ph = h / k, pw = w / k;
-  const long long total = (long long)n * h * w * c;
   const float inv = 1.0f / (float)(k * k);
+  if ((c & 7) == 0) {
+    const unsigned cg = (unsigned)c / 8;
+    const unsigned total = (unsigned)n * h * w * cg;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const unsigned g = i % cg;
+      unsigned t = i / cg;
+      const int x = (int)(t % (unsigned)w); t /= (unsigned)w;
+      const int y = (int)(t % (unsigned)h);
+      const int nn = (int)(t / (unsigned)h);
+      const int py = y / k, px = x / k;
+      Vec8<T> o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = 0.f;
+        if (py < ph && px < pw) v = dout[(long long)nn * c * ph * pw + (long long)(g * 8 + j) * ph * pw + py * pw + px] * inv;
+        o.v[j] = v;
+      }
+      o.store(dx + (long long)i * 8);
+    }
+    return;
+  }
+  const long long total = (long long)n * h * w * c;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int ch = (int)(i % c);
     long long t = i / c;
