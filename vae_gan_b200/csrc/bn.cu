@@ -287,7 +287,7 @@ __global__ void bn_act_fwd_scalar_kernel(const T* __restrict__ x, const float* _
 // backward: g = dy * drop' * lrelu'(a*x+b);  reduce: sum g, sum g*xhat;  apply: dx
 // ------------------------------------------------------------------------------------------
 template <typename T, bool DROP, bool APPLY>
-__global__ void __launch_bounds__(kBnThreads) bn_act_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(kBnThreads, APPLY ? 1 : 3) bn_act_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                                      const float* __restrict__ mean_rstd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                      BnK k, double* __restrict__ sums_out /* reduce */,

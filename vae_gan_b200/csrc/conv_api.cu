@@ -12,7 +12,7 @@ int simt_pack_weights(const VgConvDesc*, const float*, const float*, void*, void
 bool tc_conv_supported(const VgConvDesc*, bool dgrad);
 bool tc_wgrad_supported(const VgConvDesc*);
 int tc_conv_run(const VgConvDesc*, bool dgrad, const void* in, const void* wpack, const float* bias, const float* colscale, void* out,
-                int out_dtype, cudaStream_t);
+                int out_dtype, double* stats, bool* stats_fused, cudaStream_t);
 int tc_wgrad_run(const VgConvDesc*, const void* x, const void* dy, float* dw, float* workspace, cudaStream_t);
 }  // namespace vg
 
@@ -51,12 +51,13 @@ extern "C" int vg_conv_forward(const VgConvDesc* d, const void* x, const void* p
   if (d->n == 0) return VG_OK;   // empty batch: nothing to do (pointers of empty tensors may be null)
   VG_CHECK_ARG(x && y && pack_kn && pack_nk, "null pointer");
   cudaStream_t s = as_stream(stream);
+  bool stats_fused = false;
   if (tc_conv_supported(d, false) && !(d->c_out == 1 && colscale != nullptr))
-    rc = tc_conv_run(d, false, x, pack_kn, bias, colscale, y, d->out_dtype, s);
+    rc = tc_conv_run(d, false, x, pack_kn, bias, colscale, y, d->out_dtype, stats, &stats_fused, s);
   else
     rc = simt_conv_forward(d, x, pack_nk, bias, colscale, y, s);
   if (rc) return rc;
-  if (stats != nullptr) {
+  if (stats != nullptr && !stats_fused) {
     VgBnDesc b{};
     b.rows = (long long)d->n * d->h_out * d->w_out;
     b.c = d->c_out;
@@ -75,7 +76,7 @@ extern "C" int vg_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pa
   if (d->n == 0) return VG_OK;
   VG_CHECK_ARG(dy && dx && pack_kn && pack_nk, "null pointer");
   cudaStream_t s = as_stream(stream);
-  if (tc_conv_supported(d, true)) return tc_conv_run(d, true, dy, pack_nk, nullptr, nullptr, dx, d->act_dtype, s);
+  if (tc_conv_supported(d, true)) return tc_conv_run(d, true, dy, pack_nk, nullptr, nullptr, dx, d->act_dtype, nullptr, nullptr, s);
   return simt_conv_dgrad(d, dy, pack_kn, dx, s);
 }
 

@@ -53,6 +53,7 @@ struct alignas(64) TcConvParams {
   void* out;
   const float* bias;
   const float* colscale;
+  double* stats;         // nullable: [2*n_out] per-channel sum / sum of squares of the stored output
 };
 
 struct alignas(64) TcWgradParams {
@@ -66,14 +67,91 @@ struct alignas(64) TcWgradParams {
   float* dw;
 };
 
+constexpr int kStatsSmemBytes = 4 * 16 * 33 * 4;   // per epilogue warp: a [16][33] fp32 transpose buffer
 constexpr int kTcThreads = 256;
 constexpr int kABytes = 128 * 128;   // 128 rows x 64 bf16
 
 template <int BN, int MT, int STAGES>
 struct ConvSmem {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 1) * 8 + 16 + 1024 + kStatsSmemBytes;
 };
+
+
+// Finishes one 32-column chunk of one accumulator row per thread: bias, Dropout2d column scale, store
+// (bf16 / fp32 / split-K atomics / single channel) and - when `tbuf` is given - adds this warp's
+// per-column sum and sum of squares of the values AS STORED to (st_sum, st_sq): lane l owns column l.
+// Those feed the BatchNorm that follows the convolution (README.md:192), saving a full read of y.
+__device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint32_t (&r)[32], bool valid, bool add_bias,
+                                               long long opix, int gn, int ncol, bool first_chunk, float* tbuf, int lane,
+                                               float& st_sum, float& st_sq) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias != nullptr && add_bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (ncol + j < p.n_out) v[j] += __ldg(p.bias + ncol + j);
+  }
+  if (p.colscale != nullptr && valid) {
+    const float* cs = p.colscale + (long long)gn * p.n_out + ncol;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
+  }
+  if (valid) {
+    if (p.n_store == 1) {
+      // single-channel output (Conv2d C->1 forward / Conv2d 1->C dgrad): only column 0 is real
+      // (static register index - a dynamic one would push v[] into local memory)
+      if (first_chunk) {
+        if (p.out_f32) reinterpret_cast<float*>(p.out)[opix] = v[0];
+        else reinterpret_cast<__nv_bfloat16*>(p.out)[opix] = __float2bfloat16_rn(v[0]);
+      }
+    } else if (p.ksplit > 1) {
+      float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
+    } else if (p.out_f32) {
+      float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.n_out + ncol;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * i], v[j + 2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(o + j) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  if (tbuf != nullptr) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if ((lane >> 4) == half) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = valid ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16_rn(v[j]))) : 0.f;
+          tbuf[(lane & 15) * 33 + j] = a;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = tbuf[i * 33 + lane];
+        s1 += a;
+        s2 = fmaf(a, a, s2);
+      }
+      __syncwarp();
+    }
+    st_sum += s1;
+    st_sq += s2;
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // forward / dgrad implicit GEMM
@@ -94,6 +172,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* stats_buf = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : blockIdx.z];
@@ -193,13 +272,19 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
       ptx::mbar_wait(tmem_full, 0);
       ptx::tc_fence_after();
     }
+    const bool do_stats = p.stats != nullptr && p.ksplit <= 1 && num_k > 0;
+    float* tbuf = do_stats ? stats_buf + q * 16 * 33 : nullptr;
+    float st_s[BN / 32], st_q[BN / 32];
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) st_s[c] = st_q[c] = 0.f;
 #pragma unroll 1
     for (int m = 0; m < nvalid; ++m) {
       const int gx = x0s[m] + xl, gy = y0s[m] + yl, gn = n0s[m] + nl;
-      const bool valid = gx < p.gw && gy < p.gh && gn < p.gn;
+      const bool valid = gx < p.gw && gy < p.gh && gn < p.gn && !(p.ksplit > 1 && num_k == 0);
       const long long opix = ((long long)gn * p.OH + (long long)gy * p.os + ph.oy_off) * p.OW + (long long)gx * p.os + ph.ox_off;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        const int c0 = c * 32;
         uint32_t r[32];
         if (num_k > 0) {
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * BN + c0), r);
@@ -208,48 +293,16 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
-        if (valid && !(p.ksplit > 1 && num_k == 0)) {
-          float v[32];
+        epilogue_chunk(p, r, valid, p.ksplit <= 1 || blockIdx.z == 0, opix, gn, ncol0 + c0, c == 0, tbuf, lane, st_s[c], st_q[c]);
+      }
+    }
+    if (do_stats) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr && (p.ksplit <= 1 || blockIdx.z == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ncol0 + c0 + j < p.n_out) v[j] += __ldg(p.bias + ncol0 + c0 + j);
-          }
-          if (p.colscale != nullptr) {
-            const float* cs = p.colscale + (long long)gn * p.n_out + ncol0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
-          }
-          if (p.n_store == 1) {
-            // single-channel output (Conv2d C->1 forward / Conv2d 1->C dgrad): only column 0 is real
-            // (static register index - a dynamic one would push v[] into local memory)
-            if (c0 == 0) {
-              if (p.out_f32) reinterpret_cast<float*>(p.out)[opix] = v[0];
-              else reinterpret_cast<__nv_bfloat16*>(p.out)[opix] = __float2bfloat16_rn(v[0]);
-            }
-          } else if (p.ksplit > 1) {
-            float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
-          } else if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.n_out + ncol0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t w[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * i], v[j + 2 * i + 1]);
-                w[i] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              *reinterpret_cast<uint4*>(o + j) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col = ncol0 + c * 32 + lane;
+        if (col < p.n_out) {
+          atomicAdd(p.stats + col, (double)st_s[c]);
+          atomicAdd(p.stats + p.n_out + col, (double)st_q[c]);
         }
       }
     }
@@ -267,7 +320,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 template <int BN, int MT, int STAGES>
 struct ConvPersistSmem {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024 + kStatsSmemBytes;
 };
 
 template <int BN, int MT, int STAGES>
@@ -288,6 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __
   uint64_t* acc_full = empty + STAGES;       // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* stats_buf = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
@@ -417,6 +471,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __
     const int yl = (row >> p.tw_log2) & (p.TH - 1);
     const int nl = row >> (p.tw_log2 + p.th_log2);
     int it = 0;
+    const bool do_stats = p.stats != nullptr && p.ksplit <= 1;
+    float* tbuf = do_stats ? stats_buf + q * 16 * 33 : nullptr;
+    float st_s[BN / 32], st_q[BN / 32];
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) st_s[c] = st_q[c] = 0.f;
+    int st_nt = -1;                      // N tile the register statistics belong to
+    auto flush_stats = [&]() {
+      if (st_nt < 0) return;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col = st_nt * BN + c * 32 + lane;
+        if (col < p.n_out) {
+          atomicAdd(p.stats + col, (double)st_s[c]);
+          atomicAdd(p.stats + p.n_out + col, (double)st_q[c]);
+        }
+        st_s[c] = st_q[c] = 0.f;
+      }
+    };
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       int z, nt, g;
       decode(w, z, nt, g);
@@ -429,6 +501,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __
       const int nvalid = min(MT, total_tiles - tile0);
       const int ncol0 = nt * BN;
       const int as = it & 1;
+      if (do_stats && nt != st_nt) {
+        flush_stats();
+        st_nt = nt;
+      }
       if (has_k) {
         ptx::mbar_wait(&acc_full[as], (uint32_t)((it >> 1) & 1));
         ptx::tc_fence_after();
@@ -441,8 +517,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __
         const int gx = x0 + xl, gy = y0 + yl, gn = n0 + nl;
         const bool valid = gx < p.gw && gy < p.gh && gn < p.gn;
         const long long opix = ((long long)gn * p.OH + (long long)gy * p.os + ph.oy_off) * p.OW + (long long)gx * p.os + ph.ox_off;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          const int c0 = c * 32;
           uint32_t r[32];
           if (has_k) {
             ptx::tmem_ld_32x32(acc + (uint32_t)(m * BN + c0), r);
@@ -451,49 +528,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
-          if (valid) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (p.bias != nullptr && (p.ksplit <= 1 || z == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ncol0 + c0 + j < p.n_out) v[j] += __ldg(p.bias + ncol0 + c0 + j);
-            }
-            if (p.colscale != nullptr) {
-              const float* cs = p.colscale + (long long)gn * p.n_out + ncol0 + c0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
-            }
-            if (p.n_store == 1) {
-              // single-channel output (Conv2d C->1 forward / Conv2d 1->C dgrad): only column 0 is real
-              // (static register index - a dynamic one would push v[] into local memory)
-              if (c0 == 0) {
-                if (p.out_f32) reinterpret_cast<float*>(p.out)[opix] = v[0];
-                else reinterpret_cast<__nv_bfloat16*>(p.out)[opix] = __float2bfloat16_rn(v[0]);
-              }
-            } else if (p.ksplit > 1) {
-              float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
-            } else if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol0 + c0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.n_out + ncol0 + c0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint32_t wv[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * i], v[j + 2 * i + 1]);
-                  wv[i] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                *reinterpret_cast<uint4*>(o + j) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-              }
-            }
-          }
+          epilogue_chunk(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, tbuf, lane, st_s[c], st_q[c]);
         }
       }
       if (has_k) {
@@ -504,6 +539,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __
         ++it;
       }
     }
+    if (do_stats) flush_stats();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -887,7 +923,8 @@ static int pick_bn(int n_out) {
 
 // dgrad=false: y = conv(x).  dgrad=true: dx from dy.  `in` is the tensor being read.
 int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpack, const float* bias, const float* colscale,
-                void* out, int out_dtype, cudaStream_t s) {
+                void* out, int out_dtype, double* stats, bool* stats_fused, cudaStream_t s) {
+  if (stats_fused) *stats_fused = false;
   TcConvParams p;
   memset(&p, 0, sizeof(p));
   // pattern: which side is the coarse grid
@@ -904,6 +941,7 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   p.OH = out_h; p.OW = out_w;
   p.out = out; p.out_f32 = out_dtype == VG_F32;
   p.bias = bias; p.colscale = colscale;
+  p.stats = nullptr;
   int nphase = 1;
   if (gather) {
     p.gw = out_w; p.gh = out_h; p.gn = d->n; p.os = 1;
@@ -949,6 +987,16 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
       }
     }
   }
+  // Fusing the BatchNorm statistics into the epilogue is implemented and parity-tested, but with only
+  // four epilogue warps it makes the epilogue the bottleneck of the persistent kernel (measured on B200:
+  // 128->128 @96 goes from 115 to 184 us per launch, far more than the 20 us statistics kernel it
+  // saves).  Opt-in (VG_TC_FUSE_STATS=1) until the epilogue is spread over eight warps.
+  static int fuse_stats = -1;
+  if (fuse_stats < 0) { const char* e = getenv("VG_TC_FUSE_STATS"); fuse_stats = (e && atoi(e)) ? 1 : 0; }
+  if (fuse_stats && stats != nullptr && p.ksplit == 1 && n_out % 32 == 0) {
+    p.stats = stats;               // per-channel sum / sum-of-squares accumulated by the epilogue warps
+    if (stats_fused) *stats_fused = true;
+  }
   // several pixel tiles per CTA (sharing the weight tile) when there are enough tiles to keep
   // every SM busy; single-tile CTAs (two resident per SM) for small problems and split-K
   // Measured on B200 (scripts/sweep_conv.py, batch 64): with one CTA per SM the epilogue of a
@@ -976,7 +1024,7 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
     }
   }
   switch (BN) {
-    case 64: return big ? launch_conv<64, 4, 3>(p, grid, s) : launch_conv<64, 1, 4>(p, grid, s);
+    case 64: return big ? launch_conv<64, 2, 4>(p, grid, s) : launch_conv<64, 1, 4>(p, grid, s);
     case 128: return big ? launch_conv<128, 2, 4>(p, grid, s) : launch_conv<128, 1, 3>(p, grid, s);
     case 256: return launch_conv<256, 1, 4>(p, grid, s);
     default: set_error("unsupported BN %d", BN); return VG_EUNSUPPORTED;
