@@ -234,6 +234,37 @@ typedef struct {
 int vg_optimizer_step(float* p, const float* g, float* m, float* v, long long n,
                       const VgOptDesc* d, const unsigned long long* step_ptr, vg_stream_t stream);
 
+/* ---- SyncBN statistics exchange over NVLink peer memory ------------------
+ * One-shot all-reduce(sum) of a small fp64 vector (the 2C BatchNorm sums) without NCCL: every rank
+ * stores its vector into slot [slot][rank] of EVERY peer's exchange buffer (plain stores through
+ * peer-mapped pointers over NVLink/NVSwitch), publishes a flag, waits for all peers' flags and sums
+ * the `world` sub-slots in rank order (bit-identical on all ranks).  Latency ~ one NVLink round trip
+ * instead of a collective launch; 96 of these sit on the critical path of one training iteration.
+ *   peer_data[r]  : rank r's data buffer,  double[n_slots][world][VG_PEER_MAX_N]   (peer-mapped)
+ *   peer_flags[r] : rank r's flag buffer,  unsigned long long[n_slots][world]      (zero-initialised)
+ *   epoch_ptr     : device counter, identical on all ranks, strictly increasing between two uses of
+ *                   the same slot (the trainer's step counter, >= 1)
+ * The vector is reduced IN PLACE.  A rank must not reuse a slot before every peer has consumed it; using
+ * each slot once per step with at least two exchanges per step guarantees that. */
+#define VG_PEER_MAX_WORLD 8
+#define VG_PEER_MAX_N 2048
+typedef struct {
+  void* peer_data[VG_PEER_MAX_WORLD];
+  void* peer_flags[VG_PEER_MAX_WORLD];
+  int rank, world, n_slots;
+} VgPeerDesc;
+/* enable P2P access from the current device to `peer_device` (idempotent) */
+int vg_enable_peer_access(int peer_device);
+/* Setup-time helpers (NOT on the hot path; the only calls that touch the allocator): the exchange
+ * buffers are plain cudaMalloc allocations whose 64-byte CUDA IPC handles the other ranks open. */
+int vg_peer_alloc(size_t bytes, void** ptr);                   /* cudaMalloc + zero fill */
+int vg_peer_free(void* ptr);
+int vg_peer_get_handle(void* ptr, void* handle64);             /* HOST buffer of 64 bytes */
+int vg_peer_open_handle(const void* handle64, void** ptr);     /* maps a peer's buffer into this process */
+int vg_peer_close_handle(void* ptr);
+int vg_peer_allreduce_f64(double* vec, int n, const VgPeerDesc* pd, int slot,
+                          const unsigned long long* epoch_ptr, vg_stream_t stream);
+
 /* ---- layout / dtype helpers at the module boundary --------------------------------------- */
 int vg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, vg_stream_t stream);
 /* NCHW fp32 <-> NHWC dtype */

@@ -70,7 +70,7 @@ def main():
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             same = bool(((hi - lo).abs() <= 1e-6 * hi.abs().clamp_min(1)).all())
-        results[str(cdt)] = dict(worst_pre_update_loss_rel=worst_pre, worst_loss_rel=worst, frac_params_off_g=frac_g, frac_params_off_d=frac_d, replicas_identical=same)
+        results[str(cdt)] = dict(peer_syncbn=dp.peer is not None, worst_pre_update_loss_rel=worst_pre, worst_loss_rel=worst, frac_params_off_g=frac_g, frac_params_off_d=frac_d, replicas_identical=same)
         lim = 2e-3 if cdt == torch.float32 else 0.08
         tol_pre = 2e-5 if cdt == torch.float32 else 2e-2
         tol_post = 5e-3 if cdt == torch.float32 else 5e-2

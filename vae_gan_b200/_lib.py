@@ -35,6 +35,10 @@ class VgLossDesc(C.Structure):
                 ("w_kl", c_f), ("xhat_dtype", c_int)]
 
 
+class VgPeerDesc(C.Structure):
+    _fields_ = [("peer_data", c_vp * 8), ("peer_flags", c_vp * 8), ("rank", c_int), ("world", c_int), ("n_slots", c_int)]
+
+
 class VgOptDesc(C.Structure):
     _fields_ = [("kind", c_int), ("lr", c_f), ("beta1", c_f), ("beta2", c_f), ("alpha", c_f), ("eps", c_f),
                 ("weight_decay", c_f), ("bias_corr1", c_f), ("bias_corr2", c_f), ("clamp", c_f),
@@ -78,6 +82,13 @@ _PROTOS = {
     "vg_generator_loss": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(VgLossDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "vg_discriminator_loss": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "vg_optimizer_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, C.POINTER(VgOptDesc), c_vp, c_vp]),
+    "vg_enable_peer_access": (c_int, [c_int]),
+    "vg_peer_alloc": (c_int, [C.c_size_t, C.POINTER(c_vp)]),
+    "vg_peer_free": (c_int, [c_vp]),
+    "vg_peer_get_handle": (c_int, [c_vp, c_vp]),
+    "vg_peer_open_handle": (c_int, [c_vp, C.POINTER(c_vp)]),
+    "vg_peer_close_handle": (c_int, [c_vp]),
+    "vg_peer_allreduce_f64": (c_int, [c_vp, c_int, C.POINTER(VgPeerDesc), c_int, c_vp, c_vp]),
     "vg_cast": (c_int, [c_vp, c_int, c_vp, c_int, c_ll, c_vp]),
     "vg_nchw_to_nhwc": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "vg_nhwc_to_nchw": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),

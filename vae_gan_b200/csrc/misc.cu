@@ -414,6 +414,49 @@ __global__ void __launch_bounds__(256) optimizer_kernel(float* __restrict__ p, c
 }
 
 // ------------------------------------------------------------------------------------------
+// one-shot all-reduce of a small fp64 vector over NVLink peer memory (SyncBN statistics)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* __restrict__ vec, int n, VgPeerDesc pd, int slot,
+                                                                 const unsigned long long* __restrict__ epoch_ptr) {
+  const unsigned long long epoch = *epoch_ptr;
+  const int tid = threadIdx.x;
+  const size_t slot_off = ((size_t)slot * pd.world + pd.rank) * VG_PEER_MAX_N;
+  // 1. my contribution into my sub-slot of every rank's buffer (NVLink stores for r != rank)
+  for (int r = 0; r < pd.world; ++r) {
+    double* dst = reinterpret_cast<double*>(pd.peer_data[r]) + slot_off;
+    for (int i = tid; i < n; i += blockDim.x) dst[i] = vec[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. publish: flag[slot][rank] = epoch on every rank
+  if (tid < pd.world) {
+    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(pd.peer_flags[tid]) + (size_t)slot * pd.world + pd.rank;
+    *f = epoch;
+  }
+  // 3. wait until every rank has published this epoch into MY flags
+  if (tid < pd.world) {
+    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(pd.peer_flags[pd.rank]) + (size_t)slot * pd.world + tid;
+    const long long t0 = clock64();
+    while (*f < epoch) {
+      if (clock64() - t0 > 20000000000LL) {     // ~10 s: a peer never arrived - fail loudly instead of hanging
+        printf("vaegan_b200: peer all-reduce timed out (rank %d waiting for rank %d, slot %d, epoch %llu, flag %llu)\n", pd.rank, tid, slot,
+               epoch, (unsigned long long)*f);
+        __trap();
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 4. sum the sub-slots in rank order (identical result on every rank); bypass L1 for peer-written data
+  const double* mine = reinterpret_cast<const double*>(pd.peer_data[pd.rank]) + (size_t)slot * pd.world * VG_PEER_MAX_N;
+  for (int i = tid; i < n; i += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < pd.world; ++r) s += __ldcv(mine + (size_t)r * VG_PEER_MAX_N + i);
+    vec[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // layout / dtype
 // ------------------------------------------------------------------------------------------
 template <typename TS, typename TD>
@@ -654,6 +697,18 @@ extern "C" int vg_optimizer_step(float* p, const float* g, float* m, float* v, l
   bool al = ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)v % 16 == 0) && (!m || (uintptr_t)m % 16 == 0);
   long long n4 = al ? n / 4 : 0;
   optimizer_kernel<<<ew_grid(n, 8), 256, 0, as_stream(stream)>>>(p, g, m, v, n4, n, *d, step_ptr);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_peer_allreduce_f64(double* vec, int n, const VgPeerDesc* pd, int slot, const unsigned long long* epoch_ptr,
+                                     vg_stream_t stream) {
+  VG_CHECK_ARG(vec && pd && epoch_ptr, "null pointer");
+  VG_CHECK_ARG(n > 0 && n <= VG_PEER_MAX_N, "n must be in 1..%d", VG_PEER_MAX_N);
+  VG_CHECK_ARG(pd->world >= 1 && pd->world <= VG_PEER_MAX_WORLD && pd->rank >= 0 && pd->rank < pd->world, "bad rank/world");
+  VG_CHECK_ARG(slot >= 0 && slot < pd->n_slots, "slot %d out of range (n_slots %d)", slot, pd->n_slots);
+  for (int r = 0; r < pd->world; ++r) VG_CHECK_ARG(pd->peer_data[r] && pd->peer_flags[r], "peer pointer %d is null", r);
+  peer_allreduce_f64_kernel<<<1, 256, 0, as_stream(stream)>>>(vec, n, *pd, slot, epoch_ptr);
   VG_LAUNCHED();
   return VG_OK;
 }

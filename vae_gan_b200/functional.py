@@ -34,6 +34,7 @@ class _Config:
     process_group = None          # data-parallel group for SyncBN statistics (None = single GPU)
     sample_offset = 0             # global index of this rank's first sample
     defer_num_batches_tracked = False   # the trainer bumps every BN's counter with ONE foreach kernel per step
+    peer = None                   # dist.PeerExchange: NVLink one-shot exchange of the SyncBN sums (else NCCL)
 
 
 config = _Config()
@@ -98,7 +99,10 @@ _DIAG_NO_SYNCBN = bool(int(_os.environ.get("VG_DIAG_NO_SYNCBN", "0")))      # ti
 
 def _allreduce_sums(t: torch.Tensor):
     if config.process_group is not None and _world() > 1 and not _DIAG_NO_SYNCBN:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=config.process_group)
+        if config.peer is not None:
+            config.peer.allreduce_(t, rng.step_tensor(t.device))
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=config.process_group)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -62,7 +62,7 @@ class VaeGanTrainer:
     def __init__(self, generator: nn.Module, discriminator: nn.Module, *, loss_mode: str = "bce",
                  optimizer: str = "adam", lr: float = 3e-4, weights=(1.0, 10.0, 0.1), clip_value: float = 0.01,
                  weight_decay: Optional[float] = None, betas=(0.9, 0.999), process_group=None,
-                 local_batch: Optional[int] = None):
+                 local_batch: Optional[int] = None, peer_syncbn: Optional[bool] = None):
         assert loss_mode in ("bce", "wgan"), "wgan_gp (double backward) is not built yet - see DESIGN.md"
         assert optimizer in ("adam", "rmsprop")
         self.G, self.D = generator, discriminator
@@ -82,8 +82,25 @@ class VaeGanTrainer:
         self.graph = None
         self.static_real = None
         self.local_batch = local_batch
+        self.peer = None
         if process_group is not None:
             VF.config.process_group = process_group
+            import os
+            if peer_syncbn is None:
+                peer_syncbn = os.environ.get("VG_PEER_SYNCBN", "1") == "1"
+            if peer_syncbn and self.world > 1:
+                try:
+                    from .dist import PeerExchange
+                    self.peer = PeerExchange(process_group, self.device)
+                except Exception as e:   # no P2P / IPC on this box: NCCL carries the statistics instead
+                    if self.rank == 0:
+                        print(f"[vae_gan_b200] NVLink peer exchange unavailable ({type(e).__name__}: {e}); SyncBN uses NCCL")
+                    self.peer = None
+                # all ranks must agree
+                ok = torch.tensor([1 if self.peer is not None else 0], device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+                if int(ok) == 0:
+                    self.peer = None
         # num_batches_tracked of every BatchNorm: G's are used once per iteration, D's three times
         self._nbt_g = [m.num_batches_tracked for m in generator.modules() if isinstance(m, nn.BatchNorm2d)]
         self._nbt_d = [m.num_batches_tracked for m in discriminator.modules() if isinstance(m, nn.BatchNorm2d)]
@@ -113,10 +130,14 @@ class VaeGanTrainer:
         if self.D.training and self._nbt_d:
             torch._foreach_add_(self._nbt_d, 3)
         VF.config.defer_num_batches_tracked = True
+        VF.config.peer = self.peer
+        if self.peer is not None:
+            self.peer.reset()
         try:
             return self._iteration(real, adv_mode)
         finally:
             VF.config.defer_num_batches_tracked = False
+            VF.config.peer = None
 
     def _iteration(self, real, adv_mode):
         with M._scope():
