@@ -42,7 +42,17 @@ static inline int grid_for(long long rows, int rpb, int iters_target = kUnroll *
 // kernels that end in a per-channel reduction: every block issues 2C same-address fp64 atomics, which
 // serialise in L2 - keep the block count at a small multiple of the SM count and give each block
 // more rows instead.
-constexpr int kReduceBlocksPerSm = 3;
+static int reduce_blocks_per_sm() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VG_BN_REDUCE_BPS"); v = e ? atoi(e) : 3; if (v < 1) v = 1; }
+  return v;
+}
+static int apply_blocks_per_sm() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VG_BN_APPLY_BPS"); v = e ? atoi(e) : 4; if (v < 1) v = 1; }
+  return v;
+}
+#define kReduceBlocksPerSm reduce_blocks_per_sm()
 
 // 16-bit Philox keep decisions for 8 consecutive elements starting at linear index e0 (e0 % 8 == 0)
 __device__ __forceinline__ void keep8(const Philox& ph, unsigned long long e0, uint32_t thr16, bool keep[8]) {
@@ -718,7 +728,7 @@ static int bn_act_backward_t(const T* dy, const T* x, const float* mr, const flo
     long long rows = k.fold ? d->rows / 8 : d->rows;
     k.rows = rows;
     RowMap m = make_rowmap(k.fold ? 8 : d->c);
-    int grid = grid_for(rows, m.rpb, kUnroll, APPLY ? 8 : kReduceBlocksPerSm);
+    int grid = grid_for(rows, m.rpb, kUnroll, APPLY ? apply_blocks_per_sm() : kReduceBlocksPerSm);
     size_t sm = APPLY ? 0 : vec_smem();
     if (k.thr16)
       bn_act_bwd_vec_kernel<T, true, APPLY><<<grid, kBnThreads, sm, s>>>(dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
@@ -774,7 +784,7 @@ static int bn_add_t(const T* a, const float* mra, const float* ga, const float* 
     long long rows = k.fold ? d->rows / 8 : d->rows;
     k.rows = rows;
     RowMap m = make_rowmap(k.fold ? 8 : d->c);
-    int grid = grid_for(rows, m.rpb, kUnroll, stats ? kReduceBlocksPerSm : 8);
+    int grid = grid_for(rows, m.rpb, kUnroll, stats ? kReduceBlocksPerSm : apply_blocks_per_sm());
     if (stats)
       bn_add_vec_kernel<T, true><<<grid, kBnThreads, vec_smem(), s>>>(a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
     else

@@ -313,19 +313,31 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// NOTE (measured, round 1): with cta_group::1 the SS-mode MMA reads A (128x16) and B (BNx16) from shared
+// memory for every instruction: (4 KB + BN*32 B) per BN/4 cycles = 192 / 128 / 96 B per cycle for
+// BN = 64 / 128 / 256 against a 128 B/cycle shared-memory port.  That - not L2 traffic - is what caps the
+// narrow tiles (a halo-reuse experiment that cut the staged A bytes 4x changed nothing): 64-wide tiles
+// reach ~35 %, 128-wide ~64 %, 256-wide 92 % of the measured peak.  The fix is cta_group::2 (the CTA pair
+// shares operands, halving the per-SM shared-memory reads), next round.
+//
 // persistent variant: one CTA per SM loops over work items (phase|k-split, N tile, group of MT
 // pixel tiles); the TMEM accumulator is double-buffered so the epilogue of item i overlaps the
 // main loop of item i+1, and the MT pixel tiles of an item share every staged weight tile.
 // ------------------------------------------------------------------------------------------
-template <int BN, int MT, int STAGES>
+template <int BN, int MT, int STAGES, int EW>
 struct ConvPersistSmem {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024 + kStatsSmemBytes;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024 + EW * 16 * 33 * 4;
 };
 
-template <int BN, int MT, int STAGES>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __grid_constant__ TcConvParams p, int n_ntiles,
-                                                                         int n_groups, int n_z, int n_work) {
+// EW = number of epilogue warps (4 or 8).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so with
+// eight warps two warps share each lane quarter and split the 32-column chunks between them; that
+// doubles the epilogue throughput, which is what makes the fused BatchNorm statistics free.
+template <int BN, int MT, int STAGES, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const __grid_constant__ TcConvParams p, int n_ntiles,
+                                                                            int n_groups, int n_z, int n_work) {
+  static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
+  constexpr int kChunkGroups = EW / 4;
   extern __shared__ uint8_t smem_raw[];
   constexpr int kBBytes = BN * 128;
   constexpr int kAStage = MT * kABytes;
@@ -357,7 +369,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&acc_full[a], 1);
-      ptx::mbar_init(&acc_empty[a], 4);      // one arrival per epilogue warp
+      ptx::mbar_init(&acc_empty[a], EW);     // one arrival per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -465,14 +477,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __
       }
     }
   } else if (warp >= 4) {
-    const int q = warp - 4;
+    const int ew = warp - 4;
+    const int q = ew & 3;                 // TMEM lane quarter this warp may access
+    const int cgrp = ew >> 2;             // which share of the 32-column chunks it handles
     const int row = q * 32 + lane;
     const int xl = row & (p.TW - 1);
     const int yl = (row >> p.tw_log2) & (p.TH - 1);
     const int nl = row >> (p.tw_log2 + p.th_log2);
     int it = 0;
     const bool do_stats = p.stats != nullptr && p.ksplit <= 1;
-    float* tbuf = do_stats ? stats_buf + q * 16 * 33 : nullptr;
+    float* tbuf = do_stats ? stats_buf + ew * 16 * 33 : nullptr;
     float st_s[BN / 32], st_q[BN / 32];
 #pragma unroll
     for (int c = 0; c < BN / 32; ++c) st_s[c] = st_q[c] = 0.f;
@@ -481,6 +495,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __
       if (st_nt < 0) return;
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
+        if ((c % kChunkGroups) != cgrp) continue;
         const int col = st_nt * BN + c * 32 + lane;
         if (col < p.n_out) {
           atomicAdd(p.stats + col, (double)st_s[c]);
@@ -519,6 +534,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_persist_kernel(const __
         const long long opix = ((long long)gn * p.OH + (long long)gy * p.os + ph.oy_off) * p.OW + (long long)gx * p.os + ph.ox_off;
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
+          if ((c % kChunkGroups) != cgrp) continue;
           const int c0 = c * 32;
           uint32_t r[32];
           if (has_k) {
@@ -840,12 +856,12 @@ static int launch_conv(const TcConvParams& p, dim3 grid, cudaStream_t s) {
   return VG_OK;
 }
 
-template <int BN, int MT, int STAGES>
+template <int BN, int MT, int STAGES, int EW>
 static int launch_conv_persist(const TcConvParams& p, dim3 grid, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    VG_CUDA(cudaFuncSetAttribute(tc_conv_persist_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 ConvPersistSmem<BN, MT, STAGES>::kBytes));
+    VG_CUDA(cudaFuncSetAttribute(tc_conv_persist_kernel<BN, MT, STAGES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 ConvPersistSmem<BN, MT, STAGES, EW>::kBytes));
     attr_done = true;
   }
   const int n_groups = (int)cdiv(grid.x, MT);
@@ -853,8 +869,8 @@ static int launch_conv_persist(const TcConvParams& p, dim3 grid, cudaStream_t s)
   const int n_z = (int)grid.z;
   const long long n_work = (long long)n_groups * n_ntiles * n_z;
   const int ctas = (int)std::min<long long>(n_work, num_sms());
-  tc_conv_persist_kernel<BN, MT, STAGES><<<ctas, kTcThreads, ConvPersistSmem<BN, MT, STAGES>::kBytes, s>>>(p, n_ntiles, n_groups, n_z,
-                                                                                                          (int)n_work);
+  tc_conv_persist_kernel<BN, MT, STAGES, EW><<<ctas, 128 + 32 * EW, ConvPersistSmem<BN, MT, STAGES, EW>::kBytes, s>>>(
+      p, n_ntiles, n_groups, n_z, (int)n_work);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -987,39 +1003,33 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
       }
     }
   }
-  // Fusing the BatchNorm statistics into the epilogue is implemented and parity-tested, but with only
-  // four epilogue warps it makes the epilogue the bottleneck of the persistent kernel (measured on B200:
-  // 128->128 @96 goes from 115 to 184 us per launch, far more than the 20 us statistics kernel it
-  // saves).  Opt-in (VG_TC_FUSE_STATS=1) until the epilogue is spread over eight warps.
-  static int fuse_stats = -1;
-  if (fuse_stats < 0) { const char* e = getenv("VG_TC_FUSE_STATS"); fuse_stats = (e && atoi(e)) ? 1 : 0; }
-  if (fuse_stats && stats != nullptr && p.ksplit == 1 && n_out % 32 == 0) {
-    p.stats = stats;               // per-channel sum / sum-of-squares accumulated by the epilogue warps
-    if (stats_fused) *stats_fused = true;
-  }
-  // several pixel tiles per CTA (sharing the weight tile) when there are enough tiles to keep
-  // every SM busy; single-tile CTAs (two resident per SM) for small problems and split-K
-  // Measured on B200 (scripts/sweep_conv.py, batch 64): with one CTA per SM the epilogue of a
-  // multi-tile CTA is no longer hidden behind a co-resident CTA's main loop, and 128->128 @96 drops
-  // from 897 to 769 TFLOP/s.  Kept opt-in (VG_TC_MT=1) until the kernel is persistent with a
-  // double-buffered TMEM accumulator.
-  static int mt_on = -1;
+  // kernel variant: persistent CTAs (double-buffered accumulator, MT pixel tiles share each staged weight
+  // tile) when there is enough work; one-shot CTAs (two resident per SM) for small problems and split-K.
+  // Measured on B200 (scripts/sweep_conv.py): a persistent single-tile CTA loses to two co-resident
+  // one-shot CTAs, and multi-tile CTAs without the double-buffered accumulator are slower still
+  // (128->128 @96: 897 -> 769 TFLOP/s), so those stay opt-in (VG_TC_MT=1).
+  static int mt_on = -1, persist = -1, mt_min = -1, fuse_stats = -1;
   if (mt_on < 0) { const char* e = getenv("VG_TC_MT"); mt_on = (e && atoi(e)) ? 1 : 0; }
+  if (persist < 0) { const char* e = getenv("VG_TC_PERSIST"); persist = e ? atoi(e) : 1; }
+  if (mt_min < 0) { const char* e = getenv("VG_TC_MT_MIN"); mt_min = e ? atoi(e) : 6; }
+  if (fuse_stats < 0) { const char* e = getenv("VG_TC_FUSE_STATS"); fuse_stats = e ? atoi(e) : 0; }
   const long long ctas1 = (long long)grid.x * grid.y * grid.z;
   const bool big = mt_on && p.ksplit == 1 && ctas1 >= 6LL * num_sms();
-  static int persist = -1;
-  if (persist < 0) { const char* e = getenv("VG_TC_PERSIST"); persist = e ? atoi(e) : 1; }
-  static int mt_min = -1;
-  if (mt_min < 0) { const char* e = getenv("VG_TC_MT_MIN"); mt_min = e ? atoi(e) : 6; }
-  if (persist && ctas1 >= 2LL * num_sms()) {
-    // enough work for several items per SM: persistent CTAs with a double-buffered accumulator; for
-    // N tiles below 256 only when there is enough work to let MT pixel tiles share each staged
-    // weight tile (measured: a persistent single-tile CTA loses to two co-resident one-shot CTAs)
-    const bool mt = ctas1 >= (long long)mt_min * num_sms();
+  const bool use_persist = persist && ctas1 >= 2LL * num_sms() &&
+                           (BN == 256 || (ctas1 >= (long long)mt_min * num_sms() && (BN == 64 || BN == 128)));
+  // BatchNorm statistics of the output can be accumulated by the epilogue warps of the 8-warp persistent
+  // kernels (parity-tested), but it is OPT-IN (VG_TC_FUSE_STATS=1): measured on B200 the per-chunk smem
+  // transposes cost the L2/smem-bound main loop more (+35 % per launch with 8 epilogue warps, +60 % with
+  // 4) than the separate 20 us statistics kernel they replace.
+  if (fuse_stats && stats != nullptr && p.ksplit == 1 && n_out % 32 == 0 && use_persist && BN >= 128) {
+    p.stats = stats;
+    if (stats_fused) *stats_fused = true;
+  }
+  if (use_persist) {
     switch (BN) {
-      case 64: if (mt) return launch_conv_persist<64, 4, 3>(p, grid, s); break;
-      case 128: if (mt) return launch_conv_persist<128, 2, 4>(p, grid, s); break;
-      case 256: return launch_conv_persist<256, 1, 4>(p, grid, s);
+      case 64: return launch_conv_persist<64, 4, 3, 4>(p, grid, s);
+      case 128: return launch_conv_persist<128, 2, 4, 8>(p, grid, s);
+      case 256: return launch_conv_persist<256, 1, 4, 8>(p, grid, s);
       default: break;
     }
   }
