@@ -214,51 +214,56 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (num_k > 0) {
+    // both role warps loop warp-uniformly and elect a lane only around the TMA / MMA issue (a divergent
+    // `lane == 0` branch makes nvcc wrap every uniform-datapath instruction in an elect-and-retry loop)
     if (warp == 0) {
-      if (lane == 0) {
-        int stage = 0;
-        uint32_t phase = 0;
-        int tp = kb0 / p.k_chunks, kc = kb0 % p.k_chunks;
-        for (int i = kb0; i < kb1; ++i) {
-          const TcTap tap = ph.taps[tp];
-          const CUtensorMap* im = &p.in_maps[tap.map];
-          ptx::mbar_wait(&empty[stage], phase ^ 1u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int tp = kb0 / p.k_chunks, kc = kb0 % p.k_chunks;
+      for (int i = kb0; i < kb1; ++i) {
+        const TcTap tap = ph.taps[tp];
+        const CUtensorMap* im = &p.in_maps[tap.map];
+        ptx::mbar_wait(&empty[stage], phase ^ 1u);
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[stage], nvalid * kABytes + kBBytes);
 #pragma unroll
           for (int m = 0; m < MT; ++m)
             if (m < nvalid)
               ptx::tma_load_4d(sA + stage * kAStage + m * kABytes, im, &full[stage], kc * 64, x0s[m] + tap.dx, y0s[m] + tap.dy, n0s[m]);
           ptx::tma_load_2d(sB + stage * kBBytes, &p.w_map, &full[stage], kc * 64, tap.wrow + ncol0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          if (++kc == p.k_chunks) { kc = 0; ++tp; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (++kc == p.k_chunks) { kc = 0; ++tp; }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 0, 0);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int i = 0; i < num_k; ++i) {
-          ptx::mbar_wait(&full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(sA + stage * kAStage);
-          const uint32_t b_addr = ptx::smem_u32(sB + stage * kBBytes);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t kDescHi = ptx::smem_desc_hi(1024);
+      const uint32_t a_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sA), 16), b_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sB), 16);
+      uint32_t a_lo = a_lo0, b_lo = b_lo0;      // descriptor low words of the current stage
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < num_k; ++i) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int m = 0; m < MT; ++m) {
             if (m < nvalid) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = ptx::make_smem_desc(a_addr + m * kABytes + k * 32, 16, 1024);
-                const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
-                ptx::mma_bf16_ss(tmem_base + (uint32_t)(m * BN), ad, bd, idesc, (i | k) != 0);
-              }
+              for (int k = 0; k < 4; ++k)
+                ptx::mma_bf16_ss_lohi(tmem_base + (uint32_t)(m * BN), a_lo + (uint32_t)((m * kABytes + k * 32) >> 4),
+                                      b_lo + (uint32_t)((k * 32) >> 4), kDescHi, idesc, (i | k) != 0);
             }
           }
           ptx::mma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        ptx::mma_commit(tmem_full);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; b_lo = b_lo0; }
+        else { a_lo += (uint32_t)(kAStage >> 4); b_lo += (uint32_t)(kBBytes >> 4); }
       }
+      if (ptx::elect_one()) ptx::mma_commit(tmem_full);
+      __syncwarp();
     }
   }
 
@@ -313,12 +318,16 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
-// NOTE (measured, round 1): with cta_group::1 the SS-mode MMA reads A (128x16) and B (BNx16) from shared
-// memory for every instruction: (4 KB + BN*32 B) per BN/4 cycles = 192 / 128 / 96 B per cycle for
-// BN = 64 / 128 / 256 against a 128 B/cycle shared-memory port.  That - not L2 traffic - is what caps the
-// narrow tiles (a halo-reuse experiment that cut the staged A bytes 4x changed nothing): 64-wide tiles
-// reach ~35 %, 128-wide ~64 %, 256-wide 92 % of the measured peak.  The fix is cta_group::2 (the CTA pair
-// shares operands, halving the per-SM shared-memory reads), next round.
+// NOTES (measured on B200, round 1; microbenchmarks in scripts/microbench/, numbers in DESIGN.md section 3):
+//  * a tcgen05.mma (M=128, K=16, SS mode) takes max(N/2, 32 + N/4) cycles - the operands are re-read from
+//    shared memory at 128 B/cycle - so N=64 tiles cap at 67 % of the tensor peak, N>=128 can reach it;
+//  * the tensor pipe queues only ~1-2 instructions and every mbarrier wait stalls the issuing thread for
+//    ~105 cycles: one wait per k-block costs a ~135-cycle bubble unless the queued MMAs are N=256 wide;
+//  * under a divergent `lane == 0` branch nvcc wraps each UTCHMMA/UTMALDG in an elect-and-retry loop and
+//    rebuilding 64-bit descriptors costs ~14 uniform instructions per MMA: the role warps therefore run
+//    warp-uniformly, elect only around the issue, and advance 32-bit descriptor halves by adds;
+//  * the chip is power-capped under tensor load (SM clock 1.3-1.5 GHz), so removing loads, stores or waits
+//    buys cycles but little time; what pays is fewer shared-memory/L2 bytes per FLOP (CTA pairs below).
 //
 // persistent variant: one CTA per SM loops over work items (phase|k-split, N tile, group of MT
 // pixel tiles); the TMEM accumulator is double-buffered so the epilogue of item i overlaps the
@@ -333,10 +342,11 @@ struct ConvPersistSmem {
 // EW = number of epilogue warps (4 or 8).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so with
 // eight warps two warps share each lane quarter and split the 32-column chunks between them; that
 // doubles the epilogue throughput, which is what makes the fused BatchNorm statistics free.
-template <int BN, int MT, int STAGES, int EW>
+template <int BN, int MT, int STAGES, int EW, int G>
 __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const __grid_constant__ TcConvParams p, int n_ntiles,
                                                                             int n_groups, int n_z, int n_work) {
   static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
+  static_assert(STAGES % G == 0 && STAGES / G >= 2, "at least two barrier groups");
   constexpr int kChunkGroups = EW / 4;
   extern __shared__ uint8_t smem_raw[];
   constexpr int kBBytes = BN * 128;
@@ -402,79 +412,108 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
     x0 = tx * p.TW; y0 = ty * p.TH; n0 = tn * p.TN;
   };
 
+  // Producer and MMA warps run their loops WARP-UNIFORMLY and elect one lane only around the TMA / MMA
+  // issue (under a divergent `lane == 0` branch nvcc wraps every uniform-datapath instruction - UTMALDG,
+  // UTCHMMA, UTCBAR - in an elect-and-retry loop).
+  // G consecutive k-blocks share ONE full/empty barrier pair: measured on B200 (scratch microbenchmarks,
+  // DESIGN.md section 3), every mbarrier wait in the MMA-issuing thread stalls it for ~105 cycles while
+  // the tensor pipe only queues ~1-2 instructions, so each wait is a ~135-cycle bubble unless the MMAs
+  // are N=256 wide (128 cycles each).  Grouping halves the number of waits per MMA.
+  constexpr int kGroups = STAGES / G;
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        int z, nt, g;
-        decode(w, z, nt, g);
-        const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : z];
-        int kb0, kb1;
-        k_range(z, ph, kb0, kb1);
-        if (kb1 == kb0) continue;
-        const int tile0 = g * MT;
-        const int nvalid = min(MT, total_tiles - tile0);
-        int x0s[MT], y0s[MT], n0s[MT];
+    int grp = 0;
+    uint32_t phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      int z, nt, g;
+      decode(w, z, nt, g);
+      const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : z];
+      int kb0, kb1;
+      k_range(z, ph, kb0, kb1);
+      if (kb1 == kb0) continue;
+      const int tile0 = g * MT;
+      const int nvalid = min(MT, total_tiles - tile0);
+      int x0s[MT], y0s[MT], n0s[MT];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) tile_origin(tile0 + m, x0s[m], y0s[m], n0s[m]);
-        const int ncol0 = nt * BN;
-        int tp = kb0 / p.k_chunks, kc = kb0 % p.k_chunks;
-        for (int i = kb0; i < kb1; ++i) {
-          const TcTap tap = ph.taps[tp];
-          const CUtensorMap* im = &p.in_maps[tap.map];
-          ptx::mbar_wait(&empty[stage], phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(&full[stage], nvalid * kABytes + kBBytes);
+      for (int m = 0; m < MT; ++m) tile_origin(tile0 + m, x0s[m], y0s[m], n0s[m]);
+      const int ncol0 = nt * BN;
+      int tp = kb0 / p.k_chunks, kc = kb0 % p.k_chunks;
+      for (int i = kb0; i < kb1; i += G) {
+        const int nk = min(G, kb1 - i);
+        ptx::mbar_wait(&empty[grp], phase ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&full[grp], nk * (nvalid * kABytes + kBBytes));
 #pragma unroll
-          for (int m = 0; m < MT; ++m)
-            if (m < nvalid)
-              ptx::tma_load_4d(sA + stage * kAStage + m * kABytes, im, &full[stage], kc * 64, x0s[m] + tap.dx, y0s[m] + tap.dy, n0s[m]);
-          ptx::tma_load_2d(sB + stage * kBBytes, &p.w_map, &full[stage], kc * 64, tap.wrow + ncol0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          if (++kc == p.k_chunks) { kc = 0; ++tp; }
+          for (int j = 0; j < G; ++j) {
+            if (j < nk) {
+              const TcTap tap = ph.taps[tp];
+              const CUtensorMap* im = &p.in_maps[tap.map];
+              const int stage = grp * G + j;
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                if (m < nvalid)
+                  ptx::tma_load_4d(sA + stage * kAStage + m * kABytes, im, &full[grp], kc * 64, x0s[m] + tap.dx, y0s[m] + tap.dy, n0s[m]);
+              ptx::tma_load_2d(sB + stage * kBBytes, &p.w_map, &full[grp], kc * 64, tap.wrow + ncol0);
+              if (++kc == p.k_chunks) { kc = 0; ++tp; }
+            }
+          }
         }
+        __syncwarp();
+        // every lane tracks (tp, kc): only the elected lane advanced them above
+        {
+          const int adv = (i - kb0) + nk + kb0;        // absolute k-block index after this group
+          tp = adv / p.k_chunks; kc = adv - tp * p.k_chunks;
+        }
+        if (++grp == kGroups) { grp = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;                       // number of accumulator uses so far
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        int z, nt, g;
-        decode(w, z, nt, g);
-        const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : z];
-        int kb0, kb1;
-        k_range(z, ph, kb0, kb1);
-        if (kb1 == kb0) continue;
-        const int nvalid = min(MT, total_tiles - g * MT);
-        const int as = it & 1;
-        ptx::mbar_wait(&acc_empty[as], (uint32_t)(((it >> 1) & 1) ^ 1));
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t kDescHi = ptx::smem_desc_hi(1024);
+    const uint32_t a_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sA), 16), b_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sB), 16);
+    uint32_t a_lo = a_lo0, b_lo = b_lo0;      // descriptor low words of the current group's first stage
+    int grp = 0;
+    uint32_t phase = 0;
+    int it = 0;                       // number of accumulator uses so far
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      int z, nt, g;
+      decode(w, z, nt, g);
+      const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : z];
+      int kb0, kb1;
+      k_range(z, ph, kb0, kb1);
+      if (kb1 == kb0) continue;
+      const int nvalid = min(MT, total_tiles - g * MT);
+      const int as = it & 1;
+      ptx::mbar_wait(&acc_empty[as], (uint32_t)(((it >> 1) & 1) ^ 1));
+      ptx::tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(as * kAccCols);
+      for (int i = kb0; i < kb1; i += G) {
+        const int nk = min(G, kb1 - i);
+        ptx::mbar_wait(&full[grp], phase);
         ptx::tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)(as * kAccCols);
-        for (int i = kb0; i < kb1; ++i) {
-          ptx::mbar_wait(&full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(sA + stage * kAStage);
-          const uint32_t b_addr = ptx::smem_u32(sB + stage * kBBytes);
+        if (ptx::elect_one()) {
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            if (m < nvalid) {
+          for (int j = 0; j < G; ++j) {
+            if (j < nk) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = ptx::make_smem_desc(a_addr + m * kABytes + k * 32, 16, 1024);
-                const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
-                ptx::mma_bf16_ss(acc + (uint32_t)(m * BN), ad, bd, idesc, (i > kb0) || (k > 0));
+              for (int m = 0; m < MT; ++m) {
+                if (m < nvalid) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    ptx::mma_bf16_ss_lohi(acc + (uint32_t)(m * BN), a_lo + (uint32_t)((j * kAStage + m * kABytes + k * 32) >> 4),
+                                          b_lo + (uint32_t)((j * kBBytes + k * 32) >> 4), kDescHi, idesc, (i + j > kb0) || (k > 0));
+                }
               }
             }
           }
-          ptx::mma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          ptx::mma_commit(&empty[grp]);
         }
-        ptx::mma_commit(&acc_full[as]);
-        ++it;
+        __syncwarp();
+        if (++grp == kGroups) { grp = 0; phase ^= 1u; a_lo = a_lo0; b_lo = b_lo0; }
+        else { a_lo += (uint32_t)((G * kAStage) >> 4); b_lo += (uint32_t)((G * kBBytes) >> 4); }
       }
+      if (ptx::elect_one()) ptx::mma_commit(&acc_full[as]);
+      __syncwarp();
+      ++it;
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
@@ -563,6 +602,232 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster - two SMs - issue ONE M=256 MMA.  Each CTA
+// stages its own MT pixel tiles (A, 128 rows each) and HALF of the weight tile (B, BN/2 rows); the
+// tensor core of each SM reads its own A and both halves of B, so the per-SM shared-memory reads per
+// MMA drop from (4 KB + BN*32 B) to (4 KB + BN*16 B) and the staged weight bytes halve as well.
+// Protocol (leader = cluster rank 0):
+//   * producer thread in BOTH CTAs: waits its own empty[s] (multicast commit), issues its TMA loads
+//     with the completion bytes counted on the LEADER's full[s]; the leader arms full[s] with the
+//     bytes of both CTAs;
+//   * MMA thread in the leader only; tcgen05.commit multicasts to empty[s] / acc_full[a] of both CTAs;
+//   * epilogue warps in both CTAs drain their own TMEM and arrive (cluster scope) on the leader's
+//     acc_empty[a], which therefore counts 2*EW arrivals.
+// Requires total pixel tiles % (2*MT) == 0 (the host falls back to the single-CTA kernel otherwise).
+// ------------------------------------------------------------------------------------------
+template <int BN, int MT, int STAGES, int EW>
+struct ConvPairSmem {
+  static constexpr int kBBytes = (BN / 2) * 128;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <int BN, int MT, int STAGES, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
+    tc_conv_pair_kernel(const __grid_constant__ TcConvParams p, int n_ntiles, int n_groups, int n_z, int n_work) {
+  static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
+  constexpr int kChunkGroups = EW / 4;
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int kBBytes = (BN / 2) * 128;
+  constexpr int kAStage = MT * kABytes;
+  constexpr int kAccCols = MT * BN;
+  constexpr int kTmemCols = 2 * kAccCols;
+  static_assert(kTmemCols <= 512 && kTmemCols >= 32, "TMEM budget");
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kAStage;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * kBBytes);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;       // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.w_map);
+    ptx::prefetch_tmap(&p.in_maps[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&acc_full[a], 1);
+      ptx::mbar_init(&acc_empty[a], 2 * EW);   // every epilogue warp of both CTAs
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc_pair<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();                         // barriers of BOTH CTAs exist before anyone signals them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int w, int& z, int& nt, int& g) {
+    const int per_z = n_ntiles * n_groups;
+    z = w / per_z;
+    const int r = w - z * per_z;
+    nt = r / n_groups;
+    g = r - nt * n_groups;
+  };
+  auto k_range = [&](int z, const TcPhase& ph, int& kb0, int& kb1) {
+    const int total = ph.ntaps * p.k_chunks;
+    if (p.ksplit > 1) { kb0 = z * p.k_per_split; kb1 = min(total, kb0 + p.k_per_split); }
+    else { kb0 = 0; kb1 = total; }
+    if (kb1 < kb0) kb1 = kb0;
+  };
+  auto tile_origin = [&](int t, int& x0, int& y0, int& n0) {
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int tn = t / p.tiles_y;
+    x0 = tx * p.TW; y0 = ty * p.TH; n0 = tn * p.TN;
+  };
+
+  if (warp == 0) {
+    {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = pair; w < n_work; w += n_pairs) {
+        int z, nt, g;
+        decode(w, z, nt, g);
+        const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : z];
+        int kb0, kb1;
+        k_range(z, ph, kb0, kb1);
+        if (kb1 == kb0) continue;
+        const int tile0 = (g * 2 + (int)rank) * MT;      // this CTA's pixel tiles of the pair's group
+        int x0s[MT], y0s[MT], n0s[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) tile_origin(tile0 + m, x0s[m], y0s[m], n0s[m]);
+        const int nrow0 = nt * BN + (int)rank * (BN / 2);  // this CTA's half of the weight tile
+        int tp = kb0 / p.k_chunks, kc = kb0 % p.k_chunks;
+        for (int i = kb0; i < kb1; ++i) {
+          const TcTap tap = ph.taps[tp];
+          const CUtensorMap* im = &p.in_maps[tap.map];
+          ptx::mbar_wait(&empty[stage], phase ^ 1u);
+          if (ptx::elect_one()) {
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * (kAStage + kBBytes));
+            const uint32_t bar = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              ptx::tma_load_4d_pair(sA + stage * kAStage + m * kABytes, im, bar, kc * 64, x0s[m] + tap.dx, y0s[m] + tap.dy, n0s[m]);
+            ptx::tma_load_2d_pair(sB + stage * kBBytes, &p.w_map, bar, kc * 64, tap.wrow + nrow0);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++kc == p.k_chunks) { kc = 0; ++tp; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(256, BN, 0, 0);
+      constexpr uint32_t kDescHi = ptx::smem_desc_hi(1024);
+      const uint32_t a_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sA), 16), b_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sB), 16);
+      uint32_t a_lo = a_lo0, b_lo = b_lo0;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = pair; w < n_work; w += n_pairs) {
+        int z, nt, g;
+        decode(w, z, nt, g);
+        const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : z];
+        int kb0, kb1;
+        k_range(z, ph, kb0, kb1);
+        if (kb1 == kb0) continue;
+        const int as = it & 1;
+        ptx::mbar_wait(&acc_empty[as], (uint32_t)(((it >> 1) & 1) ^ 1));
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(as * kAccCols);
+        for (int i = kb0; i < kb1; ++i) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::mma_bf16_ss_pair_lohi(acc + (uint32_t)(m * BN), a_lo + (uint32_t)((m * kABytes + k * 32) >> 4),
+                                           b_lo + (uint32_t)((k * 32) >> 4), kDescHi, idesc, (i > kb0) || (k > 0));
+            }
+            ptx::mma_commit_pair(&empty[stage], 3);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; b_lo = b_lo0; }
+          else { a_lo += (uint32_t)(kAStage >> 4); b_lo += (uint32_t)(kBBytes >> 4); }
+        }
+        if (ptx::elect_one()) ptx::mma_commit_pair(&acc_full[as], 3);
+        __syncwarp();
+        ++it;
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int q = ew & 3;
+    const int cgrp = ew >> 2;
+    const int row = q * 32 + lane;
+    const int xl = row & (p.TW - 1);
+    const int yl = (row >> p.tw_log2) & (p.TH - 1);
+    const int nl = row >> (p.tw_log2 + p.th_log2);
+    int it = 0;
+    float unused_s = 0.f, unused_q = 0.f;
+    for (int w = pair; w < n_work; w += n_pairs) {
+      int z, nt, g;
+      decode(w, z, nt, g);
+      const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : z];
+      int kb0, kb1;
+      k_range(z, ph, kb0, kb1);
+      const bool has_k = kb1 > kb0;
+      if (!has_k && p.ksplit > 1) continue;
+      const int tile0 = (g * 2 + (int)rank) * MT;
+      const int ncol0 = nt * BN;
+      const int as = it & 1;
+      if (has_k) {
+        ptx::mbar_wait(&acc_full[as], (uint32_t)((it >> 1) & 1));
+        ptx::tc_fence_after();
+      }
+      const uint32_t acc = tmem_base + (uint32_t)(as * kAccCols) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        int x0, y0, n0;
+        tile_origin(tile0 + m, x0, y0, n0);
+        const int gx = x0 + xl, gy = y0 + yl, gn = n0 + nl;
+        const bool valid = gx < p.gw && gy < p.gh && gn < p.gn;
+        const long long opix = ((long long)gn * p.OH + (long long)gy * p.os + ph.oy_off) * p.OW + (long long)gx * p.os + ph.ox_off;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          if ((c % kChunkGroups) != cgrp) continue;
+          const int c0 = c * 32;
+          uint32_t r[32];
+          if (has_k) {
+            ptx::tmem_ld_32x32(acc + (uint32_t)(m * BN + c0), r);
+            ptx::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
+          epilogue_chunk(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, nullptr, lane, unused_s, unused_q);
+        }
+      }
+      if (has_k) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&acc_empty[as]), 0));
+        ++it;
+      }
+    }
+  }
+  // neither CTA may retire while the other can still signal its barriers or read its shared memory
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 2) ptx::tmem_dealloc_pair<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
 // weight gradient
 // ------------------------------------------------------------------------------------------
 template <int NB, int STAGES>
@@ -611,20 +876,21 @@ __global__ void __launch_bounds__(kTcThreads) tc_wgrad_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (num_k > 0) {
+    // role warps loop warp-uniformly; one elected lane issues the TMA / MMA instructions (see tc_conv_kernel)
     if (warp == 0) {
-      if (lane == 0) {
-        const int tapA = slab0 / p.cs_chunks, chA = slab0 % p.cs_chunks;
-        const int tapB = slab1 / p.cs_chunks, chB = slab1 % p.cs_chunks;
-        const TcTap ta = p.taps[tapA], tb = p.taps[tapB];
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int b = box_begin; b < box_end; ++b) {
-          int t = b;
-          const int tx = t % p.tiles_x; t /= p.tiles_x;
-          const int ty = t % p.tiles_y;
-          const int tn = t / p.tiles_y;
-          const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
-          ptx::mbar_wait(&empty[stage], phase ^ 1u);
+      const int tapA = slab0 / p.cs_chunks, chA = slab0 % p.cs_chunks;
+      const int tapB = slab1 / p.cs_chunks, chB = slab1 % p.cs_chunks;
+      const TcTap ta = p.taps[tapA], tb = p.taps[tapB];
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b = box_begin; b < box_end; ++b) {
+        int t = b;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int tn = t / p.tiles_y;
+        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+        ptx::mbar_wait(&empty[stage], phase ^ 1u);
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[stage], kStageBytes);
           uint8_t* st = smem + stage * kStageBytes;
           ptx::tma_load_4d(st, &p.s_maps[ta.map], &full[stage], chA * 64, x0 + ta.dx, y0 + ta.dy, n0);
@@ -632,30 +898,33 @@ __global__ void __launch_bounds__(kTcThreads) tc_wgrad_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < NB; ++j)
             ptx::tma_load_4d(st + (2 + j) * 8192, &p.u_map, &full[stage], (blockIdx.y * NB + j) * 64, x0, y0, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 1, 1);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int i = 0; i < num_k; ++i) {
-          ptx::mbar_wait(&full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem + stage * kStageBytes);
-          const uint32_t b_addr = a_addr + 2 * 8192;
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN, 1, 1);
+      constexpr uint32_t kDescHi = ptx::smem_desc_hi(1024);
+      const uint32_t a_lo0 = ptx::smem_desc_lo(ptx::smem_u32(smem), 8192);   // MN-major: LBO = 64-channel slab stride
+      uint32_t a_lo = a_lo0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < num_k; ++i) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 16 pixels (two 8-row atoms) per MMA
-            const uint64_t ad = ptx::make_smem_desc(a_addr + k * 2048, 8192, 1024);
-            const uint64_t bd = ptx::make_smem_desc(b_addr + k * 2048, 8192, 1024);
-            ptx::mma_bf16_ss(tmem_base, ad, bd, idesc, (i | k) != 0);
-          }
+          for (int k = 0; k < 4; ++k)     // 16 pixels (two 8-row atoms) per MMA
+            ptx::mma_bf16_ss_lohi(tmem_base, a_lo + (uint32_t)((k * 2048) >> 4), a_lo + (uint32_t)((2 * 8192 + k * 2048) >> 4), kDescHi,
+                                  idesc, (i | k) != 0);
           ptx::mma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        ptx::mma_commit(tmem_full);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
+        else a_lo += (uint32_t)(kStageBytes >> 4);
       }
+      if (ptx::elect_one()) ptx::mma_commit(tmem_full);
+      __syncwarp();
     }
   }
 
@@ -856,11 +1125,11 @@ static int launch_conv(const TcConvParams& p, dim3 grid, cudaStream_t s) {
   return VG_OK;
 }
 
-template <int BN, int MT, int STAGES, int EW>
+template <int BN, int MT, int STAGES, int EW, int G>
 static int launch_conv_persist(const TcConvParams& p, dim3 grid, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    VG_CUDA(cudaFuncSetAttribute(tc_conv_persist_kernel<BN, MT, STAGES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VG_CUDA(cudaFuncSetAttribute(tc_conv_persist_kernel<BN, MT, STAGES, EW, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  ConvPersistSmem<BN, MT, STAGES, EW>::kBytes));
     attr_done = true;
   }
@@ -869,7 +1138,26 @@ static int launch_conv_persist(const TcConvParams& p, dim3 grid, cudaStream_t s)
   const int n_z = (int)grid.z;
   const long long n_work = (long long)n_groups * n_ntiles * n_z;
   const int ctas = (int)std::min<long long>(n_work, num_sms());
-  tc_conv_persist_kernel<BN, MT, STAGES, EW><<<ctas, 128 + 32 * EW, ConvPersistSmem<BN, MT, STAGES, EW>::kBytes, s>>>(
+  tc_conv_persist_kernel<BN, MT, STAGES, EW, G><<<ctas, 128 + 32 * EW, ConvPersistSmem<BN, MT, STAGES, EW>::kBytes, s>>>(
+      p, n_ntiles, n_groups, n_z, (int)n_work);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+template <int BN, int MT, int STAGES, int EW>
+static int launch_conv_pair(const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    VG_CUDA(cudaFuncSetAttribute(tc_conv_pair_kernel<BN, MT, STAGES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 ConvPairSmem<BN, MT, STAGES, EW>::kBytes));
+    attr_done = true;
+  }
+  const int n_groups = (int)(grid.x / (2 * MT));      // the caller checked divisibility
+  const int n_ntiles = (int)grid.y;
+  const int n_z = (int)grid.z;
+  const long long n_work = (long long)n_groups * n_ntiles * n_z;
+  const int pairs = (int)std::min<long long>(n_work, num_sms() / 2);
+  tc_conv_pair_kernel<BN, MT, STAGES, EW><<<2 * pairs, 128 + 32 * EW, ConvPairSmem<BN, MT, STAGES, EW>::kBytes, s>>>(
       p, n_ntiles, n_groups, n_z, (int)n_work);
   VG_LAUNCHED();
   return VG_OK;
@@ -1025,11 +1313,28 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
     p.stats = stats;
     if (stats_fused) *stats_fused = true;
   }
+  // CTA pairs (cta_group::2) halve the per-SM shared-memory operand reads that bound the narrow tiles
+  static int pair_on = -1;
+  if (pair_on < 0) { const char* e = getenv("VG_TC_PAIR"); pair_on = e ? atoi(e) : 6; }   // bit0: BN=64, bit1: BN=128, bit2: BN=256
+  if (use_persist && pair_on && p.stats == nullptr && p.n_store != 1) {
+    const int mt = BN == 64 ? 4 : (BN == 128 ? 2 : 1);
+    if (grid.x % (2 * mt) == 0 && (pair_on & (BN == 64 ? 1 : (BN == 128 ? 2 : 4)))) {
+      if ((rc = make_weight_map(&p.w_map, wpack, (long long)k * k * n_out, in_c, BN / 2))) return rc;
+      switch (BN) {
+        case 64: return launch_conv_pair<64, 4, 3, 4>(p, grid, s);
+        case 128: return launch_conv_pair<128, 2, 4, 8>(p, grid, s);
+        case 256: return launch_conv_pair<256, 1, 6, 8>(p, grid, s);
+        default: break;
+      }
+    }
+  }
+  static int grp2 = -1;
+  if (grp2 < 0) { const char* e = getenv("VG_TC_GROUP"); grp2 = e ? (atoi(e) == 2) : 0; }
   if (use_persist) {
     switch (BN) {
-      case 64: return launch_conv_persist<64, 4, 3, 4>(p, grid, s);
-      case 128: return launch_conv_persist<128, 2, 4, 8>(p, grid, s);
-      case 256: return launch_conv_persist<256, 1, 4, 8>(p, grid, s);
+      case 64: return launch_conv_persist<64, 4, 3, 4, 1>(p, grid, s);
+      case 128: return grp2 ? launch_conv_persist<128, 2, 4, 8, 2>(p, grid, s) : launch_conv_persist<128, 2, 4, 8, 1>(p, grid, s);
+      case 256: return grp2 ? launch_conv_persist<256, 1, 4, 8, 2>(p, grid, s) : launch_conv_persist<256, 1, 4, 8, 1>(p, grid, s);
       default: break;
     }
   }
