@@ -162,29 +162,48 @@ __global__ void sn_wt_u_kernel(const float* __restrict__ W, const float* __restr
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cols) return;
   int r0 = blockIdx.y * rows_per_slice, r1 = min(rows, r0 + rows_per_slice);
-  float s = 0.f;
-  for (int i = r0; i < r1; ++i) s = fmaf(W[(long long)i * cols + j], u[i], s);
-  atomicAdd(&t[j], s);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int i = r0;
+  for (; i + 4 <= r1; i += 4) {      // four independent loads in flight per thread
+    const float* wp = W + (long long)i * cols + j;
+    s0 = fmaf(wp[0], u[i], s0);
+    s1 = fmaf(wp[cols], u[i + 1], s1);
+    s2 = fmaf(wp[2LL * cols], u[i + 2], s2);
+    s3 = fmaf(wp[3LL * cols], u[i + 3], s3);
+  }
+  for (; i < r1; ++i) s0 = fmaf(W[(long long)i * cols + j], u[i], s0);
+  atomicAdd(&t[j], (s0 + s1) + (s2 + s3));
 }
-// one warp per row: s[i] = (W[i] . t) / max(||t||, eps)   (normalize=1), or W[i] . t (normalize=0);
-// the warp of row 0 also writes v = t / max(||t||, eps)
-__global__ void sn_w_v_kernel(const float* __restrict__ W, const float* __restrict__ t, int rows, int cols, int normalize, float eps,
-                              float* __restrict__ v_out, float* __restrict__ s_out) {
-  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+// one 128-thread block per row: s[i] = (W[i] . t) / max(||t||, eps)   (normalize=1), or W[i] . t (normalize=0);
+// the block of row 0 also writes v = t / max(||t||, eps)
+__global__ void __launch_bounds__(128) sn_w_v_kernel(const float* __restrict__ W, const float* __restrict__ t, int rows, int cols,
+                                                     int normalize, float eps, float* __restrict__ v_out, float* __restrict__ s_out) {
+  const int row = blockIdx.x;
   float dot = 0.f, nt = 0.f;
-  for (int j = lane; j < cols; j += 32) {
+  const float* wr = W + (long long)row * cols;
+  for (int j = threadIdx.x; j < cols; j += 128) {
     float tv = t[j];
-    dot = fmaf(W[(long long)row * cols + j], tv, dot);
+    dot = fmaf(wr[j], tv, dot);
     nt = fmaf(tv, tv, nt);
   }
+  __shared__ float red[2][4];
+  __shared__ float inv_s;
   dot = warp_sum(dot);
   nt = warp_sum(nt);
-  float inv = normalize ? 1.0f / fmaxf(sqrtf(nt), eps) : 1.0f;
-  if (lane == 0) s_out[row] = dot * inv;
-  if (normalize && row == 0 && v_out != nullptr)
-    for (int j = lane; j < cols; j += 32) v_out[j] = t[j] * inv;
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = dot; red[1][threadIdx.x >> 5] = nt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float d = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+    const float n = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+    const float inv = normalize ? 1.0f / fmaxf(sqrtf(n), eps) : 1.0f;
+    s_out[row] = d * inv;
+    inv_s = inv;
+  }
+  if (normalize && row == 0 && v_out != nullptr) {
+    __syncthreads();
+    const float inv = inv_s;
+    for (int j = threadIdx.x; j < cols; j += 128) v_out[j] = t[j] * inv;
+  }
 }
 // single block: training: u = s / max(||s||, eps); sigma = sum u*s.  eval: sigma = sum u*s.
 __global__ void sn_finish_kernel(const float* __restrict__ s, float* __restrict__ u, int rows, int training, float eps,
@@ -606,15 +625,15 @@ extern "C" int vg_spectral_norm_sigma(const float* w_orig, int rows, int cols, f
   float* sv = workspace + cols;    // [rows]
   if (training) {
     VG_CUDA(cudaMemsetAsync(t, 0, (size_t)cols * sizeof(float), s));
-    int slices = std::max(1, std::min(rows / 32, 16));
+    int slices = std::max(1, std::min(rows / 8, 64));
     int rps = (int)cdiv(rows, slices);
     dim3 g1((unsigned)cdiv(cols, 128), (unsigned)cdiv(rows, rps));
     sn_wt_u_kernel<<<g1, 128, 0, s>>>(w_orig, u, rows, cols, rps, t);
     VG_LAUNCHED();
-    sn_w_v_kernel<<<(unsigned)cdiv((long long)rows * 32, 256), 256, 0, s>>>(w_orig, t, rows, cols, 1, eps, v, sv);
+    sn_w_v_kernel<<<(unsigned)rows, 128, 0, s>>>(w_orig, t, rows, cols, 1, eps, v, sv);
     VG_LAUNCHED();
   } else {
-    sn_w_v_kernel<<<(unsigned)cdiv((long long)rows * 32, 256), 256, 0, s>>>(w_orig, v, rows, cols, 0, eps, nullptr, sv);
+    sn_w_v_kernel<<<(unsigned)rows, 128, 0, s>>>(w_orig, v, rows, cols, 0, eps, nullptr, sv);
     VG_LAUNCHED();
   }
   sn_finish_kernel<<<1, 256, 0, s>>>(sv, u, rows, training, eps, sigma);
