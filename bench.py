@@ -194,13 +194,13 @@ def roofline_probe(dev, batch: int, peaks):
     avg = sum(ms[1:-1]) / (len(ms) - 2)
     flops = 2.0 * batch * IMAGE * IMAGE * cout * cin * 9
     achieved = flops / (avg * 1e-3) / 1e12
-    # DRAM traffic of this exact launch from `ncu --set full` (profiles/r1_ncu_full_dominant_conv_128x128_b64.csv):
-    # 151.4 MB read (= the input tensor, once) + 101.2 MB written (the rest of the 151 MB output still sits in
+    # DRAM traffic of this exact launch from `ncu --set full` (profiles/r1_ncu_full_pair_conv_128x128_b64.csv):
+    # 151.4 MB read (= the input tensor, once) + 101.7 MB written (the rest of the 151 MB output still sits in
     # the 126 MB L2 when the kernel ends); algorithmic bytes = 151 + 151 + 0.3 MB.
-    traffic = 252.7e6 * batch / 64.0 if batch == 64 else None
+    traffic = 253.1e6 * batch / 64.0 if batch == 64 else None
     return {"bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["bf16"], "unit": "TFLOP/s",
             "frac": round(achieved / peaks["bf16"], 4), "traffic": traffic,
-            "kernel": "tc_conv_persist_kernel<128,2,4> (persistent tcgen05 implicit GEMM), Conv2d 128->128 3x3 s1 @96x96",
+            "kernel": "tc_conv_pair_kernel<128,2,4,8> (persistent cta_group::2 tcgen05 implicit GEMM), Conv2d 128->128 3x3 s1 @96x96",
             "batch": batch, "ms_per_launch": round(avg, 4), "flop_per_launch": flops,
             "peak_source": f"{peaks['source']} bf16 burst (kernel timed alone)"}
 
