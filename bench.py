@@ -252,6 +252,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--fp32", action="store_true", help="run the fp32 parity path instead of bf16")
+    ap.add_argument("--loss-mode", default="bce", choices=["bce", "wgan", "wgan_gp"],
+                    help="bce + adam = BASELINE north_star (default); wgan_gp + --optimizer rmsprop = the notebook as written")
+    ap.add_argument("--optimizer", default="adam", choices=["adam", "rmsprop"])
     ap.add_argument("--workload", default="train", choices=["train", "cfg4", "decode"],
                     help="train: BASELINE metric (96x96, fs 64); cfg4: 256x256, widths x2; decode: config-5 sampling sweep")
     args = ap.parse_args()
@@ -291,7 +294,7 @@ def main():
     with V.compute_dtype(cdt):
         G, D = V.build_vae_gan(feature_size=FEATURE, image_size=IMAGE)
         G, D = G.to(dev).train(), D.to(dev).train()
-        tr = V.VaeGanTrainer(G, D, loss_mode="bce", optimizer="adam", lr=3e-4, process_group=pg)
+        tr = V.VaeGanTrainer(G, D, loss_mode=args.loss_mode, optimizer=args.optimizer, lr=3e-4, process_group=pg)
         V.config.sample_offset = rank * local_b
         g = torch.Generator().manual_seed(1234 + rank)
         n_host = 4
@@ -389,10 +392,13 @@ def main():
             "steps": K, "warmup": W, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if args.fp32 else "bf16", "data": "synthetic",
             "config": {
-                "workload": f"full VAE-GAN train step (encoder+decoder+discriminator, KL + L1/MSE + adversarial BCE, Adam), "
+                "workload": "full VAE-GAN train step (encoder+decoder+discriminator, KL + L1/MSE + " +
+                            {"bce": "adversarial BCE", "wgan": "critic loss + clamp", "wgan_gp": "critic loss + 10 x gradient penalty "
+                             "(double backward) + clamp"}[args.loss_mode] + f", {args.optimizer}), "
                             f"1x{IMAGE}x{IMAGE} images, depth 2 / length 1 / feature_size {FEATURE}, global batch "
                             f"{args.global_batch} ({local_b}/GPU), SyncBN + gradient all-reduce" + ("" if world > 1 else " (1 GPU: no collectives)"),
                 "global_batch": args.global_batch, "per_gpu_batch": local_b, "parallelism": f"dp{world}", "mode": mode,
+                "loss_mode": args.loss_mode, "optimizer": args.optimizer,
                 "l2_note": "activations of one step (several GB) far exceed the 126 MB L2; no flush needed",
             },
             "clocks": clocks,

@@ -157,6 +157,10 @@ int vg_dropout2d_scale(float* scale, int n, int c, float p, unsigned long long s
 /* standard normal noise, element i uses Philox index start+i */
 int vg_philox_normal(float* out, long long n, unsigned long long seed, unsigned long long offset,
                      const unsigned long long* step_ptr, long long start, vg_stream_t stream);
+/* uniform [0,1) noise, element i = (Philox word of index start+i >> 8) * 2^-24: the gradient-penalty
+   interpolation weights (replaces np.random.random, README.md:719) */
+int vg_philox_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                      const unsigned long long* step_ptr, long long start, vg_stream_t stream);
 /* *counter += inc (device-side step counter used by the step_ptr arguments) */
 int vg_counter_add(unsigned long long* counter, unsigned long long inc, vg_stream_t stream);
 

@@ -559,6 +559,14 @@ def philox_uint32(n_elems: int, seed: int, offset: int, start: int = 0):
     return words[np.arange(n_elems), (idx & np.uint64(3)).astype(np.int64)]
 
 
+def philox_uniform(n_elems: int, seed: int, offset: int, start: int = 0):
+    """float32 uniform [0,1): (word >> 8) * 2^-24 (the gradient-penalty interpolation weights)."""
+    import numpy as np
+
+    w = philox_uint32(n_elems, seed, offset, start)
+    return ((w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+
+
 def philox_keep_mask(n_elems: int, seed: int, offset: int, p: float, start: int = 0):
     """Elementwise-dropout keep mask (uint8), identical to the CUDA kernels: element e uses the
     16-bit half-word (e & 7) of Philox block (e >> 3); keep iff half-word >= floor(p * 65536)."""

@@ -233,6 +233,7 @@ def test_discriminator_full_size_vs_oracle(dtype):
         D = D.to(dev()).train()
         v.rng.seed = 7
         v.rng.reset_sites()
+        v.rng.step_tensor(dev()).zero_()
         xi = x.to(dev()).requires_grad_(True)
         logits = D(xi)
         (logits * wts.to(dev())).sum().backward()
@@ -292,9 +293,17 @@ def _run_trainer_vs_oracle(dtype, loss_mode, opt, B, S, fs, steps, tol_loss, max
             gm, site = generator_masks(spec_g, B, S, seed, 0, step)
             dm_real, site = discriminator_masks(spec_d, B, seed, site, step)
             dm_fake, site = discriminator_masks(spec_d, B, seed, site, step)
+            dm_gp = alpha = None
+            if loss_mode == "wgan_gp":       # one Philox site for the interpolation weights, then D(interpolates)
+                alpha = torch.from_numpy(O.philox_uniform(B, seed, site + 65536 * step)).view(B, 1, 1, 1).to(F64)
+                dm_gp, site = discriminator_masks(spec_d, B, seed, site + 1, step)
             dm_gen, site = discriminator_masks(spec_d, B, seed, site, step)
             want = O.train_step(Pg_r, Pd_r, og, od, xs[i].to(F64), spec_g, spec_d, eps_noise=epss[i].to(F64), g_masks=gm,
-                                d_masks_real=dm_real, d_masks_fake=dm_fake, d_masks_gen=dm_gen, loss_mode=loss_mode)
+                                d_masks_real=dm_real, d_masks_fake=dm_fake, d_masks_gen=dm_gen, loss_mode=loss_mode,
+                                d_masks_gp=dm_gp, gp_alpha=alpha)
+            if loss_mode == "wgan_gp":
+                w = float(want["gp"])
+                assert abs(got["gp"] - w) <= 10 * tol_loss * max(abs(w), 1e-2), (i, "gp", got["gp"], w)
             for k in ("d_loss", "g_loss", "recon", "kl", "adv"):
                 w = float(want[k])
                 # adv is evaluated after the D update (Adam's lr*sign(g) step amplifies bf16 noise)
@@ -333,6 +342,57 @@ def test_train_step_fp32_bce_adam_vs_oracle():
 def test_train_step_fp32_wgan_rmsprop_vs_oracle():
     """The reference's own critic loss + clamp + RMSprop (without the gradient penalty)."""
     _run_trainer_vs_oracle(torch.float32, "wgan", "rmsprop", B=2, S=32, fs=8, steps=2, tol_loss=5e-5, max_bad_frac=2e-3)
+
+
+def test_train_step_fp32_wgan_gp_rmsprop_vs_oracle():
+    """The notebook's iteration exactly as written (README.md:775-834): critic loss + 10 x gradient penalty
+    (double backward through the discriminator) + clamp + RMSprop."""
+    _run_trainer_vs_oracle(torch.float32, "wgan_gp", "rmsprop", B=2, S=32, fs=8, steps=2, tol_loss=1e-4, max_bad_frac=5e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gradient_penalty_vs_oracle(dtype):
+    """compute_gradient_penalty (README.md:717-739) through OUR discriminator with torch.autograd.grad(create_graph=True)
+    exactly as the reference calls it: the penalty and its parameter gradients vs the fp64 oracle."""
+    v = V()
+    from vae_gan_b200.gp import gradient_penalty
+    full = dtype == torch.bfloat16
+    B, S, fs = (4, 96, 64) if full else (3, 32, 8)
+    spec = O.DiscriminatorSpec(1, fs, (1, 1, 1), (1, 2, 2), (2 * fs, 4 * fs, 8 * fs), input_size=S)
+    P = O.make_discriminator_params(spec, seed=14)
+    gen = torch.Generator().manual_seed(123)
+    real, fake = torch.rand(B, 1, S, S, generator=gen), torch.rand(B, 1, S, S, generator=gen)
+    alpha = torch.rand(B, 1, 1, 1, generator=gen)
+    with v.compute_dtype(dtype):
+        _, D = v.build_vae_gan(feature_size=fs, image_size=S)
+        load_params_into(D, P)
+        D = D.to(dev()).train()
+        v.rng.seed = 11
+        v.rng.reset_sites()
+        v.rng.step_tensor(dev()).zero_()
+        gp = gradient_penalty(D, real.to(dev()), fake.to(dev()), alpha.to(dev()))
+        gp.backward()
+    masks, _ = discriminator_masks(spec, B, 11, 0)
+
+    def oracle(dt, autocast=False):
+        Pr = O.clone_params(P, dtype=dt, requires_grad=True)
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+            g = O.gradient_penalty(Pr, spec, real.to(dt), fake.to(dt), alpha.to(dt), masks)
+        keys = O.trainable_keys(Pr)
+        grads = torch.autograd.grad(g, [Pr[k] for k in keys], allow_unused=True)
+        return g.detach(), {k: gr for k, gr in zip(keys, grads) if gr is not None}
+
+    gr, grads = oracle(F64)
+    glp, grads_lp = oracle(torch.float32, autocast=full)
+    tol = 5e-2 if full else 1e-4      # (|g| - 1)^2 doubles the relative error of the bf16 gradient norm
+    gp = gp.detach()
+    err = abs(float(gp) - float(gr)) / max(abs(float(gr)), 1e-6)
+    assert err <= max(tol, 3 * abs(float(glp) - float(gr)) / max(abs(float(gr)), 1e-6)), (float(gp), float(gr))
+    # biases enter the penalty only through LeakyReLU masks: autograd reports exact zeros, we report None
+    named = [(k, p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in D.named_parameters() if k in grads]
+    gerr, skipped = compare_grads(named, grads, 5e-2 if full else 5e-3, f"GP[{dtype}]", ref_lp=grads_lp, slack=3.0, metric=rel_l2,
+                                  skip=EPS_ONLY, allowance=2e-1 if full else 0.0)
+    print(f"[GP {dtype}] penalty {float(gp):.6f} vs {float(gr):.6f} (rel {err:.2e}); grads: {summarize_errs(gerr)}; skipped {skipped}")
 
 
 def test_train_step_bf16_full_size_vs_oracle():

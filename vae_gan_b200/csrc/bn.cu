@@ -603,6 +603,18 @@ __global__ void philox_normal_kernel(float* __restrict__ out, long long n, unsig
   }
 }
 
+// u[i] = (word(start + i) >> 8) * 2^-24 in [0, 1): the gradient-penalty interpolation weights (README.md:719)
+__global__ void philox_uniform_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
+                                      const unsigned long long* step_ptr, long long start) {
+  Philox ph(seed, eff_offset(offset, step_ptr));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long e = (unsigned long long)(start + i);
+    uint4 r = ph.block(e >> 2);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    out[i] = (float)(w[e & 3] >> 8) * 5.9604644775390625e-08f;
+  }
+}
+
 }  // namespace vg
 
 // ==========================================================================================
@@ -882,6 +894,16 @@ __global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc
 extern "C" int vg_counter_add(unsigned long long* counter, unsigned long long inc, vg_stream_t stream) {
   VG_CHECK_ARG(counter, "null pointer");
   counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, inc);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_philox_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                                 const unsigned long long* step_ptr, long long start, vg_stream_t stream) {
+  VG_CHECK_ARG(out && n >= 0 && start >= 0, "bad args");
+  if (n == 0) return VG_OK;
+  int grid = (int)std::min<long long>(cdiv(n, 256), (long long)num_sms() * 8);
+  philox_uniform_kernel<<<grid, 256, 0, as_stream(stream)>>>(out, n, seed, offset, step_ptr, start);
   VG_LAUNCHED();
   return VG_OK;
 }

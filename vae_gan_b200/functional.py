@@ -160,10 +160,11 @@ class ToActFn(Function):
         return as_act(x, dtype)
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, g):
-        g = as_act(g, ctx.in_dtype if ctx.in_dtype in (torch.float32, torch.bfloat16) else torch.float32)
-        return g, None
+        dt = ctx.in_dtype if ctx.in_dtype in (torch.float32, torch.bfloat16) else torch.float32
+        if torch.is_grad_enabled():          # create_graph=True (gradient penalty): stay differentiable
+            return (g if (is_act(g) and g.dtype == dt) else ToActFn.apply(g, dt)), None
+        return as_act(g, dt), None
 
 
 def to_act(x, dtype=None):
@@ -251,14 +252,23 @@ class ConvFn(Function):
         ctx.wshape = tuple(weight.shape)
         ctx.wbuf = getattr(weight, "_vg_grad_buf", None)     # trainer's flat gradient view (fused accumulation)
         ctx.bbuf = getattr(bias, "_vg_grad_buf", None) if bias is not None else None
-        ctx.save_for_backward(x, pack_kn, pack_nk, w if ctx.has_sn else None, sigma, u_saved, v_saved)
+        ctx.save_for_backward(x, pack_kn, pack_nk, w if ctx.has_sn else None, sigma, u_saved, v_saved, weight)
         return y
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dy):
-        x, pack_kn, pack_nk, w, sigma, u, v = ctx.saved_tensors
+        x, pack_kn, pack_nk, w, sigma, u, v, weight = ctx.saved_tensors
         d = ctx.d
+        if torch.is_grad_enabled():          # create_graph=True: differentiable input gradient (vae_gan_b200/gp.py)
+            from . import gp
+            # NOTE: this pass yields the INPUT gradient only (autograd.grad(..., inputs=x, create_graph=True) as in
+            # compute_gradient_penalty); ctx.needs_input_grad cannot tell whether a weight gradient was requested,
+            # so higher-order derivatives with respect to parameters are not available through create_graph.
+            if not ctx.needs_input_grad[0]:
+                return (None,) * 10
+            w_eff = gp.sn_effective_weight(weight, u, v) if ctx.has_sn else weight
+            dx = gp.ConvDgradFn.apply(dy, w_eff, d, x.dtype)
+            return (dx,) + (None,) * 9
         s = stream_ptr()
         dy = as_act(dy, x.dtype)
         dx = dw = db = None
@@ -372,13 +382,19 @@ class BnActFn(Function):
         ctx.d = d
         ctx.gbuf = getattr(gamma, "_vg_grad_buf", None)
         ctx.bbuf = getattr(beta, "_vg_grad_buf", None)
-        ctx.save_for_backward(x, mr, g, b, out_colscale)
+        ctx.save_for_backward(x, mr, g, b, out_colscale, gamma, beta)
         return y
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dy):
-        x, mr, g, b, ocs = ctx.saved_tensors
+        x, mr, g, b, ocs, gamma, beta = ctx.saved_tensors
+        if torch.is_grad_enabled():          # create_graph=True (gradient penalty)
+            from . import gp
+            assert ctx.d.drop_p == 0.0, "second-order path: elementwise dropout is not on the discriminator path"
+            if not ctx.needs_input_grad[0]:
+                return (None,) * 11
+            dx = gp.BnBwdFn.apply(dy, x, gamma, beta, mr, ctx.d, ocs)
+            return (dx,) + (None,) * 10
         dy = as_act(dy, x.dtype)
         dx, dgamma, dbeta = _bn_backward(dy, x, mr, g, b, ctx.d, out_colscale=ocs,
                                          need_dx=ctx.needs_input_grad[0], need_params=ctx.needs_input_grad[1],
@@ -420,13 +436,23 @@ class BnAddFn(Function):
         ctx.bufs_a = (getattr(ga_p, "_vg_grad_buf", None), getattr(ba_p, "_vg_grad_buf", None))
         ctx.bufs_b = (getattr(gb_p, "_vg_grad_buf", None), getattr(bb_p, "_vg_grad_buf", None))
         ctx.save_for_backward(a if mra is not None else None, mra, ga, ba, b if mrb is not None else None, mrb, gb, bb,
-                              out if slope != 1.0 else None)
+                              out if slope != 1.0 else None, ga_p, ba_p, gb_p, bb_p)
         return out
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dout):
-        a, mra, ga, ba, b, mrb, gb, bb, out = ctx.saved_tensors
+        a, mra, ga, ba, b, mrb, gb, bb, out, ga_p, ba_p, gb_p, bb_p = ctx.saved_tensors
+        if torch.is_grad_enabled():          # create_graph=True (gradient penalty)
+            from . import gp
+            dpre = dout * gp.lrelu_mask(out, ctx.slope).to(dout.dtype) if ctx.slope != 1.0 else dout
+            d1 = VgBnDesc.from_buffer_copy(ctx.d)
+            d1.slope = 1.0
+            da = db = None
+            if ctx.needs_input_grad[0]:
+                da = gp.BnBwdFn.apply(dpre, a, ga_p, ba_p, mra, d1, None) if mra is not None else dpre
+            if ctx.needs_input_grad[1]:
+                db = gp.BnBwdFn.apply(dpre, b, gb_p, bb_p, mrb, d1, None) if mrb is not None else dpre
+            return (da, db) + (None,) * 13
         ref = a if a is not None else (b if b is not None else out)
         dtype = ref.dtype if ref is not None else dout.dtype
         dout = as_act(dout, dtype)
@@ -503,6 +529,16 @@ def philox_normal(shape, device, tag="randn"):
     return out
 
 
+def philox_uniform(n, device, tag="uniform"):
+    """`n` uniform [0,1) fp32 numbers indexed by the GLOBAL sample (partition-invariant)."""
+    _lib.ensure_device(device)
+    offset = rng.next_site(tag, (n,))
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    call("vg_philox_uniform", ptr(out), n, rng.seed, offset, ptr(rng.step_tensor(device)), int(config.sample_offset),
+         stream_ptr())
+    return out
+
+
 def export_dropout_mask(shape, drop_p, offset, device, step=None, sample_offset=0, seed=None):
     """Keep-mask bytes (logical NCHW view) for a BnActFn dropout site - used by the tests to feed
     the oracle the very same mask."""
@@ -535,9 +571,11 @@ class AvgPoolFlattenFn(Function):
         return out
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, g):
         n, c, h, w = ctx.shape
+        if torch.is_grad_enabled():          # create_graph=True (gradient penalty)
+            from . import gp
+            return gp.AvgPoolBwdFn.apply(g, ctx.shape, ctx.k, ctx.dtype), None
         g = g.contiguous().float()
         dx = empty_act(n, c, h, w, ctx.dtype, g.device)
         call("vg_avgpool_flatten_backward", ptr(g), n, h, w, c, ctx.k, vg_dtype(ctx.dtype), ptr(dx), stream_ptr())
@@ -566,14 +604,19 @@ class LinearFn(Function):
         ctx.dims, ctx.slope, ctx.wdtype, ctx.has_bias = (m, n, k), slope, wdtype, bias is not None
         ctx.wbuf = getattr(weight, "_vg_grad_buf", None)
         ctx.bbuf = getattr(bias, "_vg_grad_buf", None) if bias is not None else None
-        ctx.save_for_backward(x, w, y if slope != 1.0 else None)
+        ctx.save_for_backward(x, w, y if slope != 1.0 else None, weight)
         return y
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dy):
-        x, w, y = ctx.saved_tensors
+        x, w, y, weight = ctx.saved_tensors
         m, n, k = ctx.dims
+        if torch.is_grad_enabled():          # create_graph=True (gradient penalty)
+            from . import gp
+            if not ctx.needs_input_grad[0]:          # input gradient only, see ConvFn.backward
+                return (None,) * 5
+            dpre = dy * gp.lrelu_mask(y, ctx.slope) if ctx.slope != 1.0 else dy
+            return gp.LinearDgradFn.apply(dpre, weight, ctx.wdtype), None, None, None, None
         s = stream_ptr()
         dy = dy.contiguous().float()
         if ctx.slope != 1.0:
@@ -607,9 +650,11 @@ class LeakyReluFn(Function):
         return y
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, dy):
         (y,) = ctx.saved_tensors
+        if torch.is_grad_enabled():          # create_graph=True (gradient penalty)
+            from . import gp
+            return dy * gp.lrelu_mask(y, ctx.slope).to(dy.dtype), None
         if dy.stride() != y.stride():
             dy = dy.contiguous() if y.is_contiguous() else as_act(dy, torch.float32)
         dx = torch.empty_like(y)

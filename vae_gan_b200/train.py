@@ -4,7 +4,8 @@ Order follows the reference exactly (it is result-affecting): G forward -> D(rea
 -> D backward -> D optimizer step [-> clamp in WGAN mode] -> D(fake) with the UPDATED D -> G
 backward (D dgrad only) -> G optimizer step.  Differences, all result-neutral or named by
 BASELINE.json north_star: BCE-with-logits adversarial loss and Adam are the default (the
-reference's critic loss / RMSprop+clamp are `loss_mode="wgan"`, `optimizer="rmsprop"`); the unused
+reference's critic loss / RMSprop+clamp are `loss_mode="wgan"`, `optimizer="rmsprop"`; the notebook exactly as
+written - critic loss + 10 x gradient penalty + clamp - is `loss_mode="wgan_gp"`, see gp.py); the unused
 D weight gradients of the G step are not computed; losses stay on the device (no per-step sync).
 
 Parameters, gradients and optimizer state of each network live in ONE flat fp32 buffer: weight
@@ -62,12 +63,14 @@ class VaeGanTrainer:
     def __init__(self, generator: nn.Module, discriminator: nn.Module, *, loss_mode: str = "bce",
                  optimizer: str = "adam", lr: float = 3e-4, weights=(1.0, 10.0, 0.1), clip_value: float = 0.01,
                  weight_decay: Optional[float] = None, betas=(0.9, 0.999), process_group=None,
-                 local_batch: Optional[int] = None, peer_syncbn: Optional[bool] = None):
-        assert loss_mode in ("bce", "wgan"), "wgan_gp (double backward) is not built yet - see DESIGN.md"
+                 local_batch: Optional[int] = None, peer_syncbn: Optional[bool] = None, lambda_gp: float = 10.0):
+        assert loss_mode in ("bce", "wgan", "wgan_gp")
         assert optimizer in ("adam", "rmsprop")
         self.G, self.D = generator, discriminator
         self.loss_mode, self.opt_kind, self.lr, self.weights = loss_mode, optimizer, lr, tuple(weights)
-        self.clip = clip_value if loss_mode == "wgan" else 0.0
+        self.clip = clip_value if loss_mode in ("wgan", "wgan_gp") else 0.0
+        self.lambda_gp = lambda_gp
+        self.gp_alpha_override = None        # tests inject the interpolation weights (B,1,1,1) here
         self.weight_decay = weight_decay if weight_decay is not None else (1e-5 if optimizer == "rmsprop" else 0.0)
         self.betas = betas
         self.pg = process_group
@@ -128,7 +131,7 @@ class VaeGanTrainer:
         if self.G.training and self._nbt_g:
             torch._foreach_add_(self._nbt_g, 1)
         if self.D.training and self._nbt_d:
-            torch._foreach_add_(self._nbt_d, 3)
+            torch._foreach_add_(self._nbt_d, 4 if self.loss_mode == "wgan_gp" else 3)
         VF.config.defer_num_batches_tracked = True
         VF.config.peer = self.peer
         if self.peer is not None:
@@ -150,6 +153,17 @@ class VaeGanTrainer:
                 d_real = self.D(real)
                 d_fake = self.D(gen.detach())
                 d_total, d_rl, d_fl = VF.DiscriminatorLossFn.apply(d_real, d_fake, adv_mode)
+                gp_term = None
+                if self.loss_mode == "wgan_gp":
+                    # README.md:796-798: + lambda_gp * gradient_penalty(D, real.data, gen.data)
+                    from .gp import gradient_penalty
+                    b = real.shape[0]
+                    alpha = self.gp_alpha_override
+                    if alpha is None:
+                        alpha = VF.philox_uniform(b, self.device, tag="gp_alpha").view(b, 1, 1, 1)
+                    gp_term = gradient_penalty(self.D, real.detach(), gen.detach().float(), alpha)
+                    # a mean over the LOCAL samples: 1/world of it is this rank's share of the global mean
+                    d_total = d_total + (self.lambda_gp / self.world) * gp_term
                 d_total.backward()
                 self._allreduce(self.fd)
                 self._opt(self.fd, self.clip)
@@ -165,6 +179,8 @@ class VaeGanTrainer:
                 self.fd.set_requires_grad(True)
         self.losses = dict(d_loss=d_total.detach(), real_loss=d_rl.detach(), fake_loss=d_fl.detach(),
                            g_loss=g_total.detach(), recon=recon.detach(), kl=kl.detach(), adv=adv.detach())
+        if gp_term is not None:
+            self.losses["gp"] = (gp_term / self.world).detach()
         self.last = dict(gen=gen.detach(), mu=mu.detach(), log_var=log_var.detach(), d_real=d_real.detach(),
                          d_fake=d_fake.detach(), d_gen=d_gen.detach())
         return self.losses
