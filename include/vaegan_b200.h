@@ -147,6 +147,19 @@ int vg_lrelu_backward(const void* dy, const void* y_ref, long long n, int dtype,
 /* out = a + b (elementwise, same dtype) -- gradient accumulation at residual forks */
 int vg_add(const void* a, const void* b, long long n, int dtype, void* out, vg_stream_t stream);
 
+/* Second-order backward of BatchNorm(+LeakyReLU) for the gradient penalty (README.md:717-739,
+   torch's batch_norm double backward): G = dL/d(dx) of vg_bn_act_backward_apply's dx.  reduce fills
+   sums5 = double[5*C] (zeroed by the caller; all-reduced by the caller under SyncBN); apply writes
+   g_dy = dL/d(dy) and g_x = dL/dx.  `colscale` = the out_colscale given to the first backward.
+   dL/dgamma[c] = rstd[c] * (sums5[4][c] - sums5[0][c]*sums5[2][c]/M - sums5[1][c]*sums5[3][c]/M). */
+int vg_bn_act_double_backward_reduce(const void* dy, const void* x, const void* G, const float* mean_rstd,
+                                     const float* gamma, const float* beta, const VgBnDesc* d,
+                                     const float* colscale, double* sums5, vg_stream_t stream);
+int vg_bn_act_double_backward_apply(const void* dy, const void* x, const void* G, const float* mean_rstd,
+                                    const float* gamma, const float* beta, const double* sums5, double count,
+                                    const VgBnDesc* d, const float* colscale, void* g_dy, void* g_x,
+                                    vg_stream_t stream);
+
 /* ---- Philox4x32-10 randomness (replaces torch's bernoulli_/randn_like: README.md:144,381,581) */
 /* keep-mask bytes for the elementwise dropout that vg_bn_act_forward applies */
 int vg_dropout_mask(const VgBnDesc* d, uint8_t* mask, vg_stream_t stream);

@@ -69,6 +69,9 @@ _PROTOS = {
     "vg_dropout_mask": (c_int, [C.POINTER(VgBnDesc), c_vp, c_vp]),
     "vg_dropout2d_scale": (c_int, [c_vp, c_int, c_int, c_f, c_ull, c_ull, c_vp, c_ll, c_vp]),
     "vg_philox_normal": (c_int, [c_vp, c_ll, c_ull, c_ull, c_vp, c_ll, c_vp]),
+    "vg_bn_act_double_backward_reduce": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(VgBnDesc), c_vp, c_vp, c_vp]),
+    "vg_bn_act_double_backward_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, C.POINTER(VgBnDesc), c_vp,
+                                                c_vp, c_vp, c_vp]),
     "vg_philox_uniform": (c_int, [c_vp, c_ll, c_ull, c_ull, c_vp, c_ll, c_vp]),
     "vg_counter_add": (c_int, [c_vp, c_ull, c_vp]),
     "vg_avgpool_flatten_forward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),

@@ -400,6 +400,98 @@ __global__ void __launch_bounds__(kBnThreads, APPLY ? 1 : 3) bn_act_bwd_vec_kern
   if (!APPLY) block_reduce_to_global<2>(acc, m, k.c, k.fold, sums_out, smem);
 }
 
+// ------------------------------------------------------------------------------------------
+// second-order backward (gradient penalty, README.md:717-739): derivative of the BatchNorm(+LeakyReLU)
+// input gradient  dx = gamma*rstd*(dyb - mean(dyb) - xh*mean(dyb*xh)) * cs,  dyb = dy*m,  with respect to
+// dy, x (given G = dL/d(dx)); `cs` is the Dropout2d column scale of the producing convolution (nullable).
+//   REDUCE: sums[5][C] = sum dyb, sum dyb*xh, sum G', sum G'*xh, sum G'*dyb     (G' = G*cs)
+//   APPLY : g_dy = gamma*rstd*(G' - mean(G') - xh*mean(G'*xh))*m
+//           g_x  = cs*( rstd*(Q - mean(Q) - xh*mean(Q*xh)) - rstd^2*gamma*S1/M * xh ),
+//                  Q = -gamma*rstd*(b*G' + c*dyb),  S1 = sum G'*dyb - a*sum G' - b*sum G'*xh
+// (closed form derived and checked against autograd in vae_gan_b200/gp.py:bn_double_backward)
+// ------------------------------------------------------------------------------------------
+template <typename T, bool APPLY>
+__global__ void __launch_bounds__(kBnThreads) bn_dbl_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                    const T* __restrict__ G, const float* __restrict__ mean_rstd,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    BnK k, const float* __restrict__ colscale,
+                                                                    double* __restrict__ sums_out, const double* __restrict__ sums_in,
+                                                                    double count, T* __restrict__ g_dy, T* __restrict__ g_x) {
+  extern __shared__ float smem[];
+  const int cv = k.c;
+  const RowMap m = make_rowmap(cv);
+  const int tid = threadIdx.x;
+  const int g = tid % m.cg, r0 = tid / m.cg;
+  float acc[5][8];
+#pragma unroll
+  for (int v = 0; v < 5; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
+  if (tid < m.tpb) {
+    float ga[8], be[8], mean[8], rstd[8];
+    float c_a[8], c_b[8], c_c[8], c_mg[8], c_k[8];   // APPLY: mean(dyb), mean(dyb*xh), mean(G'xh), mean(G'), rstd*gamma*S1/M
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;
+      mean[j] = mean_rstd[ch];
+      rstd[j] = mean_rstd[k.c + ch];
+      ga[j] = gamma[ch];
+      be[j] = beta[ch];
+      if (APPLY) {
+        const double s_dyb = sums_in[ch], s_dybx = sums_in[k.c + ch], s_g = sums_in[2 * k.c + ch], s_gx = sums_in[3 * k.c + ch],
+                     s_gdyb = sums_in[4 * k.c + ch];
+        const double a = s_dyb / count, b = s_dybx / count;
+        c_a[j] = (float)a; c_b[j] = (float)b; c_c[j] = (float)(s_gx / count); c_mg[j] = (float)(s_g / count);
+        c_k[j] = (float)((double)rstd[j] * ga[j] * (s_gdyb - a * s_g - b * s_gx) / count);
+      }
+    }
+    const long long stride = (long long)gridDim.x * m.rpb;
+    for (long long row = (long long)blockIdx.x * m.rpb + r0; row < k.rows; row += stride) {
+      Vec8<T> vd, vx, vg;
+      const long long off = row * cv + g * 8;
+      vd.load(dy + off);
+      vx.load(x + off);
+      vg.load(G + off);
+      float cs[8];
+      if (colscale != nullptr) {
+        const float* p = colscale + (row / k.hw) * k.c + g * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] = p[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] = 1.f;
+      }
+      Vec8<T> o_dy, o_x;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (vx.v[j] - mean[j]) * rstd[j];
+        const float mk = fmaf(ga[j], xh, be[j]) > 0.f ? 1.f : k.slope;
+        const float dyb = vd.v[j] * mk;
+        const float gg = vg.v[j] * cs[j];
+        if (!APPLY) {
+          acc[0][j] += dyb;
+          acc[1][j] += dyb * xh;
+          acc[2][j] += gg;
+          acc[3][j] += gg * xh;
+          acc[4][j] += gg * dyb;
+        } else {
+          const float gr = ga[j] * rstd[j];
+          o_dy.v[j] = gr * (gg - c_mg[j] - xh * c_c[j]) * mk;
+          const float q = -gr * (c_b[j] * gg + c_c[j] * dyb);
+          const float mq = -gr * (c_b[j] * c_mg[j] + c_c[j] * c_a[j]);
+          const float mqx = -2.f * gr * c_b[j] * c_c[j];
+          o_x.v[j] = (rstd[j] * (q - mq - xh * mqx) - rstd[j] * c_k[j] * xh) * cs[j];
+        }
+      }
+      if (APPLY) {
+        o_dy.store(g_dy + off);
+        o_x.store(g_x + off);
+      }
+    }
+  }
+  if (!APPLY) block_reduce_to_global<5>(acc, m, k.c, false, sums_out, smem);
+}
+
 template <typename T, bool APPLY>
 __global__ void bn_act_bwd_scalar_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean_rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, BnK k,
@@ -784,6 +876,53 @@ extern "C" int vg_bn_act_backward_apply(const void* dy, const void* x, const flo
                                                   as_stream(stream));
   return bn_act_backward_t<float, true>((const float*)dy, (const float*)x, mean_rstd, gamma, beta, d, nullptr, sums, count,
                                         out_colscale, (const float*)addend, (float*)dx, as_stream(stream));
+}
+
+template <typename T, bool APPLY>
+static int bn_dbl_bwd_t(const T* dy, const T* x, const T* G, const float* mean_rstd, const float* gamma, const float* beta,
+                        const VgBnDesc* d, const float* colscale, double* sums_out, const double* sums_in, double count, T* g_dy,
+                        T* g_x, cudaStream_t s) {
+  BnK k = make_bnk(d);
+  RowMap m = make_rowmap(d->c);
+  int grid = grid_for(d->rows, m.rpb, kUnroll, APPLY ? apply_blocks_per_sm() : kReduceBlocksPerSm);
+  const size_t smem = APPLY ? 0 : (size_t)5 * 8 * kBnThreads * sizeof(float);
+  bn_dbl_bwd_vec_kernel<T, APPLY><<<grid, kBnThreads, smem, s>>>(dy, x, G, mean_rstd, gamma, beta, k, colscale, sums_out, sums_in, count,
+                                                                 g_dy, g_x);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_bn_act_double_backward_reduce(const void* dy, const void* x, const void* G, const float* mean_rstd,
+                                                const float* gamma, const float* beta, const VgBnDesc* d, const float* colscale,
+                                                double* sums5, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(dy && x && G && mean_rstd && gamma && beta && sums5, "null pointer");
+  VG_CHECK_ARG(vec_ok(d->c) && d->training && d->drop_p == 0.f, "needs training-mode BatchNorm, channels % 8 == 0 and <= 2048, no dropout");
+  if (d->rows == 0) return VG_OK;
+  if (d->dtype == VG_BF16) {
+    static bool attr = false;
+    if (!attr) { VG_CUDA(cudaFuncSetAttribute(bn_dbl_bwd_vec_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024)); attr = true; }
+    return bn_dbl_bwd_t<__nv_bfloat16, false>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)G, mean_rstd, gamma, beta,
+                                              d, colscale, sums5, nullptr, 1.0, nullptr, nullptr, as_stream(stream));
+  }
+  return bn_dbl_bwd_t<float, false>((const float*)dy, (const float*)x, (const float*)G, mean_rstd, gamma, beta, d, colscale, sums5, nullptr,
+                                    1.0, nullptr, nullptr, as_stream(stream));
+}
+
+extern "C" int vg_bn_act_double_backward_apply(const void* dy, const void* x, const void* G, const float* mean_rstd,
+                                               const float* gamma, const float* beta, const double* sums5, double count,
+                                               const VgBnDesc* d, const float* colscale, void* g_dy, void* g_x, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(dy && x && G && mean_rstd && gamma && beta && sums5 && g_dy && g_x && count > 0, "bad args");
+  VG_CHECK_ARG(vec_ok(d->c) && d->training && d->drop_p == 0.f, "needs training-mode BatchNorm, channels % 8 == 0 and <= 2048, no dropout");
+  if (d->rows == 0) return VG_OK;
+  if (d->dtype == VG_BF16)
+    return bn_dbl_bwd_t<__nv_bfloat16, true>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)G, mean_rstd, gamma, beta,
+                                             d, colscale, nullptr, sums5, count, (__nv_bfloat16*)g_dy, (__nv_bfloat16*)g_x, as_stream(stream));
+  return bn_dbl_bwd_t<float, true>((const float*)dy, (const float*)x, (const float*)G, mean_rstd, gamma, beta, d, colscale, nullptr, sums5,
+                                   count, (float*)g_dy, (float*)g_x, as_stream(stream));
 }
 
 template <typename T>

@@ -104,20 +104,35 @@ class BnBwdFn(Function):
         d = ctx.d
         c = d.c
         world = VF._world() if d.training else 1
-        scale = ocs.view(x.shape[0], c, 1, 1) if ocs is not None else None
-        if scale is not None:
-            G = G.float() * scale
+        count = float(d.rows * world)
 
         def allreduce(t):                      # SyncBN: the five per-channel sums are global
             flat = t.view(-1)
             for i in range(0, flat.numel(), 2048):      # the NVLink exchange moves <= 2048 doubles per call
                 VF._allreduce_sums(flat[i:i + 2048])
 
-        g_dy, g_x, g_gamma = bn_double_backward(G, dy, x, gamma, beta, mr[:c], mr[c:], float(d.slope),
-                                                float(d.rows * world), bool(d.training),
-                                                allreduce if world > 1 else None)
-        if scale is not None and g_x is not None:
-            g_x = (g_x.float() * scale).to(x.dtype)
+        if d.training and c % 8 == 0 and c // 8 <= 256 and d.drop_p == 0.0:
+            # fused kernels: one reduction pass (five per-channel sums) + one apply pass (both outputs)
+            s = stream_ptr()
+            G = VF.as_act(G, x.dtype)
+            g, b = gamma.detach(), beta.detach()
+            sums = VF.zeros_f64(5 * c, x.device)
+            call("vg_bn_act_double_backward_reduce", ptr(dy), ptr(x), ptr(G), ptr(mr), ptr(g), ptr(b), C.byref(d), ptr(ocs), ptr(sums), s)
+            if world > 1:
+                allreduce(sums)
+            g_dy, g_x = torch.empty_like(x), torch.empty_like(x)
+            call("vg_bn_act_double_backward_apply", ptr(dy), ptr(x), ptr(G), ptr(mr), ptr(g), ptr(b), ptr(sums), count, C.byref(d),
+                 ptr(ocs), ptr(g_dy), ptr(g_x), s)
+            sv = sums.view(5, c)
+            g_gamma = (mr[c:].double() * (sv[4] - sv[0] * sv[2] / count - sv[1] * sv[3] / count)).float()
+        else:
+            scale = ocs.view(x.shape[0], c, 1, 1) if ocs is not None else None
+            if scale is not None:
+                G = G.float() * scale
+            g_dy, g_x, g_gamma = bn_double_backward(G, dy, x, gamma, beta, mr[:c], mr[c:], float(d.slope), count,
+                                                    bool(d.training), allreduce if world > 1 else None)
+            if scale is not None and g_x is not None:
+                g_x = (g_x.float() * scale).to(x.dtype)
         if world > 1:
             g_gamma = g_gamma / world          # summed again with the flat gradient all-reduce
         return g_dy.to(ctx.dy_dtype), g_x, g_gamma, None, None, None, None
