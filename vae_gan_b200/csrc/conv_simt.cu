@@ -38,47 +38,77 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
   }
 }
 
-// Tiled variant for the layer sizes the tensor-core path uses: a block stages a 16 x 32 x taps tile of the
+// Tiled variant for the layer sizes the tensor-core path uses: a block stages a 16 x 32 x TAPS tile of the
 // torch weight [r0][r1][tap] in shared memory (coalesced reads) and writes BOTH packed layouts in runs
 // of 16 / 32 consecutive elements, i.e. whole 32-byte sectors; the element-wise kernel above scatters 2-byte
-// writes with a stride of c_out*c_in elements and ran at ~2 % of the HBM rate.
+// writes with a stride of c_out*c_in elements.  TAPS is a template parameter and the loops are nested so that
+// no thread divides by a run-time value (those divisions made a 16-block launch take 15 us).
 constexpr int kPackR0 = 16, kPackR1 = 32;
-template <typename T>
+template <typename T, int TAPS>
 __global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int n0, int n1,
-                                                                 int taps, int transposed, T* __restrict__ pack_kn,
-                                                                 T* __restrict__ pack_nk) {
-  extern __shared__ float pack_tile[];            // [kPackR0][kPackR1 * tp + 1], tp = taps | 1 (odd strides: no bank conflicts)
-  const int tp = taps | 1;
-  const int row = kPackR1 * tp + 1;
+                                                                 int transposed, T* __restrict__ pack_kn, T* __restrict__ pack_nk) {
+  constexpr int TP = TAPS | 1;                      // odd strides: no bank conflicts
+  constexpr int ROW = kPackR1 * TP + 1;
+  __shared__ float tile[kPackR0 * ROW];
   const float inv = sigma ? 1.0f / *sigma : 1.0f;
   const int r0b = blockIdx.y * kPackR0, r1b = blockIdx.x * kPackR1;
   const int n1t = min(kPackR1, n1 - r1b), n0t = min(kPackR0, n0 - r0b);
-  // load: for each r0 the (r1, tap) block is contiguous in the torch layout
-  const int run = n1t * taps;
-  for (int i = threadIdx.x; i < n0t * run; i += blockDim.x) {
-    const int a = i / run, b = i - a * run;
-    const int r1l = b / taps, tap = b - r1l * taps;
-    pack_tile[a * row + r1l * tp + tap] = w[((long long)(r0b + a) * n1 + r1b) * taps + b] * inv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // load: for each r0 the (r1, tap) block is contiguous in the torch layout; warp w takes rows w, w+8
+  const int run = n1t * TAPS;
+  for (int a = warp; a < n0t; a += 8) {
+    const float* src = w + ((long long)(r0b + a) * n1 + r1b) * TAPS;
+    for (int b = lane; b < run; b += 32) {
+      const int r1l = b / TAPS, tap = b - r1l * TAPS;
+      tile[a * ROW + r1l * TP + tap] = src[b] * inv;
+    }
   }
   __syncthreads();
   // torch layout: Conv2d [co][ci][tap] (r0 = co, r1 = ci), ConvTranspose2d [ci][co][tap] (r0 = ci, r1 = co)
-  const int c_out = transposed ? n1 : n0, c_in = transposed ? n0 : n1;
   T* along_r1 = transposed ? pack_nk : pack_kn;   // rows indexed by (tap, r0), consecutive r1
   T* along_r0 = transposed ? pack_kn : pack_nk;   // rows indexed by (tap, r1), consecutive r0
-  const int len_r1 = transposed ? c_out : c_in, len_r0 = transposed ? c_in : c_out;
-  if (along_r1 != nullptr) {
-    for (int i = threadIdx.x; i < taps * n0t * kPackR1; i += blockDim.x) {
-      const int b = i % kPackR1, t2 = i / kPackR1;
-      const int a = t2 % n0t, tap = t2 / n0t;
-      if (b < n1t) along_r1[((long long)tap * n0 + r0b + a) * len_r1 + r1b + b] = from_f32<T>(pack_tile[a * row + b * tp + tap]);
+  if (along_r1 != nullptr && lane < n1t) {
+    for (int row = warp; row < TAPS * n0t; row += 8) {          // row = tap * n0t + a, lane = r1
+      const int tap = row / n0t, a = row - tap * n0t;
+      along_r1[((long long)tap * n0 + r0b + a) * n1 + r1b + lane] = from_f32<T>(tile[a * ROW + lane * TP + tap]);
     }
   }
   if (along_r0 != nullptr) {
-    for (int i = threadIdx.x; i < taps * kPackR1 * kPackR0; i += blockDim.x) {
-      const int a = i % kPackR0, t2 = i / kPackR0;
-      const int b = t2 % kPackR1, tap = t2 / kPackR1;
-      if (a < n0t && b < n1t) along_r0[((long long)tap * n1 + r1b + b) * len_r0 + r0b + a] = from_f32<T>(pack_tile[a * row + b * tp + tap]);
+    const int a = lane & 15, half = lane >> 4;                  // 16 consecutive r0 per row, two rows per warp pass
+    if (a < n0t) {
+      for (int row = warp * 2 + half; row < TAPS * n1t; row += 16) {   // row = tap * n1t + b
+        const int tap = row / n1t, b = row - tap * n1t;
+        along_r0[((long long)tap * n1 + r1b + b) * n0 + r0b + a] = from_f32<T>(tile[a * ROW + b * TP + tap]);
+      }
     }
+  }
+}
+
+// taps == 1 (1x1 convolutions and the discriminator's Linear layers, up to 18.9 M elements): pack_kn is a cast
+// copy, pack_nk a transpose; 32 x 32 tiles, 128-byte coalesced reads, 64-byte coalesced writes.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_1x1_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int n0, int n1,
+                                                               T* __restrict__ same, T* __restrict__ transp) {
+  __shared__ float tile[32][33];
+  const float inv = sigma ? 1.0f / *sigma : 1.0f;
+  const int r0b = blockIdx.y * 32, r1b = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a = ty + 8 * i;
+    float v = 0.f;
+    if (r0b + a < n0 && r1b + tx < n1) {
+      v = w[(long long)(r0b + a) * n1 + r1b + tx] * inv;
+      if (same != nullptr) same[(long long)(r0b + a) * n1 + r1b + tx] = from_f32<T>(v);
+    }
+    tile[a][tx] = v;
+  }
+  __syncthreads();
+  if (transp == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int b = ty + 8 * i;
+    if (r1b + b < n1 && r0b + tx < n0) transp[(long long)(r1b + b) * n0 + r0b + tx] = from_f32<T>(tile[tx][b]);
   }
 }
 
@@ -772,18 +802,24 @@ int simt_pack_weights(const VgConvDesc* d, const float* w, const float* sigma, v
   const long long total = (long long)taps * d->c_in * d->c_out;
   if (total == 0) return VG_OK;
   const int n0 = d->transposed ? d->c_in : d->c_out, n1 = d->transposed ? d->c_out : d->c_in;
-  if (total >= 4096 && taps <= 25) {
-    dim3 tg((unsigned)cdiv(n1, kPackR1), (unsigned)cdiv(n0, kPackR0));
-    const size_t smem = (size_t)kPackR0 * (kPackR1 * (taps | 1) + 1) * sizeof(float);   // <= 51 KB at 5x5 taps
-    if (d->act_dtype == VG_BF16) {
-      static bool attr = false;
-      if (!attr) { VG_CUDA(cudaFuncSetAttribute(pack_weights_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-      pack_weights_tiled_kernel<__nv_bfloat16><<<tg, 256, smem, s>>>(w, sigma, n0, n1, taps, d->transposed, (__nv_bfloat16*)pack_kn,
-                                                                     (__nv_bfloat16*)pack_nk);
+  if (total >= 4096 && (taps == 1 || taps == 9 || taps == 16)) {
+    const bool bf = d->act_dtype == VG_BF16;
+    if (taps == 1) {
+      // [r0][r1] -> same layout (rows r0) + transpose (rows r1); which of pack_kn / pack_nk is which depends on `transposed`
+      void* same = d->transposed ? pack_nk : pack_kn;
+      void* transp = d->transposed ? pack_kn : pack_nk;
+      dim3 tg((unsigned)cdiv(n1, 32), (unsigned)cdiv(n0, 32));
+      if (bf) pack_weights_1x1_kernel<__nv_bfloat16><<<tg, 256, 0, s>>>(w, sigma, n0, n1, (__nv_bfloat16*)same, (__nv_bfloat16*)transp);
+      else pack_weights_1x1_kernel<float><<<tg, 256, 0, s>>>(w, sigma, n0, n1, (float*)same, (float*)transp);
     } else {
-      static bool attr = false;
-      if (!attr) { VG_CUDA(cudaFuncSetAttribute(pack_weights_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-      pack_weights_tiled_kernel<float><<<tg, 256, smem, s>>>(w, sigma, n0, n1, taps, d->transposed, (float*)pack_kn, (float*)pack_nk);
+      dim3 tg((unsigned)cdiv(n1, kPackR1), (unsigned)cdiv(n0, kPackR0));
+      if (taps == 9) {
+        if (bf) pack_weights_tiled_kernel<__nv_bfloat16, 9><<<tg, 256, 0, s>>>(w, sigma, n0, n1, d->transposed, (__nv_bfloat16*)pack_kn, (__nv_bfloat16*)pack_nk);
+        else pack_weights_tiled_kernel<float, 9><<<tg, 256, 0, s>>>(w, sigma, n0, n1, d->transposed, (float*)pack_kn, (float*)pack_nk);
+      } else {
+        if (bf) pack_weights_tiled_kernel<__nv_bfloat16, 16><<<tg, 256, 0, s>>>(w, sigma, n0, n1, d->transposed, (__nv_bfloat16*)pack_kn, (__nv_bfloat16*)pack_nk);
+        else pack_weights_tiled_kernel<float, 16><<<tg, 256, 0, s>>>(w, sigma, n0, n1, d->transposed, (float*)pack_kn, (float*)pack_nk);
+      }
     }
     VG_LAUNCHED();
     return VG_OK;
