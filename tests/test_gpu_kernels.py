@@ -63,6 +63,51 @@ def test_philox_masks_bit_exact():
         assert torch.equal(out.cpu(), want)
 
 
+def test_philox_uniform_bit_exact_and_partition_invariant():
+    """vg_philox_uniform (gradient-penalty interpolation weights) against the oracle's integer restatement."""
+    from vae_gan_b200 import _lib
+    seed = 0xABCDEF12345
+    for n, off, start in [(7, 3, 0), (64, 65536 * 2 + 5, 0), (33, 9, 16)]:
+        out = torch.empty(n, dtype=torch.float32, device=dev())
+        _lib.call("vg_philox_uniform", out.data_ptr(), n, seed, off, None, start, _lib.stream_ptr())
+        want = torch.from_numpy(O.philox_uniform(n, seed, off, start))
+        assert torch.equal(out.cpu(), want)
+        assert float(out.min()) >= 0.0 and float(out.max()) < 1.0
+    a = torch.empty(32, dtype=torch.float32, device=dev())
+    b = torch.empty(16, dtype=torch.float32, device=dev())
+    _lib.call("vg_philox_uniform", a.data_ptr(), 32, seed, 4, None, 0, _lib.stream_ptr())
+    _lib.call("vg_philox_uniform", b.data_ptr(), 16, seed, 4, None, 16, _lib.stream_ptr())
+    assert torch.equal(a[16:], b)          # rank 1 of 2 draws the same numbers for its samples
+
+
+@pytest.mark.parametrize("c_in,c_out,k,transposed", [(64, 128, 3, False), (128, 64, 4, True), (18432, 1024, 1, False), (100, 72, 3, False),
+                                                     (72, 100, 4, True), (40, 200, 1, False), (24, 40, 5, False), (8, 8, 3, False),
+                                                     (512, 512, 3, False)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_weight_pack_layouts_bit_exact(c_in, c_out, k, transposed, dtype):
+    """vg_conv_pack_weights: both packed layouts ([tap][c_out][c_in] and [tap][c_in][c_out]) are pure permutations
+    (+ division by sigma, + cast) of the torch weight - bit-exact against torch, for every kernel variant the
+    launcher picks (1x1 transpose, tiled 3x3 / 4x4, element-wise fallback) incl. ragged channel counts."""
+    vf = VF()
+    from vae_gan_b200 import _lib
+    g = torch.Generator().manual_seed(c_in * 7 + c_out + k)
+    shape = (c_in, c_out, k, k) if transposed else (c_out, c_in, k, k)
+    w = torch.randn(shape, generator=g).to(dev())
+    sigma = torch.tensor([1.7], device=dev())
+    d, _, _ = vf._conv_desc((1, c_in, 8, 8), c_out, vf.ConvGeom(k, 1, 0 if k == 1 else 1, transposed), dtype, dtype)
+    for sg in (None, sigma):
+        kn = torch.empty(w.numel(), dtype=dtype, device=dev())
+        nk = torch.empty(w.numel(), dtype=dtype, device=dev())
+        _lib.call("vg_conv_pack_weights", C.byref(d), w.data_ptr(), sg.data_ptr() if sg is not None else None, kn.data_ptr(), nk.data_ptr(),
+                  _lib.stream_ptr())
+        ws = (w * (1.0 / sigma)) if sg is not None else w      # the kernels multiply by 1/sigma
+        w4 = ws.permute(1, 0, 2, 3) if transposed else ws      # -> [c_out][c_in][kh][kw]
+        want_kn = w4.permute(2, 3, 0, 1).reshape(-1).to(dtype)  # [tap][c_out][c_in]
+        want_nk = w4.permute(2, 3, 1, 0).reshape(-1).to(dtype)  # [tap][c_in][c_out]
+        assert torch.equal(kn, want_kn), "pack_kn"
+        assert torch.equal(nk, want_nk), "pack_nk"
+
+
 def test_philox_normal_statistics_and_partition_invariance():
     vf = VF()
     from vae_gan_b200 import _lib

@@ -82,3 +82,28 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import pytest
     with pytest.raises(_lib.VgError):
         _lib.load()
+
+
+def test_bn_double_backward_closed_form_matches_autograd():
+    """vae_gan_b200.gp.bn_double_backward (the math behind vg_bn_act_double_backward_*) against torch's own double
+    backward of batch_norm + leaky_relu in fp64 (README.md:717-739 needs it for the gradient penalty)."""
+    import torch
+    import torch.nn.functional as F
+    from vae_gan_b200 import gp
+    torch.manual_seed(0)
+    N, Cc, H, W = 3, 5, 4, 4
+    for slope in (0.2, 1.0):
+        x = torch.randn(N, Cc, H, W, dtype=torch.float64, requires_grad=True)
+        gamma = torch.randn(Cc, dtype=torch.float64, requires_grad=True)
+        beta = torch.randn(Cc, dtype=torch.float64, requires_grad=True)
+        dy = torch.randn(N, Cc, H, W, dtype=torch.float64, requires_grad=True)
+        G = torch.randn(N, Cc, H, W, dtype=torch.float64)
+        y = F.leaky_relu(F.batch_norm(x, None, None, gamma, beta, True, 0.1, 1e-5), slope)
+        (dx,) = torch.autograd.grad(y, x, dy, create_graph=True)
+        g_dy, g_x, g_gamma = torch.autograd.grad((dx * G).sum(), [dy, x, gamma])
+        mean, var = x.mean((0, 2, 3)), x.var((0, 2, 3), unbiased=False)
+        o_dy, o_x, o_g = gp.bn_double_backward(G, dy.detach(), x.detach(), gamma.detach(), beta.detach(), mean.detach(),
+                                               (var + 1e-5).rsqrt().detach(), slope, N * H * W, True)
+        assert (o_dy - g_dy).abs().max() < 1e-12
+        assert (o_x - g_x).abs().max() < 1e-12
+        assert (o_g.double() - g_gamma).abs().max() < 1e-5      # returned in fp32
