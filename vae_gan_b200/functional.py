@@ -402,6 +402,59 @@ class BnActFn(Function):
         return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
+class BnActForkFn(Function):
+    """(y, x_pass) = (dropout(leaky_relu(batch_norm(x))), x): the fork at the top of a pre-activation residual
+    block, where x feeds both the main path and the shortcut (README.md:188-195, 410-417).  Autograd hands the
+    backward BOTH gradients at once, and the shortcut's gradient is added inside the BatchNorm backward-apply
+    kernel (`addend`) instead of by a separate full-tensor accumulation kernel."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, sums, slope, drop_p, offset, training):
+        _lib.ensure_device(x.device)
+        assert is_act(x)
+        g, b = gamma.detach(), beta.detach()
+        mr = bn_batch_stats(x, sums, running_mean, running_var, training)
+        d = _bn_desc(x, slope, drop_p if training else 0.0, offset, training)
+        y = torch.empty_like(x)
+        call("vg_bn_act_forward", ptr(x), ptr(mr), ptr(g), ptr(b), C.byref(d), ptr(y), stream_ptr())
+        ctx.d = d
+        ctx.gbuf = getattr(gamma, "_vg_grad_buf", None)
+        ctx.bbuf = getattr(beta, "_vg_grad_buf", None)
+        ctx.save_for_backward(x, mr, g, b, gamma, beta)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dpass):
+        x, mr, g, b, gamma, beta = ctx.saved_tensors
+        if torch.is_grad_enabled():          # create_graph=True (gradient penalty)
+            from . import gp
+            assert ctx.d.drop_p == 0.0, "second-order path: elementwise dropout is not on the discriminator path"
+            if not ctx.needs_input_grad[0]:
+                return (None,) * 10
+            dx = gp.BnBwdFn.apply(dy, x, gamma, beta, mr, ctx.d, None) if dy is not None else None
+            if dpass is not None:
+                dx = dpass.to(x.dtype) if dx is None else dx + dpass.to(dx.dtype)
+            return (dx,) + (None,) * 9
+        if dy is None:                       # only the pass-through branch was used
+            return (as_act(dpass, x.dtype) if dpass is not None else None,) + (None,) * 9
+        dy = as_act(dy, x.dtype)
+        addend = as_act(dpass, x.dtype) if dpass is not None else None
+        dx, dgamma, dbeta = _bn_backward(dy, x, mr, g, b, ctx.d, addend=addend, need_dx=ctx.needs_input_grad[0],
+                                         need_params=ctx.needs_input_grad[1], gbuf=ctx.gbuf, bbuf=ctx.bbuf)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def bn_act_fork(x, bn, *, slope=1.0, drop_p=0.0, training=True, sums=None, tag=""):
+    """bn_act that also returns x for the block's shortcut; see BnActForkFn."""
+    if not (torch.is_grad_enabled() and x.requires_grad):
+        # nothing flows back into x: keep the plain tensor so the shortcut does not compute a useless input gradient
+        return bn_act(x, bn, slope=slope, drop_p=drop_p, training=training, sums=sums, tag=tag), x
+    offset = rng.next_site(tag, tuple(x.shape)) if (training and drop_p > 0) else 0
+    if training and bn.track_running_stats and not config.defer_num_batches_tracked:
+        bn.num_batches_tracked += 1
+    return BnActForkFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, sums, slope, drop_p, offset, training)
+
+
 def bn_act(x, bn, *, slope=1.0, drop_p=0.0, training=True, sums=None, out_colscale=None, tag=""):
     """`bn` is an nn.BatchNorm2d used as a parameter/buffer container."""
     offset = rng.next_site(tag, tuple(x.shape)) if (training and drop_p > 0) else 0

@@ -130,7 +130,7 @@ class ResBlockVAE(nn.Module):
             c_out = self.bn2.num_features
             tag = f"ResBlockVAE:{self.mode}"
             if self.res_mode == "pre-activation":
-                a = VF.bn_act(x, self.bn1, slope=slope, drop_p=p, training=tr, sums=_pop_stats(x, tr), tag=tag)
+                a, x = VF.bn_act_fork(x, self.bn1, slope=slope, drop_p=p, training=tr, sums=_pop_stats(x, tr), tag=tag)
                 s2 = _new_stats(c_out, dev, tr)
                 c1 = _conv_apply(self.conv1, a, g1, stats_out=s2, training=tr)
                 b = VF.bn_act(c1, self.bn2, slope=slope, training=tr, sums=s2)
@@ -239,7 +239,7 @@ class ResBlockDiscriminator(nn.Module):
             has_sc = len(self.shortcut) > 0
             scale = VF.dropout2d_scale(x.shape[0], c_out, p, dev, tag="ResBlockDiscriminator") if (tr and p > 0) else None
             if self.res_mode == "pre-activation":
-                a = VF.bn_act(x, self.bn1, slope=slope, training=tr, sums=_pop_stats(x, tr))
+                a, x = VF.bn_act_fork(x, self.bn1, slope=slope, training=tr, sums=_pop_stats(x, tr))
                 s2 = _new_stats(c_out, dev, tr)
                 c1 = _conv_apply(self.conv1, a, g1, colscale=scale, stats_out=s2, training=tr)
                 b = VF.bn_act(c1, self.bn2, slope=slope, training=tr, sums=s2, out_colscale=scale)
