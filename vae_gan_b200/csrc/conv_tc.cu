@@ -1363,7 +1363,11 @@ int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, 
   choose_box(wu, hu, d->n, 64, &p.TW, &p.TH, &p.TN);
   p.tiles_x = (int)cdiv(wu, p.TW); p.tiles_y = (int)cdiv(hu, p.TH); p.tiles_n = (int)cdiv(d->n, p.TN);
   p.n_boxes = p.tiles_x * p.tiles_y * p.tiles_n;
-  p.packed = workspace != nullptr;
+  // 1x1 convolutions / Linear layers: torch layout [c_u][c_s] already has c_s contiguous, so the epilogue's per-lane
+  // reductions are coalesced (32 lanes = 32 consecutive c_s) and the scratch + memset + unpack round trip is skipped
+  static int direct11 = -1;
+  if (direct11 < 0) { const char* e = getenv("VG_WGRAD_DIRECT_1X1"); direct11 = e ? atoi(e) : 1; }
+  p.packed = workspace != nullptr && (tmp.ntaps > 1 || !direct11);
   p.dw = p.packed ? workspace : dw;
   const size_t welems = (size_t)k * k * cs * cu;
   if (p.packed) VG_CUDA(cudaMemsetAsync(workspace, 0, welems * sizeof(float), s));
