@@ -350,6 +350,90 @@ def test_train_step_fp32_wgan_gp_rmsprop_vs_oracle():
     _run_trainer_vs_oracle(torch.float32, "wgan_gp", "rmsprop", B=2, S=32, fs=8, steps=2, tol_loss=1e-4, max_bad_frac=5e-3)
 
 
+def test_notebook_style_loop_with_stock_autograd_and_optimizers():
+    """Drop-in check of the MODULE surface (no VaeGanTrainer): the notebook's iteration (README.md:775-834) written
+    the way a user of the reference writes it - nn.L1Loss / nn.MSELoss, the KL expression, autograd.grad(create_graph)
+    for the gradient penalty, .backward(), torch.optim.RMSprop, p.data.clamp_ - on our Generator / Discriminator, against
+    oracle.train_step(loss_mode="wgan_gp") in fp64."""
+    v = V()
+    import torch.nn as nn
+    B, S, fs, steps, lr = 2, 32, 8, 2, 3e-4
+    spec_g = O.GeneratorSpec(depth=2, length=1, feature_size=fs)
+    spec_d = O.DiscriminatorSpec(1, fs, (1, 1, 1), (1, 2, 2), (2 * fs, 4 * fs, 8 * fs), input_size=S)
+    Pg, Pd = O.make_generator_params(spec_g, seed=15), O.make_discriminator_params(spec_d, seed=16)
+    gen_ = torch.Generator().manual_seed(77)
+    xs = [torch.rand(B, 1, S, S, generator=gen_) for _ in range(steps)]
+    epss = [torch.randn(B, spec_g.feature_depth, S // 4, S // 4, generator=gen_) for _ in range(steps)]
+    seed = 2468
+    with v.compute_dtype(torch.float32):
+        G, D = v.build_vae_gan(feature_size=fs, image_size=S)
+        load_params_into(G, Pg)
+        load_params_into(D, Pd)
+        G, D = G.to(dev()).train(), D.to(dev()).train()
+        v.rng.seed = seed
+        v.rng.step_tensor(dev()).zero_()
+        opt_g = torch.optim.RMSprop(G.parameters(), lr=lr, weight_decay=1e-5)
+        opt_d = torch.optim.RMSprop(D.parameters(), lr=lr, weight_decay=1e-5)
+        recon_funs = [nn.L1Loss(), nn.MSELoss()]
+        og, od = O.OptState(kind="rmsprop", lr=lr, weight_decay=1e-5), O.OptState(kind="rmsprop", lr=lr, weight_decay=1e-5)
+        Pg_r, Pd_r = O.clone_params(Pg, dtype=F64), O.clone_params(Pd, dtype=F64)
+        for i in range(steps):
+            v.rng.reset_sites()                 # one Philox stream per iteration (what VaeGanTrainer does internally)
+            v.rng.advance(dev())
+            G.code_processor.eps_override = epss[i]
+            real = xs[i].to(dev())
+            # ---- discriminator step ----
+            opt_d.zero_grad()
+            gen_imgs, mu, log_var = G(real)
+            real_loss = -torch.mean(D(real))
+            fake_loss = torch.mean(D(gen_imgs.detach()))
+            alpha = v.functional.philox_uniform(B, dev(), tag="gp_alpha").view(B, 1, 1, 1)
+            inter = (alpha * real.data + (1 - alpha) * gen_imgs.data).requires_grad_(True)
+            d_inter = D(inter)
+            grads = torch.autograd.grad(outputs=d_inter, inputs=inter, grad_outputs=torch.ones_like(d_inter), create_graph=True,
+                                        retain_graph=True, only_inputs=True)[0]
+            gp = ((grads.view(B, -1).norm(2, dim=1) - 1) ** 2).mean()
+            d_loss = real_loss + fake_loss + 10.0 * gp
+            d_loss.backward()
+            opt_d.step()
+            for p in D.parameters():
+                p.data.clamp_(-0.01, 0.01)
+            # ---- generator step ----
+            opt_g.zero_grad()
+            adv = -torch.mean(D(gen_imgs))
+            recon = sum(f(gen_imgs, real) for f in recon_funs)
+            lv, m_ = torch.flatten(log_var, start_dim=1), torch.flatten(mu, start_dim=1)
+            kl = (-0.5 * torch.sum(1 + lv - m_.pow(2) - lv.exp())).mean()
+            g_loss = 1.0 * adv + 10.0 * recon + 0.1 * kl
+            g_loss.backward()
+            opt_g.step()
+            # ---- oracle ----
+            step = i + 1
+            gm, site = generator_masks(spec_g, B, S, seed, 0, step)
+            dm_real, site = discriminator_masks(spec_d, B, seed, site, step)
+            dm_fake, site = discriminator_masks(spec_d, B, seed, site, step)
+            alpha_r = torch.from_numpy(O.philox_uniform(B, seed, site + 65536 * step)).view(B, 1, 1, 1).to(F64)
+            dm_gp, site = discriminator_masks(spec_d, B, seed, site + 1, step)
+            dm_gen, site = discriminator_masks(spec_d, B, seed, site, step)
+            want = O.train_step(Pg_r, Pd_r, og, od, xs[i].to(F64), spec_g, spec_d, eps_noise=epss[i].to(F64), g_masks=gm,
+                                d_masks_real=dm_real, d_masks_fake=dm_fake, d_masks_gen=dm_gen, loss_mode="wgan_gp",
+                                d_masks_gp=dm_gp, gp_alpha=alpha_r)
+            for name, got in (("d_loss", d_loss), ("gp", gp), ("g_loss", g_loss), ("recon", recon), ("kl", kl), ("adv", adv)):
+                w = float(want[name])
+                assert abs(float(got) - w) <= 2e-4 * max(abs(w), 1e-2), (i, name, float(got), w)
+        bad = tot = 0
+        for net, Pr, P0 in ((G, Pg_r, Pg), (D, Pd_r, Pd)):
+            for k, p in net.named_parameters():
+                if float((Pr[k] - P0[k].double()).abs().mean()) < 0.01 * lr:
+                    continue
+                diff = (p.data.double().cpu() - Pr[k]).abs()
+                bad += int((diff > 0.5 * lr).sum())
+                tot += diff.numel()
+        assert bad / tot <= 5e-3, f"{bad}/{tot} parameter elements deviate by more than lr/2"
+        print(f"[notebook-style loop] {steps} WGAN-GP iterations with torch.optim.RMSprop: losses match the fp64 oracle, "
+              f"{bad}/{tot} parameter elements off by > lr/2")
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_gradient_penalty_vs_oracle(dtype):
     """compute_gradient_penalty (README.md:717-739) through OUR discriminator with torch.autograd.grad(create_graph=True)
