@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
     "-DVG_BUILDING=1",
-] + os.environ.get("VG_BUILD_DEFINES", "").split()   # e.g. -DVG_TC_PROFILE (diagnosis build of conv_tc.cu)
+] + os.environ.get("VG_BUILD_DEFINES", "").split()   # extra -D flags for experiments
 
 
 def _nvcc() -> str:
