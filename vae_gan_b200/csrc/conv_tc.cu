@@ -13,8 +13,11 @@
 //     of the fine tensor), so every load is still a dense unit-stride box;
 //   * stride-2 scatters (ConvTranspose2d forward, Conv2d-s2 dgrad) are decomposed into the four
 //     output sub-pixel phases (blockIdx.z), each a small stride-1 convolution - no zero insertion.
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
-//     warps 4-7 = epilogue (tcgen05.ld -> bias / Dropout2d column scale -> bf16|f32 -> global).
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
+//     warps 4.. = epilogue (tcgen05.ld -> bias / Dropout2d column scale -> bf16|f32 -> global).
+//   Three forms, chosen per layer by tc_conv_run: one-shot CTAs (tc_conv_kernel, small problems and split-K),
+//   persistent CTAs with a double-buffered TMEM accumulator (tc_conv_persist_kernel), and persistent CTA
+//   pairs issuing M=256 cta_group::2 MMAs (tc_conv_pair_kernel, 128/256-wide tiles).
 //
 // tc_wgrad_kernel: dW[128 = 2 x 64 (tap, c_s chunk)][BN = c_u tile] += S^T . U over a range of
 //   64-pixel boxes (split-K across CTAs, fp32 atomics into the torch-layout gradient).  Both

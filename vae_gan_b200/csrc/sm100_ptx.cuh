@@ -177,14 +177,6 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
 }
 // issued by ONE thread of the pair's leader CTA (rank 0): A = 128 rows from each CTA, B = N/2 rows from
 // each CTA (same shared-memory offsets in both), D = 128 TMEM lanes x N columns in each CTA
-__device__ __forceinline__ void mma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void mma_bf16_ss_pair_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                                       bool accumulate) {
   asm volatile(
