@@ -125,6 +125,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use the host's cores
+    try:
+        torch.set_num_threads(max(1, min(len(os.sched_getaffinity(0)), 64)))
+    except Exception:
+        pass
     from oracle import vaegan_oracle as O
     batch = 4
     spec_g = O.GeneratorSpec(depth=2, length=1, feature_size=FEATURE)
