@@ -101,3 +101,72 @@ def test_data_parallel_contract_world2_gloo():
         assert p.exitcode == 0
     for rank, worst in res:
         assert worst < 1e-9, f"rank {rank}: summed DP gradients differ from the global-batch gradients by {worst:.2e}"
+
+
+def _worker_gp(rank, world, port, out_q):
+    """Gradient penalty under data parallelism (vae_gan_b200/train.py, loss_mode="wgan_gp"): every rank differentiates
+    the sum of ITS critic outputs with respect to ITS interpolates, the SyncBN all-reduces (forward sums, backward sums
+    and - in the second-order pass - their derivatives) supply the cross-rank terms, the local mean penalty is scaled
+    by 1/world, and the parameter gradients are summed."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from oracle import vaegan_oracle as O
+    from tests.gpu_util import discriminator_masks
+    B, S, fs = 4, 16, 8
+    spec = O.DiscriminatorSpec(1, fs, (1, 1, 1), (1, 2, 2), (2 * fs, 4 * fs, 8 * fs), input_size=S)
+    P0 = O.make_discriminator_params(spec, seed=21, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(2)
+    for k in P0:
+        if k.endswith((".weight", ".bias")) and P0[k].dim() == 1 and "bn" in k:
+            P0[k] = P0[k] + 0.1 * torch.randn(P0[k].shape, generator=gen, dtype=torch.float64)
+    real = torch.rand(B, 1, S, S, generator=gen, dtype=torch.float64)
+    fake = torch.rand(B, 1, S, S, generator=gen, dtype=torch.float64)
+    alpha = torch.rand(B, 1, 1, 1, generator=gen, dtype=torch.float64)
+    lb = B // world
+    g_masks, _ = discriminator_masks(spec, B, 13, 0)
+    l_masks, _ = discriminator_masks(spec, lb, 13, 0, sample_offset=rank * lb)
+    # single process, global batch
+    Pg = O.clone_params(P0, requires_grad=True)
+    keys = O.trainable_keys(Pg)
+    gp_g = O.gradient_penalty(Pg, spec, real, fake, alpha, g_masks)
+    want = torch.autograd.grad(gp_g, [Pg[k] for k in keys], allow_unused=True)
+    # data parallel
+    orig = O.batch_norm
+    O.batch_norm = _sync_batch_norm
+    try:
+        Pl = O.clone_params(P0, requires_grad=True)
+        sl = slice(rank * lb, (rank + 1) * lb)
+        gp_l = O.gradient_penalty(Pl, spec, real[sl], fake[sl], alpha[sl], l_masks) / world
+        got = torch.autograd.grad(gp_l, [Pl[k] for k in keys], allow_unused=True)
+    finally:
+        O.batch_norm = orig
+    tot = gp_l.detach().clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    worst = abs(float(tot) - float(gp_g)) / max(abs(float(gp_g)), 1e-12)
+    for k, g, w in zip(keys, got, want):
+        if w is None:
+            continue
+        g = (g if g is not None else torch.zeros_like(w)).clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        denom = float(w.abs().max())
+        if denom > 1e-12:
+            worst = max(worst, float((g - w).abs().max()) / denom)
+    out_q.put((rank, worst))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_penalty_data_parallel_contract_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker_gp, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, worst in res:
+        assert worst < 1e-8, f"rank {rank}: DP gradient penalty / its summed gradients differ from the global batch by {worst:.2e}"
