@@ -35,6 +35,10 @@ import torch
 IMAGE = 96
 FEATURE = 64
 GFLOP_PER_IMG_STEP = 127.59        # 3*G + 8*D forward GFLOPs, SURVEY.md section 8d / BASELINE.md
+# algorithmic bytes of the memory-bound family per image per step (10 B x E_G + 30 B x E_D)
+# and of the fused optimizer per step (28 B/param)
+MB_PER_IMG_STEP = 270.0
+OPT_GB_PER_STEP = 0.80
 
 
 def measured_peaks():
@@ -119,6 +123,77 @@ def cpu_baseline(budget_s: float = 20.0, batch: int = 4):
                       f"1x{IMAGE}x{IMAGE}, after 1 warm-up; {dt / n:.2f} s/iteration"}
 
 
+def gpu_lib_baseline(dev, batches=(256, 64), steps: int = 6, warm: int = 3):
+    """The bar SURVEY.md section 2.1 / BASELINE.md section 4 name ("GPU-lib"): the SAME modules in stock PyTorch
+    eager on this B200 - cuDNN convolutions, cuBLAS Linear layers, ATen BatchNorm / optimizer maths - i.e. what the
+    reference notebook itself runs when `device = cuda:0` (README.md:694, 910-911).  CHECKER code (the oracle port
+    on CUDA tensors; never imported by the product).  Full BCE + Adam iteration per step, CUDA events.
+    Variants: fp32 with TF32 off (the notebook's default numerics), fp32 with TF32 on, bf16 autocast + channels_last."""
+    from oracle import vaegan_oracle as O
+    spec_g = O.GeneratorSpec(depth=2, length=1, feature_size=FEATURE)
+    spec_d = O.DiscriminatorSpec(1, FEATURE, (1, 1, 1), (1, 2, 2), (2 * FEATURE, 4 * FEATURE, 8 * FEATURE), input_size=IMAGE)
+    out = {}
+    old_tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+
+    def run(variant, batch):
+        cl = variant == "bf16_autocast_channels_last"
+        tf32 = variant != "fp32"
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        Pg = {k: v.to(dev) for k, v in O.make_generator_params(spec_g, 0).items()}
+        Pd = {k: v.to(dev) for k, v in O.make_discriminator_params(spec_d, 1).items()}
+        if cl:
+            for P in (Pg, Pd):
+                for k, v in P.items():
+                    if v.dim() == 4:
+                        P[k] = v.contiguous(memory_format=torch.channels_last)
+        og, od = O.OptState(), O.OptState()
+        g = torch.Generator().manual_seed(1234)
+        x = torch.rand(batch, 1, IMAGE, IMAGE, generator=g).to(dev)
+        if cl:
+            x = x.contiguous(memory_format=torch.channels_last)
+
+        def one():
+            if cl:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return O.train_step(Pg, Pd, og, od, x, spec_g, spec_d)
+            return O.train_step(Pg, Pd, og, od, x, spec_g, spec_d)
+
+        for _ in range(warm):
+            one()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        return {"images_per_s": round(batch / ms * 1e3, 1), "ms_per_step": round(ms, 2)}
+
+    try:
+        for batch in batches:
+            for variant in ("fp32", "fp32_tf32", "bf16_autocast_channels_last"):
+                key = f"{variant}_b{batch}"
+                try:
+                    out[key] = run(variant, batch)
+                except torch.cuda.OutOfMemoryError:
+                    out[key] = {"error": "out of memory"}
+                except Exception as e:      # pragma: no cover - report, never fail the bench line
+                    out[key] = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
+                torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old_tf32
+    # `value` = the fastest library variant at the bench's own batch (batches[0]); the other batch is reported beside it
+    good = {k: v["images_per_s"] for k, v in out.items() if "images_per_s" in v and k.endswith(f"_b{batches[0]}")}
+    best = max(good, key=good.get) if good else None
+    return {"kind": "stock PyTorch eager on the same B200 (cuDNN/cuBLAS/ATen), oracle port on CUDA tensors, "
+                    "full BCE + Adam iteration, CUDA events", "unit": "images/s", "steps": steps, "warmup": warm,
+            "variants": out, "best": best, "value": good.get(best) if best else None,
+            "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (the oracle port; the
     notebook itself is not present on the GPU box), all host threads, bounded sample per step."""
@@ -199,15 +274,73 @@ def roofline_probe(dev, batch: int, peaks):
     avg = sum(ms[1:-1]) / (len(ms) - 2)
     flops = 2.0 * batch * IMAGE * IMAGE * cout * cin * 9
     achieved = flops / (avg * 1e-3) / 1e12
-    # DRAM traffic of this exact launch from `ncu --set full` (profiles/r1_ncu_full_pair_conv_128x128_b64.csv):
-    # 151.4 MB read (= the input tensor, once) + 101.7 MB written (the rest of the 151 MB output still sits in
-    # the 126 MB L2 when the kernel ends); algorithmic bytes = 151 + 151 + 0.3 MB.
-    traffic = 253.1e6 * batch / 64.0 if batch == 64 else None
+    traffic = ncu_traffic("conv_128x128_fwd", batch)       # measured by ncu this round, or None
     return {"bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["bf16"], "unit": "TFLOP/s",
             "frac": round(achieved / peaks["bf16"], 4), "traffic": traffic,
             "kernel": "tc_conv_pair_kernel<128,2,4,8> (persistent cta_group::2 tcgen05 implicit GEMM), Conv2d 128->128 3x3 s1 @96x96",
             "batch": batch, "ms_per_launch": round(avg, 4), "flop_per_launch": flops,
             "peak_source": f"{peaks['source']} bf16 burst (kernel timed alone)"}
+
+
+def roofline_hbm_probe(dev, batch: int, peaks):
+    """Top memory-bound kernel of the step by time share: the BatchNorm(+LeakyReLU) backward APPLY
+    (dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*lrelu'), on the 128-channel 96x96 tensor of D's first
+    residual block.  Algorithmic bytes: read dy, read x, write dx at bf16 = 6 B/element.
+    Timed alone with CUDA events; three rotating buffer sets (> 126 MB L2 each)."""
+    import ctypes as C
+    import vae_gan_b200.functional as VF
+    from vae_gan_b200 import _lib
+    c = 128
+    g = torch.Generator().manual_seed(0)
+    nbuf = 3
+    xs = [VF.as_act(torch.randn(batch, c, IMAGE, IMAGE, generator=g).to(dev), torch.bfloat16) for _ in range(nbuf)]
+    dys = [VF.as_act(torch.randn(batch, c, IMAGE, IMAGE, generator=g).to(dev), torch.bfloat16) for _ in range(nbuf)]
+    dx = torch.empty_like(xs[0])
+    gamma = torch.rand(c, device=dev) + 0.5
+    beta = torch.randn(c, device=dev) * 0.1
+    mr = torch.cat([torch.zeros(c, device=dev), torch.ones(c, device=dev)])
+    sums = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+    d = VF._bn_desc(xs[0], 0.2, 0.0, 0, True)
+    rows = batch * IMAGE * IMAGE
+    iters = 12
+    s = _lib.stream_ptr()
+    for i in range(3):
+        _lib.call("vg_bn_act_backward_apply", dys[i % nbuf].data_ptr(), xs[i % nbuf].data_ptr(), mr.data_ptr(), gamma.data_ptr(),
+                  beta.data_ptr(), sums.data_ptr(), float(rows), C.byref(d), None, None, dx.data_ptr(), s)
+    torch.cuda.synchronize(dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for i in range(iters):
+        evs[i][0].record()
+        _lib.call("vg_bn_act_backward_apply", dys[i % nbuf].data_ptr(), xs[i % nbuf].data_ptr(), mr.data_ptr(), gamma.data_ptr(),
+                  beta.data_ptr(), sums.data_ptr(), float(rows), C.byref(d), None, None, dx.data_ptr(), s)
+        evs[i][1].record()
+    torch.cuda.synchronize(dev)
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    avg = sum(ms[1:-1]) / (len(ms) - 2)
+    nbytes = 3.0 * rows * c * 2
+    achieved = nbytes / (avg * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": round(achieved / peaks["hbm"], 4), "traffic": ncu_traffic("bn_act_bwd_apply", batch),
+            "kernel": "BatchNorm+LeakyReLU backward apply (vg_bn_act_backward_apply), 128 channels @96x96",
+            "batch": batch, "ms_per_launch": round(avg, 4), "bytes_per_launch": nbytes,
+            "peak_source": f"{peaks['source']} HBM copy bandwidth"}
+
+
+def ncu_traffic(tag: str, batch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture
+    of this round (profiles/r2_ncu_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep); None when
+    no capture of that kernel at that batch is committed."""
+    f = ROOT / "profiles" / "r2_ncu_traffic.json"
+    if not f.exists():
+        return None
+    try:
+        d = json.loads(f.read_text())
+        e = d.get(tag)
+        if e and int(e.get("batch", -1)) == int(batch):
+            return float(e["dram_bytes"])
+    except Exception:
+        pass
+    return None
 
 
 def run_decode_sweep(args):
@@ -256,6 +389,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-lib-baseline", action="store_true", help="skip the stock-PyTorch-on-this-GPU leg (gpu_lib_baseline)")
     ap.add_argument("--fp32", action="store_true", help="run the fp32 parity path instead of bf16")
     ap.add_argument("--loss-mode", default="bce", choices=["bce", "wgan", "wgan_gp"],
                     help="bce + adam = BASELINE north_star (default); wgan_gp + --optimizer rmsprop = the notebook as written")
@@ -269,9 +403,10 @@ def main():
     if args.workload == "decode":
         run_decode_sweep(args)
         return
-    global IMAGE, FEATURE, GFLOP_PER_IMG_STEP
+    global IMAGE, FEATURE, GFLOP_PER_IMG_STEP, MB_PER_IMG_STEP, OPT_GB_PER_STEP
     if args.workload == "cfg4":
         IMAGE, FEATURE, GFLOP_PER_IMG_STEP = 256, 128, 3621.5
+        MB_PER_IMG_STEP, OPT_GB_PER_STEP = 10 * 81.99 + 30 * 100.66, 28 * 305.13e6 / 1e9
         if args.global_batch == 256:
             args.global_batch = 16 * max(1, int(os.environ.get("WORLD_SIZE", "1")))
 
@@ -379,7 +514,7 @@ def main():
             ms_e = float(t)
         e2e_value = args.global_batch * Ke / (ms_e * 1e-3)
 
-        roof = cpu = None
+        roof = roof_hbm = cpu = lib = None
         # drop the captured graph (it holds NCCL work) on EVERY rank before any teardown
         tr.graph = None
         torch.cuda.synchronize(dev)
@@ -387,11 +522,19 @@ def main():
         if rank == 0:
             torch.cuda.empty_cache()
             roof = roofline_probe(dev, min(local_b, 64), peaks)
+            roof_hbm = roofline_hbm_probe(dev, min(local_b, 64), peaks)
+            if world == 1 and not args.skip_lib_baseline and args.workload == "train":
+                del tr, G, D
+                torch.cuda.empty_cache()
+                lib = gpu_lib_baseline(dev, batches=tuple(dict.fromkeys((args.global_batch, 64))))
             if world == 1 and not args.skip_cpu_baseline:
                 cpu = cpu_baseline()
 
     if rank == 0:
         step_tflops = GFLOP_PER_IMG_STEP * 1e9 * args.global_batch / (ms_per_step * 1e-3) / 1e12 / world
+        # step-level roofline: t_ideal = F_step / tensor peak + Bytes_step / HBM peak, per GPU
+        t_tensor = GFLOP_PER_IMG_STEP * 1e9 * local_b / (peaks["bf16"] * 1e12) * 1e3
+        t_hbm = (MB_PER_IMG_STEP * 1e6 * local_b + OPT_GB_PER_STEP * 1e9) / (peaks["hbm"] * 1e9) * 1e3
         out = {
             "metric": "train_images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
@@ -413,7 +556,12 @@ def main():
             "launches_per_step": int(launches_per_step),
             "step_model_tflops_per_gpu": round(step_tflops, 1),
             "step_frac_of_tensor_peak": round(step_tflops / peaks["bf16_sustained"], 4),
+            "t_ideal_ms": round(t_tensor + t_hbm, 3), "t_ideal_tensor_ms": round(t_tensor, 3), "t_ideal_hbm_ms": round(t_hbm, 3),
+            "t_measured_ms": round(ms_per_step, 3), "step_frac_of_ideal": round((t_tensor + t_hbm) / ms_per_step, 4),
             "roofline": roof,
+            "roofline_hbm": roof_hbm,
+            "gpu_lib_baseline": lib,
+            "vs_gpu_lib": (round(value / lib["value"], 3) if lib and lib.get("value") else None),
             "cpu_baseline": cpu,
             "losses_last_step": {k: round(v, 4) for k, v in losses.items()},
         }

@@ -12,8 +12,10 @@
  *   - plain C types only; every pointer is a DEVICE pointer unless stated otherwise;
  *   - activations are NHWC (channels innermost), dtype VG_F32 or VG_BF16;
  *     parameters, statistics and gradients of parameters are fp32 in torch's own layouts;
- *   - the caller owns every buffer (incl. workspaces); the library never allocates device
- *     memory and keeps no pointer after a call returns;
+ *   - the caller owns every buffer (incl. workspaces); no compute entry point allocates device
+ *     memory or keeps a pointer after it returns (the only allocator calls are the setup-time
+ *     vg_peer_alloc / vg_peer_free helpers of the NVLink exchange buffers, which must be plain
+ *     cudaMalloc memory so that their IPC handles can be opened by the other ranks);
  *   - all work is enqueued on `stream` (a cudaStream_t); no host synchronisation, CUDA-graph
  *     capturable;
  *   - return value: VG_OK or a negative VgStatus; vg_last_error() gives a thread-local
@@ -139,6 +141,42 @@ int vg_bn_add_forward(const void* a, const float* mean_rstd_a, const float* gamm
                       const float* beta_a, const void* b, const float* mean_rstd_b,
                       const float* gamma_b, const float* beta_b, const VgBnDesc* d, void* out,
                       double* stats, vg_stream_t stream);
+/* ---- fused-statistics forms (round 2): the same BatchNorm call sites (README.md:143,152,159,166,169,
+ *      376,382,388,442 and the residual adds :183,195,405,417) with the small per-layer kernels folded in.
+ * A VgBnChannel says where one BatchNorm's (mean, rstd) come from:
+ *   mean_rstd_in != NULL           : use them as given (float[2c]);
+ *   else training && sums != NULL  : finalize from the FINAL (already all-reduced under SyncBN) double[2c]
+ *                                    sum / sum of squares over `count` elements per channel; running_mean /
+ *                                    running_var (nullable) are updated with `momentum` and the unbiased
+ *                                    variance exactly like vg_bn_finalize;
+ *   else (eval)                    : from running_mean / running_var like vg_bn_eval_stats.
+ * In the last two cases mean_rstd_out (nullable, float[2c]) receives (mean, rstd) for the backward. */
+typedef struct {
+  const float* gamma;
+  const float* beta;
+  const float* mean_rstd_in;
+  const double* sums;
+  double count;
+  float* running_mean;
+  float* running_var;
+  float* mean_rstd_out;
+  float eps, momentum;
+} VgBnChannel;
+/* y = dropout(leaky_relu(batch_norm(x))): vg_bn_finalize | vg_bn_eval_stats + vg_bn_act_forward in ONE launch */
+int vg_bn_act_forward_fused(const void* x, const VgBnChannel* bn, const VgBnDesc* d, void* y, vg_stream_t stream);
+/* out = leaky_relu(bnA(a) + bnB(b)) (+ stats of out), bn_a / bn_b nullable = identity: both finalizes folded in */
+int vg_bn_add_forward_fused(const void* a, const VgBnChannel* bn_a, const void* b, const VgBnChannel* bn_b,
+                            const VgBnDesc* d, void* out, double* stats, vg_stream_t stream);
+/* vg_bn_act_backward_apply + vg_bn_param_grads in ONE launch: additionally dgamma += param_scale * sum g*xhat,
+ * dbeta += param_scale * sum g (both nullable; param_scale = 1/world under data parallelism, where the sums are
+ * already global and the flat gradient buffer is summed over the ranks afterwards). */
+int vg_bn_act_backward_apply_fused(const void* dy, const void* x, const float* mean_rstd,
+                                   const float* gamma, const float* beta, const double* sums,
+                                   double count, const VgBnDesc* d, const float* out_colscale,
+                                   const void* addend, void* dx, float* dgamma, float* dbeta,
+                                   float param_scale, vg_stream_t stream);
+/* dgamma += scale * sum g*xhat, dbeta += scale * sum g (vg_bn_param_grads with the 1/world factor) */
+int vg_bn_param_grads_scaled(const double* sums, int c, float scale, float* dgamma, float* dbeta, vg_stream_t stream);
 /* y = leaky_relu(x) on a flat fp32 tensor (discriminator head, README.md:475-481) */
 int vg_lrelu_forward(const void* x, long long n, int dtype, float slope, void* y, vg_stream_t stream);
 /* dx = dy * (y_ref > 0 ? 1 : slope) */
@@ -201,7 +239,7 @@ int vg_linear_wgrad(const void* x, const void* dy, int m, int n, int k, int dtyp
 int vg_spectral_norm_sigma(const float* w_orig, int rows, int cols, float* u, float* v,
                            int training, float eps, float* sigma, float* workspace,
                            vg_stream_t stream);
-/* dw_orig += (dw_hat - <dw_hat, w_orig/sigma> u v^T) / sigma ; workspace float[1] */
+/* dw_orig += (dw_hat - <dw_hat, w_orig/sigma> u v^T) / sigma ; workspace: float[1] (callers may pass more) */
 int vg_spectral_norm_backward(const float* dw_hat, const float* w_orig, const float* u,
                               const float* v, const float* sigma, int rows, int cols,
                               float* dw_orig, float* workspace, vg_stream_t stream);
@@ -260,7 +298,8 @@ int vg_optimizer_step(float* p, const float* g, float* m, float* v, long long n,
  *   peer_data[r]  : rank r's data buffer,  double[n_slots][world][VG_PEER_MAX_N]   (peer-mapped)
  *   peer_flags[r] : rank r's flag buffer,  unsigned long long[n_slots][world]      (zero-initialised)
  *   epoch_ptr     : device counter, identical on all ranks, strictly increasing between two uses of
- *                   the same slot (the trainer's step counter, >= 1)
+ *                   the same slot (the exchange's own per-iteration counter, >= 1; a flag passes the wait only
+ *                   when it EQUALS the epoch, so stale and future values are both rejected)
  * The vector is reduced IN PLACE.  A rank must not reuse a slot before every peer has consumed it; using
  * each slot once per step with at least two exchanges per step guarantees that. */
 #define VG_PEER_MAX_WORLD 8
@@ -288,6 +327,9 @@ int vg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long 
 int vg_nchw_to_nhwc(const float* src, int n, int c, int h, int w, int dst_dtype, void* dst, vg_stream_t stream);
 int vg_nhwc_to_nchw(const void* src, int src_dtype, int n, int c, int h, int w, float* dst, vg_stream_t stream);
 int vg_fill_zero(void* p, size_t bytes, vg_stream_t stream);
+/* dst = src * (*scale): `scale` is a DEVICE scalar (no host sync) - rescales the loss kernels' stored gradients
+ * when the loss is back-propagated with a gradient other than 1 */
+int vg_scale(const void* src, const float* scale, long long n, int dtype, void* dst, vg_stream_t stream);
 
 #ifdef __cplusplus
 }

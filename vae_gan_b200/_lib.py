@@ -29,6 +29,11 @@ class VgBnDesc(C.Structure):
                 ("training", c_int), ("step_ptr", c_vp)]
 
 
+class VgBnChannel(C.Structure):
+    _fields_ = [("gamma", c_vp), ("beta", c_vp), ("mean_rstd_in", c_vp), ("sums", c_vp), ("count", c_d),
+                ("running_mean", c_vp), ("running_var", c_vp), ("mean_rstd_out", c_vp), ("eps", c_f), ("momentum", c_f)]
+
+
 class VgLossDesc(C.Structure):
     _fields_ = [("n_pix", c_ll), ("n_pix_global", c_ll), ("n_lat", c_ll), ("n_logits", c_int),
                 ("n_logits_global", c_int), ("adv_mode", c_int), ("w_adv", c_f), ("w_recon", c_f),
@@ -63,6 +68,12 @@ _PROTOS = {
     "vg_bn_act_backward_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, C.POINTER(VgBnDesc), c_vp, c_vp, c_vp, c_vp]),
     "vg_bn_param_grads": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp]),
     "vg_bn_add_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(VgBnDesc), c_vp, c_vp, c_vp]),
+    "vg_bn_act_forward_fused": (c_int, [c_vp, C.POINTER(VgBnChannel), C.POINTER(VgBnDesc), c_vp, c_vp]),
+    "vg_bn_add_forward_fused": (c_int, [c_vp, C.POINTER(VgBnChannel), c_vp, C.POINTER(VgBnChannel), C.POINTER(VgBnDesc), c_vp, c_vp, c_vp]),
+    "vg_bn_act_backward_apply_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, C.POINTER(VgBnDesc), c_vp, c_vp, c_vp,
+                                               c_vp, c_vp, c_f, c_vp]),
+    "vg_bn_param_grads_scaled": (c_int, [c_vp, c_int, c_f, c_vp, c_vp, c_vp]),
+    "vg_scale": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_vp]),
     "vg_lrelu_forward": (c_int, [c_vp, c_ll, c_int, c_f, c_vp, c_vp]),
     "vg_lrelu_backward": (c_int, [c_vp, c_vp, c_ll, c_int, c_f, c_vp, c_vp]),
     "vg_add": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_vp]),

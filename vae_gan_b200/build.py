@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libvaegan_sm100.so"
-SOURCES = ["lib.cu", "bn.cu", "conv_simt.cu", "conv_tc.cu", "conv_api.cu", "misc.cu"]
+SOURCES = ["lib.cu", "bn.cu", "bn_stream.cu", "conv_simt.cu", "conv_tc.cu", "conv_api.cu", "misc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",

@@ -9,6 +9,7 @@
 // atomicAdd per (block, channel).  C == 1 tensors are folded into an [rows/8][8] view.
 // Anything else takes the scalar path.
 #include <algorithm>
+#include <mutex>
 #include "vg_common.cuh"
 
 namespace vg {
@@ -196,11 +197,11 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* 
   mean_rstd[c + ch] = (float)(1.0 / sqrt((double)rv[ch] + (double)eps));
 }
 
-__global__ void bn_param_grads_kernel(const double* __restrict__ sums, int c, float* dgamma, float* dbeta) {
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, int c, double scale, float* dgamma, float* dbeta) {
   int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
-  if (dbeta) dbeta[ch] += (float)sums[ch];
-  if (dgamma) dgamma[ch] += (float)sums[c + ch];
+  if (dbeta) dbeta[ch] += (float)(sums[ch] * scale);
+  if (dgamma) dgamma[ch] += (float)(sums[c + ch] * scale);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -720,6 +721,20 @@ __global__ void philox_uniform_kernel(float* __restrict__ out, long long n, unsi
 // ==========================================================================================
 using namespace vg;
 
+namespace vg {
+// bn_stream.cu: the bulk-copy pipelined implementations (default whenever the tensor qualifies)
+bool bn_stream_ok(const VgBnDesc* d, const void* p0, const void* p1, const void* p2, const void* p3);
+int bn_stream_stats(const void* x, const VgBnDesc* d, double* sums, cudaStream_t s);
+int bn_stream_act_forward(const void* x, const VgBnChannel* bn, const VgBnDesc* d, void* y, cudaStream_t s);
+int bn_stream_bwd_reduce(const void* dy, const void* x, const float* mean_rstd, const float* gamma, const float* beta,
+                         const VgBnDesc* d, double* sums, cudaStream_t s);
+int bn_stream_bwd_apply(const void* dy, const void* x, const float* mean_rstd, const float* gamma, const float* beta,
+                        const double* sums, double count, const VgBnDesc* d, const float* out_colscale, const void* addend,
+                        void* dx, float* dgamma, float* dbeta, float param_scale, cudaStream_t s);
+int bn_stream_add(const void* x0, const VgBnChannel* bn_a, const void* x1, const VgBnChannel* bn_b, const VgBnDesc* d, void* out,
+                  double* stats, cudaStream_t s);
+}  // namespace vg
+
 static int check_desc(const VgBnDesc* d) {
   VG_CHECK_ARG(d != nullptr, "VgBnDesc is null");
   VG_CHECK_ARG(d->rows >= 0 && d->c > 0 && d->hw > 0, "bad VgBnDesc dims rows=%lld c=%d hw=%d", d->rows, d->c, d->hw);
@@ -742,6 +757,11 @@ extern "C" int vg_bn_stats(const void* x, const VgBnDesc* d, double* sums, vg_st
   VG_CHECK_ARG(x && sums, "null pointer");
   if (d->rows == 0) return VG_OK;
   cudaStream_t s = as_stream(stream);
+  {
+    VgBnDesc dd = *d;
+    dd.drop_p = 0.f;                 // statistics never draw dropout bits
+    if (bn_stream_ok(&dd, x, nullptr, nullptr, nullptr)) return bn_stream_stats(x, &dd, sums, s);
+  }
   int path = path_for(d);
   if (path) {
     bool fold = path == 2;
@@ -784,11 +804,15 @@ extern "C" int vg_bn_eval_stats(const float* running_mean, const float* running_
   return VG_OK;
 }
 
-extern "C" int vg_bn_param_grads(const double* sums, int c, float* dgamma, float* dbeta, vg_stream_t stream) {
+extern "C" int vg_bn_param_grads_scaled(const double* sums, int c, float scale, float* dgamma, float* dbeta, vg_stream_t stream) {
   VG_CHECK_ARG(sums && c > 0, "bad args");
-  bn_param_grads_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, c, dgamma, dbeta);
+  bn_param_grads_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, c, (double)scale, dgamma, dbeta);
   VG_LAUNCHED();
   return VG_OK;
+}
+
+extern "C" int vg_bn_param_grads(const double* sums, int c, float* dgamma, float* dbeta, vg_stream_t stream) {
+  return vg_bn_param_grads_scaled(sums, c, 1.0f, dgamma, dbeta, stream);
 }
 
 template <typename T>
@@ -821,9 +845,50 @@ extern "C" int vg_bn_act_forward(const void* x, const float* mean_rstd, const fl
   if (rc) return rc;
   VG_CHECK_ARG(x && mean_rstd && gamma && beta && y, "null pointer");
   if (d->rows == 0) return VG_OK;
+  if (bn_stream_ok(d, x, y, nullptr, nullptr)) {
+    VgBnChannel ch{};
+    ch.gamma = gamma; ch.beta = beta; ch.mean_rstd_in = mean_rstd;
+    return bn_stream_act_forward(x, &ch, d, y, as_stream(stream));
+  }
   if (d->dtype == VG_BF16)
     return bn_act_forward_t<__nv_bfloat16>((const __nv_bfloat16*)x, mean_rstd, gamma, beta, d, (__nv_bfloat16*)y, as_stream(stream));
   return bn_act_forward_t<float>((const float*)x, mean_rstd, gamma, beta, d, (float*)y, as_stream(stream));
+}
+
+// (mean, rstd) of a VgBnChannel through the stand-alone finalize / eval-stats kernels: the composed path for tensors
+// the streaming kernels do not take (odd channel counts, misaligned views)
+static int channel_mean_rstd(const VgBnChannel* bn, const VgBnDesc* d, const float** mr, vg_stream_t stream) {
+  if (bn->mean_rstd_in != nullptr) { *mr = bn->mean_rstd_in; return VG_OK; }
+  VG_CHECK_ARG(bn->mean_rstd_out != nullptr, "mean_rstd_out is required when (mean, rstd) are not given");
+  *mr = bn->mean_rstd_out;
+  if (d->training && bn->sums != nullptr)
+    return vg_bn_finalize(bn->sums, bn->count, d->c, bn->eps, bn->momentum, bn->running_mean, bn->running_var, bn->mean_rstd_out, stream);
+  VG_CHECK_ARG(bn->running_mean && bn->running_var, "eval-mode BatchNorm needs running statistics");
+  return vg_bn_eval_stats(bn->running_mean, bn->running_var, d->c, bn->eps, bn->mean_rstd_out, stream);
+}
+static int check_channel(const VgBnChannel* bn, const VgBnDesc* d) {
+  VG_CHECK_ARG(bn->gamma && bn->beta, "BatchNorm needs gamma / beta");
+  if (bn->mean_rstd_in == nullptr) {
+    if (d->training && bn->sums != nullptr) {
+      VG_CHECK_ARG(bn->count > 0, "count must be positive");
+      VG_CHECK_ARG((bn->running_mean == nullptr) == (bn->running_var == nullptr), "running_mean/var must both be given or both null");
+    } else {
+      VG_CHECK_ARG(bn->running_mean && bn->running_var, "eval-mode BatchNorm needs running statistics");
+    }
+  }
+  return VG_OK;
+}
+
+extern "C" int vg_bn_act_forward_fused(const void* x, const VgBnChannel* bn, const VgBnDesc* d, void* y, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(x && bn && y, "null pointer");
+  if ((rc = check_channel(bn, d))) return rc;
+  if (d->rows == 0) return VG_OK;
+  if (bn_stream_ok(d, x, y, nullptr, nullptr)) return bn_stream_act_forward(x, bn, d, y, as_stream(stream));
+  const float* mr = nullptr;
+  if ((rc = channel_mean_rstd(bn, d, &mr, stream))) return rc;
+  return vg_bn_act_forward(x, mr, bn->gamma, bn->beta, d, y, stream);
 }
 
 template <typename T, bool APPLY>
@@ -861,11 +926,32 @@ extern "C" int vg_bn_act_backward_reduce(const void* dy, const void* x, const fl
   if (rc) return rc;
   VG_CHECK_ARG(dy && x && mean_rstd && gamma && beta && sums, "null pointer");
   if (d->rows == 0) return VG_OK;
+  if (bn_stream_ok(d, dy, x, nullptr, nullptr)) return bn_stream_bwd_reduce(dy, x, mean_rstd, gamma, beta, d, sums, as_stream(stream));
   if (d->dtype == VG_BF16)
     return bn_act_backward_t<__nv_bfloat16, false>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean_rstd, gamma, beta, d, sums,
                                                    nullptr, 1.0, nullptr, nullptr, nullptr, as_stream(stream));
   return bn_act_backward_t<float, false>((const float*)dy, (const float*)x, mean_rstd, gamma, beta, d, sums, nullptr, 1.0, nullptr,
                                          nullptr, nullptr, as_stream(stream));
+}
+
+extern "C" int vg_bn_act_backward_apply_fused(const void* dy, const void* x, const float* mean_rstd, const float* gamma,
+                                              const float* beta, const double* sums, double count, const VgBnDesc* d,
+                                              const float* out_colscale, const void* addend, void* dx, float* dgamma,
+                                              float* dbeta, float param_scale, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(dy && x && mean_rstd && gamma && beta && dx, "null pointer");
+  VG_CHECK_ARG(!d->training || (sums != nullptr && count > 0), "training-mode BN backward needs sums and count");
+  VG_CHECK_ARG((dgamma == nullptr && dbeta == nullptr) || sums != nullptr, "parameter gradients need the sums");
+  if (d->rows == 0) return VG_OK;
+  const bool fold_cs = (d->c == 1 && out_colscale != nullptr);      // per-sample scale needs real row indices
+  if (!fold_cs && bn_stream_ok(d, dy, x, addend, dx))
+    return bn_stream_bwd_apply(dy, x, mean_rstd, gamma, beta, sums, count, d, out_colscale, addend, dx, dgamma, dbeta, param_scale,
+                               as_stream(stream));
+  rc = vg_bn_act_backward_apply(dy, x, mean_rstd, gamma, beta, sums, count, d, out_colscale, addend, dx, stream);
+  if (rc) return rc;
+  if (dgamma != nullptr || dbeta != nullptr) rc = vg_bn_param_grads_scaled(sums, d->c, param_scale, dgamma, dbeta, stream);
+  return rc;
 }
 
 extern "C" int vg_bn_act_backward_apply(const void* dy, const void* x, const float* mean_rstd, const float* gamma,
@@ -876,6 +962,9 @@ extern "C" int vg_bn_act_backward_apply(const void* dy, const void* x, const flo
   VG_CHECK_ARG(dy && x && mean_rstd && gamma && beta && dx, "null pointer");
   VG_CHECK_ARG(!d->training || (sums != nullptr && count > 0), "training-mode BN backward needs sums and count");
   if (d->rows == 0) return VG_OK;
+  if (!(d->c == 1 && out_colscale != nullptr) && bn_stream_ok(d, dy, x, addend, dx))
+    return bn_stream_bwd_apply(dy, x, mean_rstd, gamma, beta, sums, count, d, out_colscale, addend, dx, nullptr, nullptr, 1.f,
+                               as_stream(stream));
   if (d->dtype == VG_BF16)
     return bn_act_backward_t<__nv_bfloat16, true>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean_rstd, gamma, beta, d, nullptr,
                                                   sums, count, out_colscale, (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx,
@@ -907,8 +996,10 @@ extern "C" int vg_bn_act_double_backward_reduce(const void* dy, const void* x, c
   VG_CHECK_ARG(vec_ok(d->c) && d->training && d->drop_p == 0.f, "needs training-mode BatchNorm, channels % 8 == 0 and <= 2048, no dropout");
   if (d->rows == 0) return VG_OK;
   if (d->dtype == VG_BF16) {
-    static bool attr = false;
-    if (!attr) { VG_CUDA(cudaFuncSetAttribute(bn_dbl_bwd_vec_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024)); attr = true; }
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(bn_dbl_bwd_vec_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024); });
+    VG_CUDA(attr_err);
     return bn_dbl_bwd_t<__nv_bfloat16, false>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)G, mean_rstd, gamma, beta,
                                               d, colscale, sums5, nullptr, 1.0, nullptr, nullptr, as_stream(stream));
   }
@@ -966,11 +1057,33 @@ extern "C" int vg_bn_add_forward(const void* a, const float* mean_rstd_a, const 
   VG_CHECK_ARG(!mean_rstd_a || (gamma_a && beta_a), "bnA needs gamma/beta");
   VG_CHECK_ARG(!mean_rstd_b || (gamma_b && beta_b), "bnB needs gamma/beta");
   if (d->rows == 0) return VG_OK;
+  if (bn_stream_ok(d, a, b, out, nullptr)) {
+    VgBnChannel ca{}, cb{};
+    ca.gamma = gamma_a; ca.beta = beta_a; ca.mean_rstd_in = mean_rstd_a;
+    cb.gamma = gamma_b; cb.beta = beta_b; cb.mean_rstd_in = mean_rstd_b;
+    return bn_stream_add(a, mean_rstd_a ? &ca : nullptr, b, mean_rstd_b ? &cb : nullptr, d, out, stats, as_stream(stream));
+  }
   if (d->dtype == VG_BF16)
     return bn_add_t<__nv_bfloat16>((const __nv_bfloat16*)a, mean_rstd_a, gamma_a, beta_a, (const __nv_bfloat16*)b, mean_rstd_b, gamma_b,
                                    beta_b, d, (__nv_bfloat16*)out, stats, as_stream(stream));
   return bn_add_t<float>((const float*)a, mean_rstd_a, gamma_a, beta_a, (const float*)b, mean_rstd_b, gamma_b, beta_b, d, (float*)out,
                          stats, as_stream(stream));
+}
+
+extern "C" int vg_bn_add_forward_fused(const void* a, const VgBnChannel* bn_a, const void* b, const VgBnChannel* bn_b,
+                                       const VgBnDesc* d, void* out, double* stats, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(a && b && out, "null pointer");
+  if (bn_a != nullptr && (rc = check_channel(bn_a, d))) return rc;
+  if (bn_b != nullptr && (rc = check_channel(bn_b, d))) return rc;
+  if (d->rows == 0) return VG_OK;
+  if (bn_stream_ok(d, a, b, out, nullptr)) return bn_stream_add(a, bn_a, b, bn_b, d, out, stats, as_stream(stream));
+  const float *mra = nullptr, *mrb = nullptr;
+  if (bn_a != nullptr && (rc = channel_mean_rstd(bn_a, d, &mra, stream))) return rc;
+  if (bn_b != nullptr && (rc = channel_mean_rstd(bn_b, d, &mrb, stream))) return rc;
+  return vg_bn_add_forward(a, mra, bn_a ? bn_a->gamma : nullptr, bn_a ? bn_a->beta : nullptr, b, mrb, bn_b ? bn_b->gamma : nullptr,
+                           bn_b ? bn_b->beta : nullptr, d, out, stats, stream);
 }
 
 extern "C" int vg_lrelu_backward(const void* dy, const void* y_ref, long long n, int dtype, float slope, void* dx,

@@ -1116,12 +1116,11 @@ bool tc_wgrad_supported(const VgConvDesc* d) {
 
 template <int BN, int MT, int STAGES>
 static int launch_conv(const TcConvParams& p, dim3 grid, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    VG_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 ConvSmem<BN, MT, STAGES>::kBytes));
-    attr_done = true;
-  }
+  static std::once_flag once;          // autograd worker threads call in concurrently
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_conv_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 ConvSmem<BN, MT, STAGES>::kBytes); });
+  VG_CUDA(attr_err);
   grid.x = (unsigned)cdiv(grid.x, MT);
   tc_conv_kernel<BN, MT, STAGES><<<grid, kTcThreads, ConvSmem<BN, MT, STAGES>::kBytes, s>>>(p);
   VG_LAUNCHED();
@@ -1130,12 +1129,11 @@ static int launch_conv(const TcConvParams& p, dim3 grid, cudaStream_t s) {
 
 template <int BN, int MT, int STAGES, int EW, int G>
 static int launch_conv_persist(const TcConvParams& p, dim3 grid, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    VG_CUDA(cudaFuncSetAttribute(tc_conv_persist_kernel<BN, MT, STAGES, EW, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 ConvPersistSmem<BN, MT, STAGES, EW>::kBytes));
-    attr_done = true;
-  }
+  static std::once_flag once;          // autograd worker threads call in concurrently
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_conv_persist_kernel<BN, MT, STAGES, EW, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 ConvPersistSmem<BN, MT, STAGES, EW>::kBytes); });
+  VG_CUDA(attr_err);
   const int n_groups = (int)cdiv(grid.x, MT);
   const int n_ntiles = (int)grid.y;
   const int n_z = (int)grid.z;
@@ -1149,12 +1147,11 @@ static int launch_conv_persist(const TcConvParams& p, dim3 grid, cudaStream_t s)
 
 template <int BN, int MT, int STAGES, int EW>
 static int launch_conv_pair(const TcConvParams& p, dim3 grid, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    VG_CUDA(cudaFuncSetAttribute(tc_conv_pair_kernel<BN, MT, STAGES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 ConvPairSmem<BN, MT, STAGES, EW>::kBytes));
-    attr_done = true;
-  }
+  static std::once_flag once;          // autograd worker threads call in concurrently
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_conv_pair_kernel<BN, MT, STAGES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 ConvPairSmem<BN, MT, STAGES, EW>::kBytes); });
+  VG_CUDA(attr_err);
   const int n_groups = (int)(grid.x / (2 * MT));      // the caller checked divisibility
   const int n_ntiles = (int)grid.y;
   const int n_z = (int)grid.z;
@@ -1168,11 +1165,10 @@ static int launch_conv_pair(const TcConvParams& p, dim3 grid, cudaStream_t s) {
 
 template <int NB, int STAGES>
 static int launch_wgrad(const TcWgradParams& p, dim3 grid, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    VG_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<NB, STAGES>::kBytes));
-    attr_done = true;
-  }
+  static std::once_flag once;          // autograd worker threads call in concurrently
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_wgrad_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<NB, STAGES>::kBytes); });
+  VG_CUDA(attr_err);
   tc_wgrad_kernel<NB, STAGES><<<grid, kTcThreads, WgradSmem<NB, STAGES>::kBytes, s>>>(p);
   VG_LAUNCHED();
   return VG_OK;

@@ -445,26 +445,28 @@ __global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* __restr
     double* dst = reinterpret_cast<double*>(pd.peer_data[r]) + slot_off;
     for (int i = tid; i < n; i += blockDim.x) dst[i] = vec[i];
   }
-  __threadfence_system();
-  __syncthreads();
-  // 2. publish: flag[slot][rank] = epoch on every rank
+  __threadfence_system();          // every writer: its stores are visible system-wide ...
+  __syncthreads();                 // ... before any thread of the block publishes
+  // 2. publish: flag[slot][rank] = epoch on every rank.  The publishing threads did not write all the data
+  //    themselves: the fence after the barrier orders the block's (already system-visible) stores before the flag.
   if (tid < pd.world) {
+    __threadfence_system();
     volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(pd.peer_flags[tid]) + (size_t)slot * pd.world + pd.rank;
     *f = epoch;
   }
-  // 3. wait until every rank has published this epoch into MY flags
+  // 3. wait until every rank has published THIS epoch into MY flags (equality: a stale or a future value never passes)
   if (tid < pd.world) {
     volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(pd.peer_flags[pd.rank]) + (size_t)slot * pd.world + tid;
     const long long t0 = clock64();
-    while (*f < epoch) {
+    while (*f != epoch) {
       if (clock64() - t0 > 20000000000LL) {     // ~10 s: a peer never arrived - fail loudly instead of hanging
         printf("vaegan_b200: peer all-reduce timed out (rank %d waiting for rank %d, slot %d, epoch %llu, flag %llu)\n", pd.rank, tid, slot,
                epoch, (unsigned long long)*f);
         __trap();
       }
     }
+    __threadfence_system();
   }
-  __threadfence_system();
   __syncthreads();
   // 4. sum the sub-slots in rank order (identical result on every rank); bypass L1 for peer-written data
   const double* mine = reinterpret_cast<const double*>(pd.peer_data[pd.rank]) + (size_t)slot * pd.world * VG_PEER_MAX_N;
@@ -482,6 +484,12 @@ template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = from_f32<TD>(to_f32(src[i]));
+}
+template <typename T>
+__global__ void scale_kernel(const T* __restrict__ src, const float* __restrict__ scale, long long n, T* __restrict__ dst) {
+  const float sc = *scale;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = from_f32<T>(to_f32(src[i]) * sc);
 }
 // tiled transpose of [c][hw] <-> [hw][c] per image
 template <typename TD>
@@ -764,6 +772,18 @@ extern "C" int vg_nhwc_to_nchw(const void* src, int src_dtype, int n, int c, int
   dim3 grid((unsigned)cdiv(h * w, 32), (unsigned)cdiv(c, 32), (unsigned)n), block(32, 8);
   if (src_dtype == VG_BF16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, c, h * w, dst);
   else nhwc_to_nchw_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)src, c, h * w, dst);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_scale(const void* src, const float* scale, long long n, int dtype, void* dst, vg_stream_t stream) {
+  VG_CHECK_ARG(src && scale && dst && n >= 0, "bad args");
+  VG_CHECK_ARG(dtype == VG_F32 || dtype == VG_BF16, "bad dtype %d", dtype);
+  if (n == 0) return VG_OK;
+  if (dtype == VG_BF16)
+    scale_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, scale, n, (__nv_bfloat16*)dst);
+  else
+    scale_kernel<float><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const float*)src, scale, n, (float*)dst);
   VG_LAUNCHED();
   return VG_OK;
 }

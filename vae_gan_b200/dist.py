@@ -53,16 +53,44 @@ class PeerExchange:
             desc.peer_flags[r] = fptr
         desc.rank, desc.world, desc.n_slots = self.rank, self.world, n_slots
         self.desc = desc
+        # the exchange's OWN epoch: a device counter that only ever grows (one increment per iteration, captured in
+        # the CUDA graph), independent of the Philox step that tests and capture() reset / restore
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        self._closed = False
         dist.barrier(group=pg)
 
     def reset(self):
-        """Called once per training iteration (all ranks walk the same slot sequence)."""
+        """Called once per training iteration (all ranks walk the same slot sequence): next epoch, slot 0."""
         self.slot = 0
+        _lib.call("vg_counter_add", self.epoch.data_ptr(), 1, _lib.stream_ptr())
 
-    def allreduce_(self, vec: torch.Tensor, epoch_tensor: torch.Tensor):
+    def allreduce_(self, vec: torch.Tensor, epoch_tensor: torch.Tensor = None):
         assert vec.dtype == torch.float64 and vec.is_contiguous() and vec.numel() <= MAX_N
         if self.slot >= self.n_slots:
             raise _lib.VgError(f"more than {self.n_slots} SyncBN exchanges in one iteration")
-        _lib.call("vg_peer_allreduce_f64", vec.data_ptr(), vec.numel(), C.byref(self.desc), self.slot, epoch_tensor.data_ptr(),
+        _lib.call("vg_peer_allreduce_f64", vec.data_ptr(), vec.numel(), C.byref(self.desc), self.slot, self.epoch.data_ptr(),
                   _lib.stream_ptr())
         self.slot += 1
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (collective: every rank must have stopped using them)."""
+        if self._closed:
+            return
+        self._closed = True
+        try:
+            torch.cuda.synchronize(self.device)
+            for p in self._opened:
+                _lib.call("vg_peer_close_handle", p)
+            _lib.call("vg_peer_free", self._data)
+            _lib.call("vg_peer_free", self._flags)
+        except Exception:      # interpreter / context teardown: nothing left to release
+            pass
+
+    def __del__(self):
+        # peers may still have our buffers mapped at interpreter exit; only unmap ours, the driver frees the rest
+        if not getattr(self, "_closed", True):
+            try:
+                for p in self._opened:
+                    _lib.call("vg_peer_close_handle", p)
+            except Exception:
+                pass

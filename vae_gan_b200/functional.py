@@ -35,6 +35,7 @@ class _Config:
     sample_offset = 0             # global index of this rank's first sample
     defer_num_batches_tracked = False   # the trainer bumps every BN's counter with ONE foreach kernel per step
     peer = None                   # dist.PeerExchange: NVLink one-shot exchange of the SyncBN sums (else NCCL)
+    trainer_active = False        # inside VaeGanTrainer._iteration: loss backward is called with grad 1 (no rescale kernels)
 
 
 config = _Config()
@@ -105,6 +106,23 @@ def _allreduce_sums(t: torch.Tensor):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=config.process_group)
 
 
+def live_grad_buf(param):
+    """The trainer's flat gradient view for `param` (FlatParams sets `param._vg_grad_buf` and `param.grad` to the SAME
+    storage) - or None when the fused accumulation must not be used: the parameter is driven by stock machinery
+    (e.g. `optimizer.zero_grad()` replaced / dropped `.grad`), in which case the backward returns ordinary gradients
+    and autograd accumulates them.  Evaluated at BACKWARD time."""
+    if param is None:
+        return None
+    buf = getattr(param, "_vg_grad_buf", None)
+    if buf is None:
+        return None
+    owner = getattr(param, "_vg_owner", param)
+    g = owner.grad
+    if g is None or g.data_ptr() != buf.data_ptr():
+        return None
+    return buf
+
+
 # ----------------------------------------------------------------------------------------------
 # tensor helpers
 # ----------------------------------------------------------------------------------------------
@@ -138,7 +156,49 @@ def as_act(t: torch.Tensor, dtype=None) -> torch.Tensor:
     return out
 
 
+class StatsArena:
+    """Zero-initialised fp64 accumulators (BatchNorm sums, loss sums) for ONE training iteration, carved from a
+    single buffer that the trainer clears with ONE memset at the start of the iteration - instead of one
+    memset node per accumulator (~150 per iteration).  Outside a trainer iteration (`active` False) every
+    request falls back to its own zero-filled tensor."""
+
+    CAPACITY = 1 << 19          # doubles (4 MB): ~150 accumulators of <= 2 * 1024 channels (+ the 5C second-order sums)
+
+    def __init__(self):
+        self.buf = None
+        self.pos = 0
+        self.active = False
+        self._lock = threading.Lock()
+
+    def begin(self, device):
+        if self.buf is None or self.buf.device != device:
+            self.buf = torch.empty(self.CAPACITY, dtype=torch.float64, device=device)
+        call("vg_fill_zero", ptr(self.buf), self.buf.numel() * 8, stream_ptr())
+        self.pos = 0
+        self.active = True
+
+    def end(self):
+        self.active = False
+
+    def take(self, n, device):
+        if not self.active or self.buf is None or self.buf.device != device:
+            return None
+        with self._lock:
+            n2 = (n + 1) // 2 * 2                   # keep every slice 16-byte aligned
+            if self.pos + n2 > self.buf.numel():
+                return None
+            t = self.buf[self.pos:self.pos + n]
+            self.pos += n2
+        return t
+
+
+arena = StatsArena()
+
+
 def zeros_f64(n, device):
+    t = arena.take(n, device)
+    if t is not None:
+        return t
     t = torch.empty(n, dtype=torch.float64, device=device)
     call("vg_fill_zero", ptr(t), t.numel() * 8, stream_ptr())
     return t
@@ -174,8 +234,31 @@ def to_act(x, dtype=None):
     return ToActFn.apply(x, dtype)
 
 
+class FromActFn(Function):
+    """Module-boundary conversion back to what the reference modules return: a CONTIGUOUS NCHW fp32 tensor (so
+    reference-style code such as `out.view(out.size(0), -1)` works on it)."""
+
+    @staticmethod
+    def forward(ctx, y):
+        _lib.ensure_device(y.device)
+        n, c, h, w = y.shape
+        ctx.in_dtype = y.dtype
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=y.device)
+        call("vg_nhwc_to_nchw", ptr(y), vg_dtype(y.dtype), n, c, h, w, ptr(out), stream_ptr())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if torch.is_grad_enabled():          # create_graph=True (gradient penalty): stay differentiable
+            return ToActFn.apply(g, ctx.in_dtype)
+        return as_act(g, ctx.in_dtype)
+
+
 def from_act(y, dtype=torch.float32):
-    """Internal activation -> user-facing tensor (same logical NCHW shape, fp32)."""
+    """Internal activation -> user-facing tensor: contiguous NCHW fp32, like the reference modules' outputs.
+    (A 1-channel tensor is bit-identical in NCHW and NHWC, so only the dtype changes there.)"""
+    if y.shape[1] > 1 and is_act(y) and not y.is_contiguous() and dtype == torch.float32:
+        return FromActFn.apply(y)
     if y.dtype == dtype:
         return y
     return ToActFn.apply(y, dtype)
@@ -250,8 +333,7 @@ class ConvFn(Function):
         ctx.has_bias = bias is not None
         ctx.has_sn = sn_u is not None
         ctx.wshape = tuple(weight.shape)
-        ctx.wbuf = getattr(weight, "_vg_grad_buf", None)     # trainer's flat gradient view (fused accumulation)
-        ctx.bbuf = getattr(bias, "_vg_grad_buf", None) if bias is not None else None
+        ctx.weight_ref, ctx.bias_ref = weight, bias          # live_grad_buf() is evaluated at backward time
         ctx.save_for_backward(x, pack_kn, pack_nk, w if ctx.has_sn else None, sigma, u_saved, v_saved, weight)
         return y
 
@@ -276,16 +358,18 @@ class ConvFn(Function):
             dx = empty_act(d.n, d.c_in, d.h_in, d.w_in, x.dtype, x.device)
             call("vg_conv_dgrad", C.byref(d), ptr(dy), ptr(pack_kn), ptr(pack_nk), ptr(dx), s)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            fused = ctx.wbuf is not None
+            wbuf = live_grad_buf(ctx.weight_ref)          # trainer's flat gradient view (fused accumulation) or None
+            bbuf = live_grad_buf(ctx.bias_ref)
+            fused = wbuf is not None
             direct = fused and not ctx.has_sn
-            dwh = ctx.wbuf if direct else zeros_f32(ctx.wshape, x.device)
+            dwh = wbuf if direct else zeros_f32(ctx.wshape, x.device)
             if ctx.has_bias:
-                db = ctx.bbuf if ctx.bbuf is not None else zeros_f32((d.c_out,), x.device)
+                db = bbuf if bbuf is not None else zeros_f32((d.c_out,), x.device)
             ws = torch.empty(dwh.numel(), dtype=torch.float32, device=x.device) if x.dtype == torch.bfloat16 else None
             call("vg_conv_wgrad", C.byref(d), ptr(x), ptr(dy), ptr(dwh), ptr(db), ptr(ws), s)
             if ctx.has_sn:
                 rows, cols = ctx.wshape[0], dwh.numel() // ctx.wshape[0]
-                dw = ctx.wbuf if fused else zeros_f32(ctx.wshape, x.device)
+                dw = wbuf if fused else zeros_f32(ctx.wshape, x.device)
                 ws = torch.empty(4, dtype=torch.float32, device=x.device)
                 call("vg_spectral_norm_backward", ptr(dwh), ptr(w), ptr(u), ptr(v), ptr(sigma), rows, cols,
                      ptr(dw), ptr(ws), s)
@@ -293,7 +377,7 @@ class ConvFn(Function):
                 dw = dwh
             if fused:
                 dw = None
-            if ctx.bbuf is not None:
+            if bbuf is not None:
                 db = None
         return dx, dw, db, None, None, None, None, None, None, None
 
@@ -315,18 +399,39 @@ def _bn_desc(x, slope=1.0, drop_p=0.0, offset=0, training=True):
     return d
 
 
+def _bn_channel(x, gamma, beta, running_mean, running_var, sums, training, mr_out):
+    """VgBnChannel for the fused kernels: batch statistics (`sums`, already all-reduced under SyncBN) in training,
+    running statistics in eval.  The returned struct holds raw pointers - the caller keeps the tensors alive."""
+    n, c, h, w = x.shape
+    use_batch = training or running_mean is None
+    count = float(n * h * w * (_world() if training else 1))
+    return _lib.VgBnChannel(ptr(gamma), ptr(beta), None, ptr(sums) if use_batch else None, count,
+                            ptr(running_mean), ptr(running_var), ptr(mr_out), BN_EPS, BN_MOMENTUM)
+
+
+def _bn_prepare_sums(x, sums, training, running_mean):
+    """Training: make sure the per-channel sums of x exist (the producer may have accumulated them already) and are
+    global (SyncBN all-reduce).  Eval: nothing."""
+    if not (training or running_mean is None):
+        return None
+    if sums is None:
+        sums = zeros_f64(2 * x.shape[1], x.device)
+        d = _bn_desc(x)
+        call("vg_bn_stats", ptr(x), C.byref(d), ptr(sums), stream_ptr())
+    if training:
+        _allreduce_sums(sums)
+    return sums
+
+
 def bn_batch_stats(x, sums, running_mean, running_var, training, momentum=BN_MOMENTUM, eps=BN_EPS):
-    """Per-channel (mean, rstd) of `x` (float[2C]) - batch statistics (+ SyncBN all-reduce, +
-    running-stat update) in training, running statistics in eval."""
+    """Per-channel (mean, rstd) of `x` (float[2C]) as a stand-alone step - batch statistics (+ SyncBN all-reduce, +
+    running-stat update) in training, running statistics in eval.  The hot path folds this into the consuming
+    kernel (vg_bn_act_forward_fused / vg_bn_add_forward_fused); kept for callers that need the numbers alone."""
     n, c, h, w = x.shape
     s = stream_ptr()
     mr = torch.empty(2 * c, dtype=torch.float32, device=x.device)
     if training:
-        if sums is None:
-            sums = zeros_f64(2 * c, x.device)
-            d = _bn_desc(x)
-            call("vg_bn_stats", ptr(x), C.byref(d), ptr(sums), s)
-        _allreduce_sums(sums)
+        sums = _bn_prepare_sums(x, sums, True, running_mean)
         count = float(n * h * w * _world())
         call("vg_bn_finalize", ptr(sums), count, c, eps, momentum, ptr(running_mean), ptr(running_var), ptr(mr), s)
     else:
@@ -334,33 +439,45 @@ def bn_batch_stats(x, sums, running_mean, running_var, training, momentum=BN_MOM
     return mr
 
 
+def _bn_act_forward(x, g, b, running_mean, running_var, sums, d, training):
+    """finalize (or eval statistics) + BatchNorm + LeakyReLU + dropout in ONE launch; returns (y, mean_rstd)."""
+    c = x.shape[1]
+    sums = _bn_prepare_sums(x, sums, training, running_mean)
+    mr = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+    ch = _bn_channel(x, g, b, running_mean, running_var, sums, training, mr)
+    y = torch.empty_like(x)
+    call("vg_bn_act_forward_fused", ptr(x), C.byref(ch), C.byref(d), ptr(y), stream_ptr())
+    return y, mr
+
+
 def _bn_backward(dy, x, mr, gamma, beta, d, out_colscale=None, addend=None, need_dx=True, need_params=True,
                  gbuf=None, bbuf=None):
     """Shared BN(+act+dropout) backward: returns dx, dgamma, dbeta (None when accumulated into the
-    trainer's flat gradient views gbuf / bbuf)."""
+    trainer's flat gradient views gbuf / bbuf).  Two launches: the reduction, then the apply - which also adds the
+    parameter gradients (block 0) and the shortcut gradient `addend` of a residual fork."""
     s = stream_ptr()
     c = d.c
     sums = zeros_f64(2 * c, x.device)
     call("vg_bn_act_backward_reduce", ptr(dy), ptr(x), ptr(mr), ptr(gamma), ptr(beta), C.byref(d), ptr(sums), s)
     if d.training:
         _allreduce_sums(sums)          # SyncBN: global sums enter dx; param grads get reduced again
+    fused = gbuf is not None and bbuf is not None
+    dgamma = dbeta = None
+    if need_params:
+        dgamma = gbuf if fused else zeros_f32((c,), x.device)
+        dbeta = bbuf if fused else zeros_f32((c,), x.device)
+    # the parameter gradients are all-reduced (summed) later with the flat gradient buffer, so each rank
+    # contributes 1/world of the already-global sums
+    pscale = 1.0 / _world() if (d.training and _world() > 1) else 1.0
     dx = None
     if need_dx:
         dx = torch.empty_like(x)
         count = float(d.rows * _world())
-        call("vg_bn_act_backward_apply", ptr(dy), ptr(x), ptr(mr), ptr(gamma), ptr(beta), ptr(sums), count,
-             C.byref(d), ptr(out_colscale), ptr(addend), ptr(dx), s)
-    if not need_params:
-        return dx, None, None
-    fused = gbuf is not None and bbuf is not None
-    dgamma = gbuf if fused else zeros_f32((c,), x.device)
-    dbeta = bbuf if fused else zeros_f32((c,), x.device)
-    if d.training and _world() > 1:
-        # the parameter gradients are all-reduced (summed) later with the flat gradient buffer,
-        # so each rank must contribute 1/world of the already-global sums
-        sums = sums / _world()
-    call("vg_bn_param_grads", ptr(sums), c, ptr(dgamma), ptr(dbeta), s)
-    if fused:
+        call("vg_bn_act_backward_apply_fused", ptr(dy), ptr(x), ptr(mr), ptr(gamma), ptr(beta), ptr(sums), count,
+             C.byref(d), ptr(out_colscale), ptr(addend), ptr(dx), ptr(dgamma), ptr(dbeta), pscale, s)
+    elif need_params:
+        call("vg_bn_param_grads_scaled", ptr(sums), c, pscale, ptr(dgamma), ptr(dbeta), s)
+    if fused or not need_params:
         return dx, None, None
     return dx, dgamma, dbeta
 
@@ -375,13 +492,9 @@ class BnActFn(Function):
         _lib.ensure_device(x.device)
         assert is_act(x)
         g, b = gamma.detach(), beta.detach()
-        mr = bn_batch_stats(x, sums, running_mean, running_var, training)
         d = _bn_desc(x, slope, drop_p if training else 0.0, offset, training)
-        y = torch.empty_like(x)
-        call("vg_bn_act_forward", ptr(x), ptr(mr), ptr(g), ptr(b), C.byref(d), ptr(y), stream_ptr())
+        y, mr = _bn_act_forward(x, g, b, running_mean, running_var, sums, d, training)
         ctx.d = d
-        ctx.gbuf = getattr(gamma, "_vg_grad_buf", None)
-        ctx.bbuf = getattr(beta, "_vg_grad_buf", None)
         ctx.save_for_backward(x, mr, g, b, out_colscale, gamma, beta)
         return y
 
@@ -398,7 +511,7 @@ class BnActFn(Function):
         dy = as_act(dy, x.dtype)
         dx, dgamma, dbeta = _bn_backward(dy, x, mr, g, b, ctx.d, out_colscale=ocs,
                                          need_dx=ctx.needs_input_grad[0], need_params=ctx.needs_input_grad[1],
-                                         gbuf=ctx.gbuf, bbuf=ctx.bbuf)
+                                         gbuf=live_grad_buf(gamma), bbuf=live_grad_buf(beta))
         return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
@@ -413,13 +526,9 @@ class BnActForkFn(Function):
         _lib.ensure_device(x.device)
         assert is_act(x)
         g, b = gamma.detach(), beta.detach()
-        mr = bn_batch_stats(x, sums, running_mean, running_var, training)
         d = _bn_desc(x, slope, drop_p if training else 0.0, offset, training)
-        y = torch.empty_like(x)
-        call("vg_bn_act_forward", ptr(x), ptr(mr), ptr(g), ptr(b), C.byref(d), ptr(y), stream_ptr())
+        y, mr = _bn_act_forward(x, g, b, running_mean, running_var, sums, d, training)
         ctx.d = d
-        ctx.gbuf = getattr(gamma, "_vg_grad_buf", None)
-        ctx.bbuf = getattr(beta, "_vg_grad_buf", None)
         ctx.save_for_backward(x, mr, g, b, gamma, beta)
         return y, x.view_as(x)
 
@@ -440,7 +549,8 @@ class BnActForkFn(Function):
         dy = as_act(dy, x.dtype)
         addend = as_act(dpass, x.dtype) if dpass is not None else None
         dx, dgamma, dbeta = _bn_backward(dy, x, mr, g, b, ctx.d, addend=addend, need_dx=ctx.needs_input_grad[0],
-                                         need_params=ctx.needs_input_grad[1], gbuf=ctx.gbuf, bbuf=ctx.bbuf)
+                                         need_params=ctx.needs_input_grad[1], gbuf=live_grad_buf(gamma),
+                                         bbuf=live_grad_buf(beta))
         return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
@@ -473,21 +583,26 @@ class BnAddFn(Function):
         _lib.ensure_device(a.device)
         assert is_act(a) and is_act(b) and a.shape == b.shape and a.dtype == b.dtype
         mra = mrb = None
+        cha = chb = None
         ga_p, ba_p, gb_p, bb_p = ga, ba, gb, bb
+        c = a.shape[1]
         if ga is not None:
             ga, ba = ga.detach(), ba.detach()
-            mra = bn_batch_stats(a, sums_a, rma, rva, training)
+            sums_a = _bn_prepare_sums(a, sums_a, training, rma)
+            mra = torch.empty(2 * c, dtype=torch.float32, device=a.device)
+            cha = _bn_channel(a, ga, ba, rma, rva, sums_a, training, mra)
         if gb is not None:
             gb, bb = gb.detach(), bb.detach()
-            mrb = bn_batch_stats(b, sums_b, rmb, rvb, training)
+            sums_b = _bn_prepare_sums(b, sums_b, training, rmb)
+            mrb = torch.empty(2 * c, dtype=torch.float32, device=a.device)
+            chb = _bn_channel(b, gb, bb, rmb, rvb, sums_b, training, mrb)
         d = _bn_desc(a, slope, 0.0, 0, training)
         out = torch.empty_like(a)
-        call("vg_bn_add_forward", ptr(a), ptr(mra), ptr(ga), ptr(ba), ptr(b), ptr(mrb), ptr(gb), ptr(bb),
-             C.byref(d), ptr(out), ptr(stats_out), stream_ptr())
+        # both finalizes (running-stat updates included) + affine + add + LeakyReLU + next block's statistics: one launch
+        call("vg_bn_add_forward_fused", ptr(a), C.byref(cha) if cha is not None else None, ptr(b),
+             C.byref(chb) if chb is not None else None, C.byref(d), ptr(out), ptr(stats_out), stream_ptr())
         ctx.d = d
         ctx.slope = slope
-        ctx.bufs_a = (getattr(ga_p, "_vg_grad_buf", None), getattr(ba_p, "_vg_grad_buf", None))
-        ctx.bufs_b = (getattr(gb_p, "_vg_grad_buf", None), getattr(bb_p, "_vg_grad_buf", None))
         ctx.save_for_backward(a if mra is not None else None, mra, ga, ba, b if mrb is not None else None, mrb, gb, bb,
                               out if slope != 1.0 else None, ga_p, ba_p, gb_p, bb_p)
         return out
@@ -521,12 +636,14 @@ class BnAddFn(Function):
         da = db = dga = dba = dgb = dbb = None
         if mra is not None:
             da, dga, dba = _bn_backward(dpre, a, mra, ga, ba, d, need_dx=ctx.needs_input_grad[0],
-                                        need_params=ctx.needs_input_grad[2], gbuf=ctx.bufs_a[0], bbuf=ctx.bufs_a[1])
+                                        need_params=ctx.needs_input_grad[2], gbuf=live_grad_buf(ga_p),
+                                        bbuf=live_grad_buf(ba_p))
         elif ctx.needs_input_grad[0]:
             da = dpre
         if mrb is not None:
             db, dgb, dbb = _bn_backward(dpre, b, mrb, gb, bb, d, need_dx=ctx.needs_input_grad[1],
-                                        need_params=ctx.needs_input_grad[7], gbuf=ctx.bufs_b[0], bbuf=ctx.bufs_b[1])
+                                        need_params=ctx.needs_input_grad[7], gbuf=live_grad_buf(gb_p),
+                                        bbuf=live_grad_buf(bb_p))
         elif ctx.needs_input_grad[1]:
             db = dpre
         return da, db, dga, dba, None, None, None, dgb, dbb, None, None, None, None, None, None
@@ -655,8 +772,7 @@ class LinearFn(Function):
         b = bias.detach() if bias is not None else None
         call("vg_linear_forward", ptr(x), ptr(w), ptr(b), m, n, k, vg_dtype(wdtype), float(slope), ptr(y), s)
         ctx.dims, ctx.slope, ctx.wdtype, ctx.has_bias = (m, n, k), slope, wdtype, bias is not None
-        ctx.wbuf = getattr(weight, "_vg_grad_buf", None)
-        ctx.bbuf = getattr(bias, "_vg_grad_buf", None) if bias is not None else None
+        ctx.weight_ref, ctx.bias_ref = weight, bias
         ctx.save_for_backward(x, w, y if slope != 1.0 else None, weight)
         return y
 
@@ -681,9 +797,10 @@ class LinearFn(Function):
             dx = torch.empty((m, k), dtype=torch.float32, device=dy.device)
             call("vg_linear_dgrad", ptr(dy), ptr(w), m, n, k, vg_dtype(ctx.wdtype), ptr(dx), s)
         if ctx.needs_input_grad[1]:
-            fused = ctx.wbuf is not None and (not ctx.has_bias or ctx.bbuf is not None)
-            dw = ctx.wbuf if fused else zeros_f32((n, k), dy.device)
-            db = (ctx.bbuf if fused else zeros_f32((n,), dy.device)) if ctx.has_bias else None
+            wbuf, bbuf = live_grad_buf(ctx.weight_ref), live_grad_buf(ctx.bias_ref)
+            fused = wbuf is not None and (not ctx.has_bias or bbuf is not None)
+            dw = wbuf if fused else zeros_f32((n, k), dy.device)
+            db = (bbuf if fused else zeros_f32((n,), dy.device)) if ctx.has_bias else None
             call("vg_linear_wgrad", ptr(x), ptr(dy), m, n, k, vg_dtype(ctx.wdtype), ptr(dw), ptr(db), s)
             if fused:
                 dw = db = None
@@ -727,6 +844,7 @@ def linear(x, weight, bias, slope, wdtype):
         gb = getattr(weight, "_vg_grad_buf", None)
         if gb is not None:
             wv._vg_grad_buf = gb.view(n, k, 1, 1)      # wgrad accumulates straight into the flat buffer
+            wv._vg_owner = weight                      # ... while weight.grad still IS that buffer (live_grad_buf)
         y = conv(xa, wv, bias, geom=ConvGeom(1, 1, 0, False), out_dtype=torch.float32)
         if slope != 1.0:
             y = LeakyReluFn.apply(y, slope)
@@ -771,6 +889,13 @@ class ReparamFn(Function):
         return d_mu, d_lv, None, None, None
 
 
+def _scaled(t, scale):
+    """t * scale with a DEVICE scalar `scale` (no host sync, CUDA-graph safe) on this library's kernels."""
+    out = torch.empty_like(t)
+    call("vg_scale", ptr(t), ptr(scale.reshape(1).contiguous()), t.numel(), vg_dtype(t.dtype), ptr(out), stream_ptr())
+    return out
+
+
 class GeneratorLossFn(Function):
     """One fused kernel for the generator objective AND its gradients (README.md:816-831):
     adv (BCE-with-logits vs 1, or -mean D) + w_recon*(L1+MSE) + w_kl*KL.  Returns
@@ -795,15 +920,24 @@ class GeneratorLossFn(Function):
         call("vg_generator_loss", ptr(xhat), ptr(xf), ptr(mu), ptr(lv), ptr(lg), C.byref(d), ptr(d_xhat), ptr(d_mu),
              ptr(d_lv), ptr(d_log), ptr(losses), stream_ptr())
         ctx.save_for_backward(d_xhat, d_mu, d_lv, d_log)
+        ctx.unit_grad = config.trainer_active
         out = losses.to(torch.float32)
-        return out[0], out[1], out[2], out[3]
+        total, recon, kl, adv = out[0], out[1], out[2], out[3]
+        # only `total` carries gradients; backprop from the reported parts raises instead of silently dropping them
+        ctx.mark_non_differentiable(recon, kl, adv)
+        return total, recon, kl, adv
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g_total, g_recon, g_kl, g_adv):
         d_xhat, d_mu, d_lv, d_log = ctx.saved_tensors
-        # the trainer calls backward with grad 1 on `total`; keep exactly that contract
-        return d_xhat, None, d_mu, d_lv, d_log, None, None, None, None
+        if ctx.unit_grad:
+            # VaeGanTrainer calls total.backward() (incoming gradient exactly 1): no rescale kernels in the hot loop
+            return d_xhat, None, d_mu, d_lv, d_log, None, None, None, None
+        # general use (loss / k, GradScaler, 0.5 * loss, ...): the stored gradients scale with the incoming one
+        sc = g_total.to(torch.float32)
+        return (_scaled(d_xhat, sc), None, _scaled(d_mu, sc), _scaled(d_lv, sc),
+                _scaled(d_log, sc) if d_log is not None else None, None, None, None, None)
 
 
 class DiscriminatorLossFn(Function):
@@ -819,14 +953,20 @@ class DiscriminatorLossFn(Function):
         call("vg_discriminator_loss", ptr(d_real.detach().contiguous()), ptr(d_fake.detach().contiguous()), n,
              n * _world(), int(adv_mode), ptr(g_real), ptr(g_fake), ptr(losses), stream_ptr())
         ctx.save_for_backward(g_real, g_fake)
+        ctx.unit_grad = config.trainer_active
         out = losses.to(torch.float32)
-        return out[0], out[1], out[2]
+        total, lr, lf = out[0], out[1], out[2]
+        ctx.mark_non_differentiable(lr, lf)
+        return total, lr, lf
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g_total, g_r, g_f):
         g_real, g_fake = ctx.saved_tensors
-        return g_real, g_fake, None
+        if ctx.unit_grad:
+            return g_real, g_fake, None
+        sc = g_total.to(torch.float32)
+        return _scaled(g_real, sc), _scaled(g_fake, sc), None
 
 
 # ----------------------------------------------------------------------------------------------

@@ -352,14 +352,14 @@ class SpatialVAECodeProcessor(nn.Module):
                     eps = VF.philox_normal(tuple(mu.shape), mu.device)
             z, lv = VF.ReparamFn.apply(mu, lv_raw, eps, bool(self.is_training), x.dtype)
             if outer:
-                z = VF.from_act(z)
+                z, mu, lv = VF.from_act(z), VF.from_act(mu), VF.from_act(lv)
             return z, mu, lv
 
     def encode(self, x):
         with _scope() as outer:
             x = VF.to_act(x)
             mu = VF.conv(x, self.mu.weight, self.mu.bias, geom=_MODE_GEOM["level"], out_dtype=torch.float32)
-            return mu if outer else VF.to_act(mu)
+            return VF.from_act(mu) if outer else mu      # fp32 (the latent mean is not rounded to the compute dtype)
 
     def decode(self, x):
         return x
@@ -389,14 +389,17 @@ class UnsupervisedGeneratorNetwork(nn.Module):
             x = self.decoder(x)
             if outer:
                 x = VF.from_act(x)
+                if self.is_vae:
+                    mu, log_var = VF.from_act(mu), VF.from_act(log_var)
             if self.is_vae:
                 return x, mu, log_var
             return x
 
     def encode(self, x):
-        with _scope():
+        with _scope() as outer:
             x = self.encoder(x)
-            return self.code_processor.encode(x)
+            mu = self.code_processor.encode(x)
+            return VF.from_act(mu) if outer else mu
 
     def decode(self, x):
         with _scope() as outer:

@@ -63,9 +63,15 @@ class VaeGanTrainer:
     def __init__(self, generator: nn.Module, discriminator: nn.Module, *, loss_mode: str = "bce",
                  optimizer: str = "adam", lr: float = 3e-4, weights=(1.0, 10.0, 0.1), clip_value: float = 0.01,
                  weight_decay: Optional[float] = None, betas=(0.9, 0.999), process_group=None,
-                 local_batch: Optional[int] = None, peer_syncbn: Optional[bool] = None, lambda_gp: float = 10.0):
+                 local_batch: Optional[int] = None, peer_syncbn: Optional[bool] = None, lambda_gp: float = 10.0,
+                 n_critics: int = 1):
         assert loss_mode in ("bce", "wgan", "wgan_gp")
         assert optimizer in ("adam", "rmsprop")
+        assert n_critics >= 1
+        # README.md:812 `if i % n_critics == 0:` - the generator is updated on every n_critics-th iteration (the
+        # first one included); its forward runs every iteration because the D step needs the fakes (README.md:789)
+        self.n_critics = int(n_critics)
+        self.iteration = 0
         self.G, self.D = generator, discriminator
         self.loss_mode, self.opt_kind, self.lr, self.weights = loss_mode, optimizer, lr, tuple(weights)
         self.clip = clip_value if loss_mode in ("wgan", "wgan_gp") else 0.0
@@ -83,6 +89,7 @@ class VaeGanTrainer:
         self.opt_step = torch.zeros(1, dtype=torch.int64, device=self.device)   # device-side Adam t
         self.losses: Dict[str, torch.Tensor] = {}
         self.graph = None
+        self.graph_d_only = None      # n_critics > 1: the iteration without the generator update
         self.static_real = None
         self.local_batch = local_batch
         self.peer = None
@@ -120,7 +127,7 @@ class VaeGanTrainer:
         if self.world > 1:
             dist.all_reduce(flat.g, op=dist.ReduceOp.SUM, group=self.pg)
 
-    def _step_impl(self, real: torch.Tensor):
+    def _step_impl(self, real: torch.Tensor, g_step: bool = True):
         dev = self.device
         if self.world > 1:
             VF.config.sample_offset = self.rank * real.shape[0]
@@ -131,18 +138,22 @@ class VaeGanTrainer:
         if self.G.training and self._nbt_g:
             torch._foreach_add_(self._nbt_g, 1)
         if self.D.training and self._nbt_d:
-            torch._foreach_add_(self._nbt_d, 4 if self.loss_mode == "wgan_gp" else 3)
+            torch._foreach_add_(self._nbt_d, (3 if self.loss_mode == "wgan_gp" else 2) + (1 if g_step else 0))
         VF.config.defer_num_batches_tracked = True
+        VF.config.trainer_active = True
         VF.config.peer = self.peer
         if self.peer is not None:
             self.peer.reset()
+        VF.arena.begin(dev)           # ONE memset for every fp64 accumulator of the iteration
         try:
-            return self._iteration(real, adv_mode)
+            return self._iteration(real, adv_mode, g_step)
         finally:
+            VF.arena.end()
             VF.config.defer_num_batches_tracked = False
+            VF.config.trainer_active = False
             VF.config.peer = None
 
-    def _iteration(self, real, adv_mode):
+    def _iteration(self, real, adv_mode, g_step=True):
         with M._scope():
             with M._scope():          # depth >= 1 everywhere: modules hand over internal activations
                 # ---- generator forward (graph kept for the G step) ----
@@ -167,47 +178,100 @@ class VaeGanTrainer:
                 d_total.backward()
                 self._allreduce(self.fd)
                 self._opt(self.fd, self.clip)
-                # ---- generator step ----
-                self.fd.set_requires_grad(False)
-                self.fg.zero_grad()
-                d_gen = self.D(gen)
-                g_total, recon, kl, adv = VF.GeneratorLossFn.apply(gen, real, mu, log_var, d_gen, adv_mode,
-                                                                   self.weights[0], self.weights[1], self.weights[2])
-                g_total.backward()
-                self._allreduce(self.fg)
-                self._opt(self.fg, 0.0)
-                self.fd.set_requires_grad(True)
-        self.losses = dict(d_loss=d_total.detach(), real_loss=d_rl.detach(), fake_loss=d_fl.detach(),
-                           g_loss=g_total.detach(), recon=recon.detach(), kl=kl.detach(), adv=adv.detach())
+                # ---- generator step (README.md:812: every n_critics-th iteration) ----
+                d_gen = None
+                if g_step:
+                    self.fd.set_requires_grad(False)
+                    self.fg.zero_grad()
+                    d_gen = self.D(gen)
+                    g_total, recon, kl, adv = VF.GeneratorLossFn.apply(gen, real, mu, log_var, d_gen, adv_mode,
+                                                                       self.weights[0], self.weights[1], self.weights[2])
+                    g_total.backward()
+                    self._allreduce(self.fg)
+                    self._opt(self.fg, 0.0)
+                    self.fd.set_requires_grad(True)
+        self.losses = dict(d_loss=d_total.detach(), real_loss=d_rl.detach(), fake_loss=d_fl.detach())
+        if g_step:
+            self.losses.update(g_loss=g_total.detach(), recon=recon.detach(), kl=kl.detach(), adv=adv.detach())
+            self._last_g_losses = {k: self.losses[k] for k in ("g_loss", "recon", "kl", "adv")}
+        elif getattr(self, "_last_g_losses", None) is not None:
+            # like the notebook's print (README.md:837), a skipped generator step reports the previous values
+            self.losses.update(self._last_g_losses)
         if gp_term is not None:
             self.losses["gp"] = (gp_term / self.world).detach()
         self.last = dict(gen=gen.detach(), mu=mu.detach(), log_var=log_var.detach(), d_real=d_real.detach(),
-                         d_fake=d_fake.detach(), d_gen=d_gen.detach())
+                         d_fake=d_fake.detach())
+        if d_gen is not None:
+            self.last["d_gen"] = d_gen.detach()
         return self.losses
 
     # ------------------------------------------------------------------------------------------
+    def _state_snapshot(self):
+        """Everything one iteration mutates: parameters and optimizer state (flat buffers), Adam's step counter, the
+        BatchNorm buffers, spectral-norm u / v, the Philox step counter."""
+        snap = dict(flat=[(f, f.p.clone(), f.m.clone(), f.v.clone()) for f in (self.fg, self.fd)],
+                    opt_step=self.opt_step.clone(), rng=VF.rng.step_tensor(self.device).clone(),
+                    bufs=[(b, b.clone()) for net in (self.G, self.D) for b in net.buffers()],
+                    iteration=self.iteration, last_g=getattr(self, "_last_g_losses", None))
+        return snap
+
+    def _state_restore(self, snap):
+        with torch.no_grad():
+            for f, p, m, v in snap["flat"]:
+                f.p.copy_(p); f.m.copy_(m); f.v.copy_(v)
+            self.opt_step.copy_(snap["opt_step"])
+            VF.rng.step_tensor(self.device).copy_(snap["rng"])
+            for b, saved in snap["bufs"]:
+                b.copy_(saved)
+        self.iteration = snap["iteration"]
+        self._last_g_losses = snap["last_g"]
+
     def capture(self, real_example: torch.Tensor, warmup: int = 3):
-        """Capture the whole iteration (fwd + bwd + collectives + optimizers) in one CUDA graph."""
+        """Capture the whole iteration (fwd + bwd + collectives + optimizers) in one CUDA graph (two when
+        n_critics > 1: with and without the generator update).
+
+        The warm-up iterations and the capture pass itself are NOT training steps: parameters, optimizer state,
+        Adam's step counter, BatchNorm running statistics / num_batches_tracked, spectral-norm u / v and the
+        Philox step are restored afterwards, so a graph-mode run starts from exactly the state an eager run
+        starts from (capture does not execute kernels, but the warm-up does)."""
         self.static_real = real_example.clone()
+        snap = self._state_snapshot()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self._step_impl(self.static_real)
+                if self.n_critics > 1:
+                    self._step_impl(self.static_real, g_step=False)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._step_impl(self.static_real)
+        self._losses_full = self.losses
+        if self.n_critics > 1:
+            self.graph_d_only = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_d_only, pool=self.graph.pool()):
+                self._step_impl(self.static_real, g_step=False)
+            self._losses_d_only = self.losses
+        self._state_restore(snap)
+        torch.cuda.synchronize(self.device)
         return self
 
     def step(self, real: torch.Tensor):
+        g_step = (self.iteration % self.n_critics) == 0
+        self.iteration += 1
         if self.graph is not None:
             if real is not self.static_real:
                 self.static_real.copy_(real, non_blocking=True)
-            self.graph.replay()
+            if g_step:
+                self.graph.replay()
+                self.losses = self._losses_full
+            else:
+                self.graph_d_only.replay()
+                self.losses = self._losses_d_only
             return self.losses
-        return self._step_impl(real)
+        return self._step_impl(real, g_step)
 
     def read_losses(self) -> Dict[str, float]:
         """One device->host read of the last step's scalars."""
