@@ -72,6 +72,19 @@ typedef struct {
 int vg_conv_pack_weights(const VgConvDesc* d, const float* w, const float* sigma,
                          void* pack_kn, void* pack_nk, vg_stream_t stream);
 
+/* The same re-layout for EVERY weight of a network in one launch (no sigma: with cached packs the spectral
+ * norm is applied in the convolution epilogue, vg_conv_forward_scaled).  `items` is a HOST array; n0, n1 are the
+ * first two dims of the torch weight ([c_out][c_in] for Conv2d / Linear, [c_in][c_out] for ConvTranspose2d),
+ * taps = kh*kw.  A pack stays valid until the optimizer changes the weight. */
+#define VG_PACK_MAX 32
+typedef struct {
+  const float* w;
+  void* pack_kn;
+  void* pack_nk;
+  int n0, n1, taps, transposed;
+} VgPackItem;
+int vg_conv_pack_weights_batched(const VgPackItem* items, int n_items, int dtype, vg_stream_t stream);
+
 /* y = conv(x) [+ bias] [* colscale[n][c_out]]  (colscale = Dropout2d keep/(1-p), README.md:413).
  * stats (nullable): double[2*c_out], accumulates per-channel sum(y) and sum(y^2) of the
  * values written, for the BatchNorm that follows (README.md:192).  Must be zeroed by caller. */
@@ -81,6 +94,14 @@ int vg_conv_forward(const VgConvDesc* d, const void* x, const void* pack_kn, con
 /* dx = conv^T(dy): gradient w.r.t. the input. */
 int vg_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pack_kn, const void* pack_nk,
                   void* dx, vg_stream_t stream);
+/* The same two with the spectral norm (README.md:378,383,387: weight = weight_orig / sigma) applied in the
+ * epilogue instead of in the pack: y = conv(x, W) / sigma[g] (+ bias) (* colscale), dx = conv^T(dy, W) / sigma[g],
+ * g = sample / sigma_group_n (sigma_group_n = 0: one sigma for the whole batch).  sigma NULL = plain call. */
+int vg_conv_forward_scaled(const VgConvDesc* d, const void* x, const void* pack_kn, const void* pack_nk,
+                           const float* bias, const float* colscale, const float* sigma, int sigma_group_n,
+                           void* y, double* stats, vg_stream_t stream);
+int vg_conv_dgrad_scaled(const VgConvDesc* d, const void* dy, const void* pack_kn, const void* pack_nk,
+                         const float* sigma, int sigma_group_n, void* dx, vg_stream_t stream);
 /* dw += x (*) dy in torch's weight layout, fp32 (caller zeroes dw for a fresh gradient);
  * dbias (nullable) += per-channel sum of dy.
  * workspace (nullable): float[kh*kw*c_in*c_out] scratch.  When given, the tensor-core kernel
@@ -239,6 +260,22 @@ int vg_linear_wgrad(const void* x, const void* dy, int m, int n, int k, int dtyp
 int vg_spectral_norm_sigma(const float* w_orig, int rows, int cols, float* u, float* v,
                            int training, float eps, float* sigma, float* workspace,
                            vg_stream_t stream);
+/* The power iteration of EVERY spectral-normed weight of a network in three launches (+ one memset).  `items`
+ * is a HOST array.  u, v: the module buffers (updated in place in training, like the hook does); u_out, v_out
+ * (nullable): the copies of the post-iteration vectors that this forward's backward needs (later forwards of the
+ * same iteration move the buffers on); sigma: device scalar per item.  workspace: sum(rows + cols) floats. */
+#define VG_SN_MAX 16
+typedef struct {
+  const float* w;
+  float* u;
+  float* v;
+  float* u_out;
+  float* v_out;
+  float* sigma;
+  int rows, cols;
+} VgSnItem;
+int vg_spectral_norm_sigma_batched(const VgSnItem* items, int n_items, int training, float eps,
+                                   float* workspace, size_t workspace_floats, vg_stream_t stream);
 /* dw_orig += (dw_hat - <dw_hat, w_orig/sigma> u v^T) / sigma ; workspace: float[1] (callers may pass more) */
 int vg_spectral_norm_backward(const float* dw_hat, const float* w_orig, const float* u,
                               const float* v, const float* sigma, int rows, int cols,
@@ -327,6 +364,15 @@ int vg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long 
 int vg_nchw_to_nhwc(const float* src, int n, int c, int h, int w, int dst_dtype, void* dst, vg_stream_t stream);
 int vg_nhwc_to_nchw(const void* src, int src_dtype, int n, int c, int h, int w, float* dst, vg_stream_t stream);
 int vg_fill_zero(void* p, size_t bytes, vg_stream_t stream);
+/* ---- input pipeline (README.md:79-90 NiftyDataset.__getitem__, :785 imgs.type(Tensor)) -------------------
+ * Per-image min-max normalisation to [0, 1] in float64 arithmetic, `(img - img.min()) / (img.max() - img.min())`
+ * (README.md:87), fused with the cast to the fp32 tensor the step consumes (README.md:785) and, optionally, the
+ * bf16 copy the convolutions read.  `raw`: n images of `pixels_per_image` voxel values in their STORAGE dtype
+ * (so the host->device copy moves 1-2 B per pixel instead of the 8 B of the dataset's float64 arrays).
+ * numpy semantics are kept: a constant image yields NaN (0/0), a NaN pixel poisons its image. */
+typedef enum { VG_RAW_U8 = 0, VG_RAW_U16 = 1, VG_RAW_I16 = 2, VG_RAW_F32 = 3, VG_RAW_F64 = 4 } VgRawDtype;
+int vg_normalize_images(const void* raw, int raw_dtype, int n, long long pixels_per_image, float* out_f32,
+                        void* out_bf16, vg_stream_t stream);
 /* dst = src * (*scale): `scale` is a DEVICE scalar (no host sync) - rescales the loss kernels' stored gradients
  * when the loss is back-propagated with a gradient other than 1 */
 int vg_scale(const void* src, const float* scale, long long n, int dtype, void* dst, vg_stream_t stream);

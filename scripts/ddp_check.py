@@ -24,7 +24,9 @@ def main():
     # (compute dtype, loss mode, optimizer): north_star's BCE + Adam in both precisions, and the notebook's own
     # WGAN-GP + RMSprop + clamp (double backward with SyncBN sums exchanged in the second-order pass too)
     for cdt, loss_mode, opt in ((torch.float32, "bce", "adam"), (torch.bfloat16, "bce", "adam"), (torch.float32, "wgan_gp", "rmsprop")):
-        B, S, fs, steps = 4 * world, 32, 64, 2
+        # 16 samples per rank: at 4 per rank single LeakyReLU kink flips in the 4-Linear head moved whole rows of D's bf16
+        # gradient by O(1) (rel-L2 7.8e-2 between partitions in round 1); they average out with the batch
+        B, S, fs, steps = 16 * world, 32, 64, 2
         gen = torch.Generator().manual_seed(5)
         xs = [torch.rand(B, 1, S, S, generator=gen).to(dev) for _ in range(steps)]
 
@@ -82,19 +84,19 @@ def main():
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             same = bool(((hi - lo).abs() <= 1e-6 * hi.abs().clamp_min(1)).all())
-        results[f"{cdt}/{loss_mode}/{opt}"] = dict(peer_syncbn=dp.peer is not None, worst_pre_update_loss_rel=worst_pre, worst_loss_rel=worst, frac_params_off_g=frac_g, frac_params_off_d=frac_d, grad_rel_l2_g=gl2_g, grad_rel_l2_d=gl2_d,
+        results[f"{cdt}/{loss_mode}/{opt}"] = dict(peer_syncbn=dp.peer is not None, grad_buckets=(len(dp.buckets_d.ranges) if dp.buckets_d is not None else 0), worst_pre_update_loss_rel=worst_pre, worst_loss_rel=worst, frac_params_off_g=frac_g, frac_params_off_d=frac_d, grad_rel_l2_g=gl2_g, grad_rel_l2_d=gl2_d,
                                                        replicas_identical=same)
         lim = 2e-3 if cdt == torch.float32 else 0.08
         tol_pre = 2e-5 if cdt == torch.float32 else 2e-2
         tol_post = 5e-3 if cdt == torch.float32 else 5e-2
-        gtol = 2e-3 if cdt == torch.float32 else 0.25
+        gtol = 2e-3 if cdt == torch.float32 else 5e-2      # stated bound on the first-step gradient rel-L2 between partitions
         if opt == "rmsprop":
             # RMSprop's first steps move EVERY element by ~10*lr*sign(g) (v = 0.01 g^2) and the clamp keeps all of D
             # within +-0.01, so elements whose gradient is summation-order noise flip freely in any implementation
             # and later steps diverge chaotically; judge the first-step gradients and D's parameters instead
             params_ok = gl2_g <= gtol and gl2_d <= gtol and frac_d <= lim
         else:
-            params_ok = frac_g <= lim and frac_d <= lim and gl2_d <= gtol
+            params_ok = frac_g <= lim and frac_d <= lim and gl2_d <= gtol and gl2_g <= gtol
         ok = ok and worst_pre <= tol_pre and worst <= tol_post and params_ok and same
     if rank == 0:
         print(json.dumps(dict(world=world, ok=ok, **results)))

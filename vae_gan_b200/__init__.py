@@ -5,7 +5,8 @@ from .functional import compute_dtype, config, rng
 from .modules import (Decoder, Discriminator, Encoder, ResBlockDiscriminator, ResBlockVAE,
                       SpatialVAECodeProcessor, UnsupervisedGeneratorNetwork, build_vae_gan, init_weights)
 from .train import VaeGanTrainer
+from .data import InputPipeline, normalize_images
 
 __all__ = ["ResBlockVAE", "Encoder", "Decoder", "ResBlockDiscriminator", "Discriminator",
            "SpatialVAECodeProcessor", "UnsupervisedGeneratorNetwork", "init_weights", "build_vae_gan",
-           "VaeGanTrainer", "functional", "compute_dtype", "config", "rng"]
+           "VaeGanTrainer", "InputPipeline", "normalize_images", "functional", "compute_dtype", "config", "rng"]

@@ -34,6 +34,14 @@ class VgBnChannel(C.Structure):
                 ("running_mean", c_vp), ("running_var", c_vp), ("mean_rstd_out", c_vp), ("eps", c_f), ("momentum", c_f)]
 
 
+class VgPackItem(C.Structure):
+    _fields_ = [("w", c_vp), ("pack_kn", c_vp), ("pack_nk", c_vp), ("n0", c_int), ("n1", c_int), ("taps", c_int), ("transposed", c_int)]
+
+
+class VgSnItem(C.Structure):
+    _fields_ = [("w", c_vp), ("u", c_vp), ("v", c_vp), ("u_out", c_vp), ("v_out", c_vp), ("sigma", c_vp), ("rows", c_int), ("cols", c_int)]
+
+
 class VgLossDesc(C.Structure):
     _fields_ = [("n_pix", c_ll), ("n_pix_global", c_ll), ("n_lat", c_ll), ("n_logits", c_int),
                 ("n_logits_global", c_int), ("adv_mode", c_int), ("w_adv", c_f), ("w_recon", c_f),
@@ -57,6 +65,10 @@ _PROTOS = {
     "vg_launch_count": (c_ull, []),
     "vg_set_force_simt": (c_int, [c_int]),
     "vg_conv_pack_weights": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vg_conv_pack_weights_batched": (c_int, [c_vp, c_int, c_int, c_vp]),
+    "vg_conv_forward_scaled": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "vg_conv_dgrad_scaled": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "vg_spectral_norm_sigma_batched": (c_int, [c_vp, c_int, c_int, c_f, c_vp, C.c_size_t, c_vp]),
     "vg_conv_forward": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "vg_conv_dgrad": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "vg_conv_wgrad": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -74,6 +86,7 @@ _PROTOS = {
                                                c_vp, c_vp, c_f, c_vp]),
     "vg_bn_param_grads_scaled": (c_int, [c_vp, c_int, c_f, c_vp, c_vp, c_vp]),
     "vg_scale": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_vp]),
+    "vg_normalize_images": (c_int, [c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp]),
     "vg_lrelu_forward": (c_int, [c_vp, c_ll, c_int, c_f, c_vp, c_vp]),
     "vg_lrelu_backward": (c_int, [c_vp, c_vp, c_ll, c_int, c_f, c_vp, c_vp]),
     "vg_add": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_vp]),

@@ -4,15 +4,17 @@
 #include "vg_common.cuh"
 
 namespace vg {
-int simt_conv_forward(const VgConvDesc*, const void*, const void*, const float*, const float*, void*, cudaStream_t);
-int simt_conv_dgrad(const VgConvDesc*, const void*, const void*, void*, cudaStream_t);
+int simt_conv_forward(const VgConvDesc*, const void*, const void*, const float*, const float*, const float* sigma, int sigma_group_n, void*,
+                      cudaStream_t);
+int simt_conv_dgrad(const VgConvDesc*, const void*, const void*, const float* sigma, int sigma_group_n, void*, cudaStream_t);
 int simt_conv_wgrad(const VgConvDesc*, const void*, const void*, float*, cudaStream_t);
 int simt_colsum(const void*, long long, int, int, float*, cudaStream_t);
 int simt_pack_weights(const VgConvDesc*, const float*, const float*, void*, void*, cudaStream_t);
+int simt_pack_weights_batched(const VgPackItem* items, int n_items, int dtype, cudaStream_t);
 bool tc_conv_supported(const VgConvDesc*, bool dgrad);
 bool tc_wgrad_supported(const VgConvDesc*);
-int tc_conv_run(const VgConvDesc*, bool dgrad, const void* in, const void* wpack, const float* bias, const float* colscale, void* out,
-                int out_dtype, double* stats, bool* stats_fused, cudaStream_t);
+int tc_conv_run(const VgConvDesc*, bool dgrad, const void* in, const void* wpack, const float* bias, const float* colscale,
+                const float* sigma, int sigma_group_n, void* out, int out_dtype, double* stats, bool* stats_fused, cudaStream_t);
 int tc_wgrad_run(const VgConvDesc*, const void* x, const void* dy, float* dw, float* workspace, cudaStream_t);
 }  // namespace vg
 
@@ -44,18 +46,32 @@ extern "C" int vg_conv_pack_weights(const VgConvDesc* d, const float* w, const f
   return simt_pack_weights(d, w, sigma, pack_kn, pack_nk, as_stream(stream));
 }
 
+extern "C" int vg_conv_pack_weights_batched(const VgPackItem* items, int n_items, int dtype, vg_stream_t stream) {
+  VG_CHECK_ARG(items != nullptr && n_items >= 0, "bad args");
+  VG_CHECK_ARG(dtype == VG_F32 || dtype == VG_BF16, "bad dtype %d", dtype);
+  if (n_items == 0) return VG_OK;
+  return simt_pack_weights_batched(items, n_items, dtype, as_stream(stream));
+}
+
 extern "C" int vg_conv_forward(const VgConvDesc* d, const void* x, const void* pack_kn, const void* pack_nk, const float* bias,
                                const float* colscale, void* y, double* stats, vg_stream_t stream) {
+  return vg_conv_forward_scaled(d, x, pack_kn, pack_nk, bias, colscale, nullptr, 0, y, stats, stream);
+}
+
+extern "C" int vg_conv_forward_scaled(const VgConvDesc* d, const void* x, const void* pack_kn, const void* pack_nk, const float* bias,
+                                      const float* colscale, const float* sigma, int sigma_group_n, void* y, double* stats,
+                                      vg_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
   if (d->n == 0) return VG_OK;   // empty batch: nothing to do (pointers of empty tensors may be null)
   VG_CHECK_ARG(x && y && pack_kn && pack_nk, "null pointer");
+  VG_CHECK_ARG(sigma_group_n >= 0, "sigma_group_n must be >= 0");
   cudaStream_t s = as_stream(stream);
   bool stats_fused = false;
   if (tc_conv_supported(d, false) && !(d->c_out == 1 && colscale != nullptr))
-    rc = tc_conv_run(d, false, x, pack_kn, bias, colscale, y, d->out_dtype, stats, &stats_fused, s);
+    rc = tc_conv_run(d, false, x, pack_kn, bias, colscale, sigma, sigma_group_n, y, d->out_dtype, stats, &stats_fused, s);
   else
-    rc = simt_conv_forward(d, x, pack_nk, bias, colscale, y, s);
+    rc = simt_conv_forward(d, x, pack_nk, bias, colscale, sigma, sigma_group_n, y, s);
   if (rc) return rc;
   if (stats != nullptr && !stats_fused) {
     VgBnDesc b{};
@@ -71,13 +87,20 @@ extern "C" int vg_conv_forward(const VgConvDesc* d, const void* x, const void* p
 
 extern "C" int vg_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pack_kn, const void* pack_nk, void* dx,
                              vg_stream_t stream) {
+  return vg_conv_dgrad_scaled(d, dy, pack_kn, pack_nk, nullptr, 0, dx, stream);
+}
+
+extern "C" int vg_conv_dgrad_scaled(const VgConvDesc* d, const void* dy, const void* pack_kn, const void* pack_nk, const float* sigma,
+                                    int sigma_group_n, void* dx, vg_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
   if (d->n == 0) return VG_OK;
   VG_CHECK_ARG(dy && dx && pack_kn && pack_nk, "null pointer");
+  VG_CHECK_ARG(sigma_group_n >= 0, "sigma_group_n must be >= 0");
   cudaStream_t s = as_stream(stream);
-  if (tc_conv_supported(d, true)) return tc_conv_run(d, true, dy, pack_nk, nullptr, nullptr, dx, d->act_dtype, nullptr, nullptr, s);
-  return simt_conv_dgrad(d, dy, pack_kn, dx, s);
+  if (tc_conv_supported(d, true))
+    return tc_conv_run(d, true, dy, pack_nk, nullptr, nullptr, sigma, sigma_group_n, dx, d->act_dtype, nullptr, nullptr, s);
+  return simt_conv_dgrad(d, dy, pack_kn, sigma, sigma_group_n, dx, s);
 }
 
 extern "C" int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias, float* workspace,

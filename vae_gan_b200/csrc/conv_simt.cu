@@ -9,6 +9,7 @@
 // W_k is [tap][c_red][c_out'] with c_out' contiguous, so a thread owning 8 output channels
 // reads 8 contiguous weights per (tap, c_red).
 #include <algorithm>
+#include <string.h>
 #include "vg_common.cuh"
 
 namespace vg {
@@ -112,11 +113,142 @@ __global__ void __launch_bounds__(256) pack_weights_1x1_kernel(const float* __re
   }
 }
 
+
+// ---- batched weight pack: EVERY conv / Linear weight of a network in one launch -----------------------------------
+// The per-layer pack kernels above are 8-10 us launches with a few blocks each (~50 of them per training iteration).
+// Here a block finds its (weight, tile) in a by-value table and runs the same tile bodies; no sigma - the spectral
+// norm is applied in the convolution epilogue (vg_conv_forward_scaled), so a pack stays valid until the optimizer step.
+struct PackTable {
+  VgPackItem it[VG_PACK_MAX];
+  int first_block[VG_PACK_MAX + 1];
+  int n;
+};
+
+template <typename T, int TAPS>
+__device__ __forceinline__ void pack_tile_body(float* tile, const float* __restrict__ w, int n0, int n1, int transposed, T* __restrict__ pack_kn,
+                                               T* __restrict__ pack_nk, int bx, int by) {
+  constexpr int TP = TAPS | 1;
+  constexpr int ROW = kPackR1 * TP + 1;
+  const int r0b = by * kPackR0, r1b = bx * kPackR1;
+  const int n1t = min(kPackR1, n1 - r1b), n0t = min(kPackR0, n0 - r0b);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int run = n1t * TAPS;
+  for (int a = warp; a < n0t; a += 8) {
+    const float* src = w + ((long long)(r0b + a) * n1 + r1b) * TAPS;
+    for (int b = lane; b < run; b += 32) {
+      const int r1l = b / TAPS, tap = b - r1l * TAPS;
+      tile[a * ROW + r1l * TP + tap] = src[b];
+    }
+  }
+  __syncthreads();
+  T* along_r1 = transposed ? pack_nk : pack_kn;
+  T* along_r0 = transposed ? pack_kn : pack_nk;
+  if (along_r1 != nullptr && lane < n1t) {
+    for (int row = warp; row < TAPS * n0t; row += 8) {
+      const int tap = row / n0t, a = row - tap * n0t;
+      along_r1[((long long)tap * n0 + r0b + a) * n1 + r1b + lane] = from_f32<T>(tile[a * ROW + lane * TP + tap]);
+    }
+  }
+  if (along_r0 != nullptr) {
+    const int a = lane & 15, half = lane >> 4;
+    if (a < n0t) {
+      for (int row = warp * 2 + half; row < TAPS * n1t; row += 16) {
+        const int tap = row / n1t, b = row - tap * n1t;
+        along_r0[((long long)tap * n1 + r1b + b) * n0 + r0b + a] = from_f32<T>(tile[a * ROW + b * TP + tap]);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const __grid_constant__ PackTable tb) {
+  __shared__ float tile[kPackR0 * (kPackR1 * 17 + 1)];      // sized for TAPS = 16; the 1x1 body uses it as [32][33]
+  int i = 0;
+  while (i + 1 < tb.n && (int)blockIdx.x >= tb.first_block[i + 1]) ++i;
+  const VgPackItem& it = tb.it[i];
+  const int lb = (int)blockIdx.x - tb.first_block[i];
+  const float* w = it.w;
+  T* kn = reinterpret_cast<T*>(it.pack_kn);
+  T* nk = reinterpret_cast<T*>(it.pack_nk);
+  const int n0 = it.n0, n1 = it.n1;
+  if (it.taps == 1) {
+    // [r0][r1] -> same layout (cast copy) + transpose; 32 x 32 tiles
+    T* same = it.transposed ? nk : kn;
+    T* transp = it.transposed ? kn : nk;
+    const int tiles_x = (n1 + 31) / 32;
+    const int r0b = (lb / tiles_x) * 32, r1b = (lb % tiles_x) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    float (*t2)[33] = reinterpret_cast<float (*)[33]>(tile);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int a = ty + 8 * q;
+      float v = 0.f;
+      if (r0b + a < n0 && r1b + tx < n1) {
+        v = w[(long long)(r0b + a) * n1 + r1b + tx];
+        if (same != nullptr) same[(long long)(r0b + a) * n1 + r1b + tx] = from_f32<T>(v);
+      }
+      t2[a][tx] = v;
+    }
+    __syncthreads();
+    if (transp == nullptr) return;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int b = ty + 8 * q;
+      if (r1b + b < n1 && r0b + tx < n0) transp[(long long)(r1b + b) * n0 + r0b + tx] = from_f32<T>(t2[tx][b]);
+    }
+    return;
+  }
+  const int tiles_x = (n1 + kPackR1 - 1) / kPackR1;
+  const int bx = lb % tiles_x, by = lb / tiles_x;
+  if (it.taps == 9) pack_tile_body<T, 9>(tile, w, n0, n1, it.transposed, kn, nk, bx, by);
+  else if (it.taps == 16) pack_tile_body<T, 16>(tile, w, n0, n1, it.transposed, kn, nk, bx, by);
+  else {
+    // generic tap count: element-wise over this block's 16 x 32 x taps chunk of the torch layout
+    const int r0b = by * kPackR0, r1b = bx * kPackR1;
+    const int n0t = min(kPackR0, n0 - r0b), n1t = min(kPackR1, n1 - r1b);
+    const int taps = it.taps;
+    const int c_out = it.transposed ? n1 : n0, c_in = it.transposed ? n0 : n1;
+    for (int e = threadIdx.x; e < n0t * n1t * taps; e += blockDim.x) {
+      const int tap = e % taps;
+      const int r = e / taps;
+      const int b = r % n1t, a = r / n1t;
+      const float v = w[((long long)(r0b + a) * n1 + r1b + b) * taps + tap];
+      const int co = it.transposed ? r1b + b : r0b + a, ci = it.transposed ? r0b + a : r1b + b;
+      if (kn) kn[((long long)tap * c_out + co) * c_in + ci] = from_f32<T>(v);
+      if (nk) nk[((long long)tap * c_in + ci) * c_out + co] = from_f32<T>(v);
+    }
+  }
+}
+
+int simt_pack_weights_batched(const VgPackItem* items, int n_items, int dtype, cudaStream_t s) {
+  for (int base = 0; base < n_items; base += VG_PACK_MAX) {
+    PackTable tb;
+    memset(&tb, 0, sizeof(tb));
+    tb.n = std::min(VG_PACK_MAX, n_items - base);
+    int blocks = 0;
+    for (int i = 0; i < tb.n; ++i) {
+      const VgPackItem& it = items[base + i];
+      VG_CHECK_ARG(it.w && (it.pack_kn || it.pack_nk) && it.n0 > 0 && it.n1 > 0 && it.taps > 0, "bad pack item %d", base + i);
+      tb.it[i] = it;
+      tb.first_block[i] = blocks;
+      if (it.taps == 1) blocks += (int)(cdiv(it.n1, 32) * cdiv(it.n0, 32));
+      else blocks += (int)(cdiv(it.n1, kPackR1) * cdiv(it.n0, kPackR0));
+    }
+    tb.first_block[tb.n] = blocks;
+    if (blocks == 0) continue;
+    if (dtype == VG_BF16) pack_weights_batched_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(tb);
+    else pack_weights_batched_kernel<float><<<blocks, 256, 0, s>>>(tb);
+    VG_LAUNCHED();
+  }
+  return VG_OK;
+}
+
 // ---- generic direct convolution --------------------------------------------------------------
 // thread -> (output pixel, group of CO_T output channels)
 template <typename TI, typename TO, bool SCATTER, int CO_T>
 __global__ void __launch_bounds__(256) conv_direct_kernel(const TI* __restrict__ in, const TI* __restrict__ W,
                                                           const float* __restrict__ bias, const float* __restrict__ colscale,
+                                                          const float* __restrict__ sigma, int sigma_group_n,
                                                           ConvGeom g, TO* __restrict__ out) {
   const unsigned cog = (unsigned)(g.co / CO_T);
   const unsigned total = (unsigned)g.n * g.ho * g.wo * cog;      // host guarantees < 2^31
@@ -187,9 +319,11 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const TI* __restrict__
       }
     }
     TO* op = out + (long long)pix * g.co + co0;
+    // spectral norm applied here (1 / sigma of the sample's group) so that the packed weights stay valid across forwards
+    const float inv_sigma = sigma ? 1.0f / sigma[sigma_group_n > 0 ? n / sigma_group_n : 0] : 1.0f;
 #pragma unroll
     for (int j = 0; j < CO_T; ++j) {
-      float v = acc[j];
+      float v = acc[j] * inv_sigma;
       if (bias) v += bias[co0 + j];
       if (colscale) v *= colscale[(long long)n * g.co + co0 + j];
       acc[j] = v;
@@ -643,13 +777,14 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long rows, int c, lo
 
 // ---- host-side launchers (called from conv_api.cu) -------------------------------------------
 template <typename TI, typename TO>
-static int launch_direct(bool scatter, const TI* in, const TI* W, const float* bias, const float* colscale, const ConvGeom& g,
-                         TO* out, cudaStream_t s) {
+static int launch_direct(bool scatter, const TI* in, const TI* W, const float* bias, const float* colscale, const float* sigma,
+                         int sigma_group_n, const ConvGeom& g, TO* out, cudaStream_t s) {
   const bool v8 = (g.co % 8 == 0);
   const long long total = (long long)g.n * g.ho * g.wo * (v8 ? g.co / 8 : g.co);
   if (total == 0) return VG_OK;
   VG_CHECK_ARG(total < (1LL << 31) && (long long)g.n * g.hi * g.wi * g.cr < (1LL << 40), "tensor too large for the CUDA-core conv path");
-  if (g.co == 1 && g.cr == 64 && g.kh == 3 && g.kw == 3 && colscale == nullptr) {
+  // the single-channel special kernels have no sigma epilogue: a spectral-normed degenerate layer takes the generic kernel
+  if (sigma == nullptr && g.co == 1 && g.cr == 64 && g.kh == 3 && g.kw == 3 && colscale == nullptr) {
     const long long thr = (long long)g.n * g.ho * g.wo * 8;
     int grid1 = (int)std::min<long long>(cdiv(thr, 256), (long long)num_sms() * 16);
     if (scatter) conv_reduce1_kernel<TI, TO, true, 9><<<grid1, 256, 0, s>>>(in, W, bias, g, out);
@@ -657,8 +792,8 @@ static int launch_direct(bool scatter, const TI* in, const TI* W, const float* b
     VG_LAUNCHED();
     return VG_OK;
   }
-  if (g.cr == 1 && v8 && g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.wo % 8 == 0 && g.ho == g.hi && g.wo == g.wi &&
-      256 % (g.co / 8) == 0) {
+  if (sigma == nullptr && g.cr == 1 && v8 && g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.wo % 8 == 0 && g.ho == g.hi &&
+      g.wo == g.wi && 256 % (g.co / 8) == 0) {
     const long long thr = (long long)g.n * g.ho * (g.wo / 8) * (g.co / 8);
     int grid1 = (int)std::min<long long>(cdiv(thr, 256), (long long)num_sms() * 8);
     if (scatter) conv_expand1_strip_kernel<TI, TO, true><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
@@ -666,7 +801,7 @@ static int launch_direct(bool scatter, const TI* in, const TI* W, const float* b
     VG_LAUNCHED();
     return VG_OK;
   }
-  if (g.cr == 1 && v8 && g.kh == 3 && g.kw == 3 && 256 % (g.co / 8) == 0) {
+  if (sigma == nullptr && g.cr == 1 && v8 && g.kh == 3 && g.kw == 3 && 256 % (g.co / 8) == 0) {
     int grid1 = (int)std::min<long long>(cdiv(total, 256 * 2), (long long)num_sms() * 16);
     if (scatter) conv_expand1_kernel<TI, TO, true><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
     else         conv_expand1_kernel<TI, TO, false><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
@@ -675,38 +810,40 @@ static int launch_direct(bool scatter, const TI* in, const TI* W, const float* b
   }
   int grid = (int)std::min<long long>(cdiv(total, 256), (long long)num_sms() * 32);
   if (scatter) {
-    if (v8) conv_direct_kernel<TI, TO, true, 8><<<grid, 256, 0, s>>>(in, W, bias, colscale, g, out);
-    else    conv_direct_kernel<TI, TO, true, 1><<<grid, 256, 0, s>>>(in, W, bias, colscale, g, out);
+    if (v8) conv_direct_kernel<TI, TO, true, 8><<<grid, 256, 0, s>>>(in, W, bias, colscale, sigma, sigma_group_n, g, out);
+    else    conv_direct_kernel<TI, TO, true, 1><<<grid, 256, 0, s>>>(in, W, bias, colscale, sigma, sigma_group_n, g, out);
   } else {
-    if (v8) conv_direct_kernel<TI, TO, false, 8><<<grid, 256, 0, s>>>(in, W, bias, colscale, g, out);
-    else    conv_direct_kernel<TI, TO, false, 1><<<grid, 256, 0, s>>>(in, W, bias, colscale, g, out);
+    if (v8) conv_direct_kernel<TI, TO, false, 8><<<grid, 256, 0, s>>>(in, W, bias, colscale, sigma, sigma_group_n, g, out);
+    else    conv_direct_kernel<TI, TO, false, 1><<<grid, 256, 0, s>>>(in, W, bias, colscale, sigma, sigma_group_n, g, out);
   }
   VG_LAUNCHED();
   return VG_OK;
 }
 
-int simt_conv_forward(const VgConvDesc* d, const void* x, const void* pack_nk, const float* bias, const float* colscale, void* y,
-                      cudaStream_t s) {
+int simt_conv_forward(const VgConvDesc* d, const void* x, const void* pack_nk, const float* bias, const float* colscale,
+                      const float* sigma, int sigma_group_n, void* y, cudaStream_t s) {
   ConvGeom g{d->n, d->h_in, d->w_in, d->c_in, d->h_out, d->w_out, d->c_out, d->kh, d->kw, d->stride, d->pad};
   const bool scatter = d->transposed != 0;
   if (d->act_dtype == VG_BF16) {
     if (d->out_dtype == VG_BF16)
-      return launch_direct<__nv_bfloat16, __nv_bfloat16>(scatter, (const __nv_bfloat16*)x, (const __nv_bfloat16*)pack_nk, bias, colscale, g,
-                                                         (__nv_bfloat16*)y, s);
-    return launch_direct<__nv_bfloat16, float>(scatter, (const __nv_bfloat16*)x, (const __nv_bfloat16*)pack_nk, bias, colscale, g, (float*)y, s);
+      return launch_direct<__nv_bfloat16, __nv_bfloat16>(scatter, (const __nv_bfloat16*)x, (const __nv_bfloat16*)pack_nk, bias, colscale, sigma,
+                                                         sigma_group_n, g, (__nv_bfloat16*)y, s);
+    return launch_direct<__nv_bfloat16, float>(scatter, (const __nv_bfloat16*)x, (const __nv_bfloat16*)pack_nk, bias, colscale, sigma,
+                                               sigma_group_n, g, (float*)y, s);
   }
   VG_CHECK_ARG(d->out_dtype == VG_F32, "fp32 activations require fp32 output");
-  return launch_direct<float, float>(scatter, (const float*)x, (const float*)pack_nk, bias, colscale, g, (float*)y, s);
+  return launch_direct<float, float>(scatter, (const float*)x, (const float*)pack_nk, bias, colscale, sigma, sigma_group_n, g, (float*)y, s);
 }
 
-int simt_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pack_kn, void* dx, cudaStream_t s) {
+int simt_conv_dgrad(const VgConvDesc* d, const void* dy, const void* pack_kn, const float* sigma, int sigma_group_n, void* dx,
+                    cudaStream_t s) {
   // reduce over c_out; output has c_in channels on the input grid
   ConvGeom g{d->n, d->h_out, d->w_out, d->c_out, d->h_in, d->w_in, d->c_in, d->kh, d->kw, d->stride, d->pad};
   const bool scatter = d->transposed == 0;   // Conv2d dgrad scatters, ConvTranspose2d dgrad gathers
   if (d->act_dtype == VG_BF16)
-    return launch_direct<__nv_bfloat16, __nv_bfloat16>(scatter, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pack_kn, nullptr, nullptr, g,
-                                                       (__nv_bfloat16*)dx, s);
-  return launch_direct<float, float>(scatter, (const float*)dy, (const float*)pack_kn, nullptr, nullptr, g, (float*)dx, s);
+    return launch_direct<__nv_bfloat16, __nv_bfloat16>(scatter, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pack_kn, nullptr, nullptr, sigma,
+                                                       sigma_group_n, g, (__nv_bfloat16*)dx, s);
+  return launch_direct<float, float>(scatter, (const float*)dy, (const float*)pack_kn, nullptr, nullptr, sigma, sigma_group_n, g, (float*)dx, s);
 }
 
 int simt_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* dw, cudaStream_t s) {

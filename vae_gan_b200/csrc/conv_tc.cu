@@ -56,6 +56,8 @@ struct alignas(64) TcConvParams {
   void* out;
   const float* bias;
   const float* colscale;
+  const float* sigma;    // nullable: the accumulator is multiplied by 1 / sigma[group] (spectral norm applied in the epilogue,
+  int sigma_group_n;     //   so the packed weights stay valid across forwards); group = sample / sigma_group_n (0: one group)
   double* stats;         // nullable: [2*n_out] per-channel sum / sum of squares of the stored output
 };
 
@@ -91,6 +93,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.sigma != nullptr && valid) {
+    const float inv = 1.0f / __ldg(p.sigma + (p.sigma_group_n > 0 ? gn / p.sigma_group_n : 0));
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= inv;
+  }
   if (p.bias != nullptr && add_bias) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -110,9 +117,13 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint
         else reinterpret_cast<__nv_bfloat16*>(p.out)[opix] = __float2bfloat16_rn(v[0]);
       }
     } else if (p.ksplit > 1) {
+      // split-K partial sums: 16-byte vector reductions (a quarter of the RED instructions of scalar atomics - the
+      // Linear layers' one-shot CTAs spent most of their time issuing them; n_out % 64 == 0 keeps them aligned)
       float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
+      for (int j = 0; j < 32; j += 4)
+        asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                     : "memory");
     } else if (p.out_f32) {
       float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol;
 #pragma unroll
@@ -1226,7 +1237,7 @@ static int pick_bn(int n_out) {
 
 // dgrad=false: y = conv(x).  dgrad=true: dx from dy.  `in` is the tensor being read.
 int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpack, const float* bias, const float* colscale,
-                void* out, int out_dtype, double* stats, bool* stats_fused, cudaStream_t s) {
+                const float* sigma, int sigma_group_n, void* out, int out_dtype, double* stats, bool* stats_fused, cudaStream_t s) {
   if (stats_fused) *stats_fused = false;
   TcConvParams p;
   memset(&p, 0, sizeof(p));
@@ -1244,6 +1255,7 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   p.OH = out_h; p.OW = out_w;
   p.out = out; p.out_f32 = out_dtype == VG_F32;
   p.bias = bias; p.colscale = colscale;
+  p.sigma = sigma; p.sigma_group_n = sigma_group_n;
   p.stats = nullptr;
   int nphase = 1;
   if (gather) {
@@ -1302,8 +1314,10 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   if (fuse_stats < 0) { const char* e = getenv("VG_TC_FUSE_STATS"); fuse_stats = e ? atoi(e) : 0; }
   const long long ctas1 = (long long)grid.x * grid.y * grid.z;
   const bool big = mt_on && p.ksplit == 1 && ctas1 >= 6LL * num_sms();
-  const bool use_persist = persist && ctas1 >= 2LL * num_sms() &&
-                           (BN == 256 || (ctas1 >= (long long)mt_min * num_sms() && (BN == 64 || BN == 128)));
+  // 256-wide tiles go persistent as soon as there is more than one work item per SM (288 tiles of the 24x24 layers at
+  // batch 64 ran as one-shot CTAs without epilogue overlap: 38-85 us for 31 us of tensor work)
+  const bool use_persist = persist && ((BN == 256 && ctas1 > (long long)num_sms()) ||
+                                       (ctas1 >= 2LL * num_sms() && ctas1 >= (long long)mt_min * num_sms() && (BN == 64 || BN == 128)));
   // BatchNorm statistics of the output can be accumulated by the epilogue warps of the 8-warp persistent
   // kernels (parity-tested), but it is OPT-IN (VG_TC_FUSE_STATS=1): measured on B200 the per-chunk smem
   // transposes cost the L2/smem-bound main loop more (+35 % per launch with 8 epilogue warps, +60 % with

@@ -2,6 +2,7 @@
 // discriminator head, avg_pool2d+flatten, spectral-norm power iteration, reparameterisation,
 // the fused loss+gradient kernels, the fused Adam/RMSprop update, and layout/dtype helpers.
 #include <algorithm>
+#include <string.h>
 #include "vg_common.cuh"
 
 namespace vg {
@@ -237,6 +238,116 @@ __global__ void sn_finish_kernel(const float* __restrict__ s, float* __restrict_
     float tot = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
     *sigma = tot;
+  }
+}
+
+// ---- batched power iteration: every spectral-normed weight of the discriminator in three launches ----------------
+// (per-weight it was memset + 3 kernels + 2 clone kernels, x 9 convolutions x 3 forwards per training iteration)
+struct SnTable {
+  VgSnItem it[VG_SN_MAX];
+  int t_off[VG_SN_MAX];      // workspace offsets (floats): t[cols] then s[rows] per item
+  int s_off[VG_SN_MAX];
+  int n;
+};
+__global__ void sn_wt_u_batched_kernel(const __grid_constant__ SnTable tb, float* __restrict__ ws) {
+  const VgSnItem& it = tb.it[blockIdx.z];
+  const int rows = it.rows, cols = it.cols;
+  const int slices = max(1, min(rows / 8, 64));
+  const int rps = (rows + slices - 1) / slices;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * rps;
+  if (j >= cols || r0 >= rows) return;
+  const int r1 = min(rows, r0 + rps);
+  const float* W = it.w;
+  const float* u = it.u;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int i = r0;
+  for (; i + 4 <= r1; i += 4) {
+    const float* wp = W + (long long)i * cols + j;
+    s0 = fmaf(wp[0], u[i], s0);
+    s1 = fmaf(wp[cols], u[i + 1], s1);
+    s2 = fmaf(wp[2LL * cols], u[i + 2], s2);
+    s3 = fmaf(wp[3LL * cols], u[i + 3], s3);
+  }
+  for (; i < r1; ++i) s0 = fmaf(W[(long long)i * cols + j], u[i], s0);
+  atomicAdd(&ws[tb.t_off[blockIdx.z] + j], (s0 + s1) + (s2 + s3));
+}
+// block (row, item): s[row] = (W[row] . t) / max(||t||, eps) (training; t = W^T u) or W[row] . v (eval);
+// row 0 also writes v = t / max(||t||, eps) into the module buffer and into the saved copy
+__global__ void __launch_bounds__(128) sn_w_v_batched_kernel(const __grid_constant__ SnTable tb, float* __restrict__ ws, int training, float eps) {
+  const VgSnItem& it = tb.it[blockIdx.y];
+  const int row = blockIdx.x;
+  if (row >= it.rows) return;
+  const int cols = it.cols;
+  const float* t = training ? ws + tb.t_off[blockIdx.y] : it.v;
+  float dot = 0.f, nt = 0.f;
+  const float* wr = it.w + (long long)row * cols;
+  for (int j = threadIdx.x; j < cols; j += 128) {
+    const float tv = t[j];
+    dot = fmaf(wr[j], tv, dot);
+    nt = fmaf(tv, tv, nt);
+  }
+  __shared__ float red[2][4];
+  __shared__ float inv_s;
+  dot = warp_sum(dot);
+  nt = warp_sum(nt);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = dot; red[1][threadIdx.x >> 5] = nt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float d = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+    const float n = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+    const float inv = training ? 1.0f / fmaxf(sqrtf(n), eps) : 1.0f;
+    ws[tb.s_off[blockIdx.y] + row] = d * inv;
+    inv_s = inv;
+  }
+  if (row == 0) {
+    __syncthreads();
+    const float inv = inv_s;
+    for (int j = threadIdx.x; j < cols; j += 128) {
+      const float vv = t[j] * inv;                  // eval: inv = 1, v unchanged
+      if (training) it.v[j] = vv;
+      if (it.v_out != nullptr) it.v_out[j] = vv;
+    }
+  }
+}
+// one block per item: training: u = s / max(||s||, eps); sigma = u . s; the saved copy of u
+__global__ void sn_finish_batched_kernel(const __grid_constant__ SnTable tb, const float* __restrict__ ws, int training, float eps) {
+  const VgSnItem& it = tb.it[blockIdx.x];
+  const float* s = ws + tb.s_off[blockIdx.x];
+  const int rows = it.rows;
+  __shared__ float red[32];
+  __shared__ float bc;
+  const int tid = threadIdx.x;
+  float part = 0.f;
+  if (training) {
+    for (int i = tid; i < rows; i += blockDim.x) part = fmaf(s[i], s[i], part);
+    part = warp_sum(part);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+      bc = 1.0f / fmaxf(sqrtf(tot), eps);
+    }
+    __syncthreads();
+    const float inv = bc;
+    for (int i = tid; i < rows; i += blockDim.x) it.u[i] = s[i] * inv;
+    __syncthreads();
+  }
+  part = 0.f;
+  for (int i = tid; i < rows; i += blockDim.x) {
+    const float uu = it.u[i];
+    if (it.u_out != nullptr) it.u_out[i] = uu;
+    part = fmaf(uu, s[i], part);
+  }
+  part = warp_sum(part);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    *it.sigma = tot;
   }
 }
 __global__ void sn_bwd_dot_kernel(const float* __restrict__ dwh, const float* __restrict__ w, long long n, float* __restrict__ acc) {
@@ -491,6 +602,50 @@ __global__ void scale_kernel(const T* __restrict__ src, const float* __restrict_
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = from_f32<T>(to_f32(src[i]) * sc);
 }
+// ------------------------------------------------------------------------------------------
+// input pipeline: per-image min-max normalisation to [0, 1] - the dataset's
+// `img = (img - img.min()) / (img.max() - img.min())` (README.md:87, float64 arithmetic) - fused with the
+// float64 -> float32 cast of README.md:785 (`imgs.type(Tensor)`) and, optionally, the bf16 copy the convolutions
+// read.  One block per image: pass 1 reduces min / max, pass 2 re-reads the image (L2-resident) and writes.
+// ------------------------------------------------------------------------------------------
+template <typename TR> __device__ __forceinline__ double raw_to_f64(TR v) { return (double)v; }
+template <typename TR>
+__global__ void __launch_bounds__(256) normalize_images_kernel(const TR* __restrict__ raw, long long pixels, float* __restrict__ out_f32,
+                                                               __nv_bfloat16* __restrict__ out_bf16) {
+  const TR* img = raw + (long long)blockIdx.x * pixels;
+  double lo = 1e300, hi = -1e300;
+  bool has_nan = false;
+  for (long long i = threadIdx.x; i < pixels; i += blockDim.x) {
+    const double v = raw_to_f64(img[i]);
+    if (v != v) has_nan = true;
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
+  }
+  __shared__ double s_lo[8], s_hi[8];
+  __shared__ int s_nan;
+  if (threadIdx.x == 0) s_nan = 0;
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+  if (has_nan) s_nan = 1;
+  __syncthreads();
+  lo = s_lo[0]; hi = s_hi[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+  // numpy semantics: a NaN pixel makes min and max NaN, hence the whole image; a constant image divides 0 by 0
+  const double range = s_nan ? __longlong_as_double(0x7ff8000000000000LL) : (hi - lo);
+  for (long long i = threadIdx.x; i < pixels; i += blockDim.x) {
+    const float r = (float)((raw_to_f64(img[i]) - lo) / range);
+    const long long o = (long long)blockIdx.x * pixels + i;
+    if (out_f32 != nullptr) out_f32[o] = r;
+    if (out_bf16 != nullptr) out_bf16[o] = __float2bfloat16_rn(r);
+  }
+}
+
 // tiled transpose of [c][hw] <-> [hw][c] per image
 template <typename TD>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int c, int hw, TD* __restrict__ dst) {
@@ -649,6 +804,42 @@ extern "C" int vg_spectral_norm_sigma(const float* w_orig, int rows, int cols, f
   return VG_OK;
 }
 
+extern "C" int vg_spectral_norm_sigma_batched(const VgSnItem* items, int n_items, int training, float eps, float* workspace,
+                                              size_t workspace_floats, vg_stream_t stream) {
+  VG_CHECK_ARG(items && n_items >= 0 && workspace, "bad args");
+  cudaStream_t s = as_stream(stream);
+  for (int base = 0; base < n_items; base += VG_SN_MAX) {
+    SnTable tb;
+    memset(&tb, 0, sizeof(tb));
+    tb.n = std::min(VG_SN_MAX, n_items - base);
+    size_t off = 0;
+    int max_rows = 0, max_cols = 0;
+    for (int i = 0; i < tb.n; ++i) {
+      const VgSnItem& it = items[base + i];
+      VG_CHECK_ARG(it.w && it.u && it.v && it.sigma && it.rows > 0 && it.cols > 0, "bad spectral-norm item %d", base + i);
+      tb.it[i] = it;
+      tb.t_off[i] = (int)off; off += (size_t)it.cols;
+      tb.s_off[i] = (int)off; off += (size_t)it.rows;
+      max_rows = std::max(max_rows, it.rows);
+      max_cols = std::max(max_cols, it.cols);
+    }
+    VG_CHECK_ARG(off <= workspace_floats, "workspace too small: need %zu floats, have %zu", off, workspace_floats);
+    if (training) {
+      VG_CUDA(cudaMemsetAsync(workspace, 0, off * sizeof(float), s));
+      const int max_slices = std::max(1, std::min(max_rows / 8, 64));
+      dim3 g1((unsigned)cdiv(max_cols, 128), (unsigned)max_slices, (unsigned)tb.n);
+      sn_wt_u_batched_kernel<<<g1, 128, 0, s>>>(tb, workspace);
+      VG_LAUNCHED();
+    }
+    dim3 g2((unsigned)max_rows, (unsigned)tb.n);
+    sn_w_v_batched_kernel<<<g2, 128, 0, s>>>(tb, workspace, training, eps);
+    VG_LAUNCHED();
+    sn_finish_batched_kernel<<<tb.n, 256, 0, s>>>(tb, workspace, training, eps);
+    VG_LAUNCHED();
+  }
+  return VG_OK;
+}
+
 extern "C" int vg_spectral_norm_backward(const float* dw_hat, const float* w_orig, const float* u, const float* v,
                                          const float* sigma, int rows, int cols, float* dw_orig, float* workspace,
                                          vg_stream_t stream) {
@@ -784,6 +975,24 @@ extern "C" int vg_scale(const void* src, const float* scale, long long n, int dt
     scale_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, scale, n, (__nv_bfloat16*)dst);
   else
     scale_kernel<float><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const float*)src, scale, n, (float*)dst);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_normalize_images(const void* raw, int raw_dtype, int n, long long pixels_per_image, float* out_f32, void* out_bf16,
+                                   vg_stream_t stream) {
+  VG_CHECK_ARG(raw && n >= 0 && pixels_per_image > 0 && (out_f32 || out_bf16), "bad args");
+  if (n == 0) return VG_OK;
+  cudaStream_t s = as_stream(stream);
+  __nv_bfloat16* ob = (__nv_bfloat16*)out_bf16;
+  switch (raw_dtype) {
+    case VG_RAW_U8: normalize_images_kernel<uint8_t><<<n, 256, 0, s>>>((const uint8_t*)raw, pixels_per_image, out_f32, ob); break;
+    case VG_RAW_U16: normalize_images_kernel<uint16_t><<<n, 256, 0, s>>>((const uint16_t*)raw, pixels_per_image, out_f32, ob); break;
+    case VG_RAW_I16: normalize_images_kernel<int16_t><<<n, 256, 0, s>>>((const int16_t*)raw, pixels_per_image, out_f32, ob); break;
+    case VG_RAW_F32: normalize_images_kernel<float><<<n, 256, 0, s>>>((const float*)raw, pixels_per_image, out_f32, ob); break;
+    case VG_RAW_F64: normalize_images_kernel<double><<<n, 256, 0, s>>>((const double*)raw, pixels_per_image, out_f32, ob); break;
+    default: set_error("unknown raw dtype %d", raw_dtype); return VG_EINVAL;
+  }
   VG_LAUNCHED();
   return VG_OK;
 }

@@ -36,6 +36,7 @@ class _Config:
     defer_num_batches_tracked = False   # the trainer bumps every BN's counter with ONE foreach kernel per step
     peer = None                   # dist.PeerExchange: NVLink one-shot exchange of the SyncBN sums (else NCCL)
     trainer_active = False        # inside VaeGanTrainer._iteration: loss backward is called with grad 1 (no rescale kernels)
+    grad_tracker = None           # train.GradBuckets: told when a parameter's fused gradient is used / final (DP overlap)
 
 
 config = _Config()
@@ -121,6 +122,32 @@ def live_grad_buf(param):
     if g is None or g.data_ptr() != buf.data_ptr():
         return None
     return buf
+
+
+def note_use(ctx, indexed_params):
+    """Forward of a Function whose backward will ACCUMULATE into the trainer's flat gradient buffer: one pending
+    contribution per (parameter, use) whose gradient autograd will ask for (ctx.needs_input_grad).  The data-parallel
+    trainer all-reduces a bucket of the flat buffer as soon as every contribution to it has been launched
+    (train.GradBuckets).  Returns the owners noted; the backward hands exactly that list to note_done."""
+    t = config.grad_tracker
+    if t is None:
+        return ()
+    noted = []
+    for idx, p in indexed_params:
+        if p is not None and ctx.needs_input_grad[idx] and getattr(p, "_vg_grad_buf", None) is not None:
+            owner = getattr(p, "_vg_owner", p)
+            t.use(owner)
+            noted.append(owner)
+    return tuple(noted)
+
+
+def note_done(noted):
+    """Backward counterpart of note_use: the kernels adding these contributions are enqueued on the current stream."""
+    t = config.grad_tracker
+    if t is None or not noted:
+        return
+    for owner in noted:
+        t.done(owner)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -300,7 +327,7 @@ class ConvFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, bias, sn_u, sn_v, colscale, geom, out_dtype, stats_out, training):
+    def forward(ctx, x, weight, bias, sn_u, sn_v, colscale, geom, out_dtype, stats_out, training, sn_pre):
         _lib.ensure_device(x.device)
         assert is_act(x), "ConvFn expects a channels_last activation"
         dev = x.device
@@ -313,27 +340,40 @@ class ConvFn(Function):
         w = weight.detach()
         if not w.is_contiguous():
             w = w.contiguous()
-        if sn_u is not None:
+        if sn_pre is not None:
+            # the discriminator ran ONE batched power iteration for all of its weights at the top of its forward
+            sigma, u_saved, v_saved = sn_pre
+        elif sn_u is not None:
             rows, cols = w.shape[0], w.numel() // w.shape[0]
             sigma = torch.empty(1, dtype=torch.float32, device=dev)
             ws = torch.empty(rows + cols + 4, dtype=torch.float32, device=dev)
             call("vg_spectral_norm_sigma", ptr(w), rows, cols, ptr(sn_u), ptr(sn_v), int(training), SN_EPS,
                  ptr(sigma), ptr(ws), s)
             u_saved, v_saved = sn_u.clone(), sn_v.clone()
-        numel = w.numel()
-        pack_kn = torch.empty(numel, dtype=x.dtype, device=dev)
-        pack_nk = torch.empty(numel, dtype=x.dtype, device=dev)
-        call("vg_conv_pack_weights", C.byref(d), ptr(w), ptr(sigma), ptr(pack_kn), ptr(pack_nk), s)
+        packs = cached_packs(weight, x.dtype)
+        if packs is not None:
+            # the trainer packed every weight of the network once after the optimizer step; W / sigma is applied in
+            # the epilogue (conv is linear), so the same pack serves every forward until the next update
+            pack_kn, pack_nk = packs
+            sigma_ep = sigma
+        else:
+            numel = w.numel()
+            pack_kn = torch.empty(numel, dtype=x.dtype, device=dev)
+            pack_nk = torch.empty(numel, dtype=x.dtype, device=dev)
+            call("vg_conv_pack_weights", C.byref(d), ptr(w), ptr(sigma), ptr(pack_kn), ptr(pack_nk), s)
+            sigma_ep = None
         y = empty_act(x.shape[0], c_out, ho, wo, out_dtype, dev)
         b = bias.detach() if bias is not None else None
-        call("vg_conv_forward", C.byref(d), ptr(x), ptr(pack_kn), ptr(pack_nk), ptr(b), ptr(colscale), ptr(y),
-             ptr(stats_out), s)
+        call("vg_conv_forward_scaled", C.byref(d), ptr(x), ptr(pack_kn), ptr(pack_nk), ptr(b), ptr(colscale), ptr(sigma_ep), 0,
+             ptr(y), ptr(stats_out), s)
         ctx.d = d
         ctx.geom = geom
         ctx.has_bias = bias is not None
-        ctx.has_sn = sn_u is not None
+        ctx.has_sn = sigma is not None
+        ctx.sigma_in_epilogue = sigma_ep is not None
         ctx.wshape = tuple(weight.shape)
         ctx.weight_ref, ctx.bias_ref = weight, bias          # live_grad_buf() is evaluated at backward time
+        ctx.noted = note_use(ctx, ((1, weight), (2, bias)))
         ctx.save_for_backward(x, pack_kn, pack_nk, w if ctx.has_sn else None, sigma, u_saved, v_saved, weight)
         return y
 
@@ -347,16 +387,17 @@ class ConvFn(Function):
             # compute_gradient_penalty); ctx.needs_input_grad cannot tell whether a weight gradient was requested,
             # so higher-order derivatives with respect to parameters are not available through create_graph.
             if not ctx.needs_input_grad[0]:
-                return (None,) * 10
+                return (None,) * 11
             w_eff = gp.sn_effective_weight(weight, u, v) if ctx.has_sn else weight
             dx = gp.ConvDgradFn.apply(dy, w_eff, d, x.dtype)
-            return (dx,) + (None,) * 9
+            return (dx,) + (None,) * 10
         s = stream_ptr()
         dy = as_act(dy, x.dtype)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = empty_act(d.n, d.c_in, d.h_in, d.w_in, x.dtype, x.device)
-            call("vg_conv_dgrad", C.byref(d), ptr(dy), ptr(pack_kn), ptr(pack_nk), ptr(dx), s)
+            call("vg_conv_dgrad_scaled", C.byref(d), ptr(dy), ptr(pack_kn), ptr(pack_nk),
+                 ptr(sigma) if ctx.sigma_in_epilogue else None, 0, ptr(dx), s)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             wbuf = live_grad_buf(ctx.weight_ref)          # trainer's flat gradient view (fused accumulation) or None
             bbuf = live_grad_buf(ctx.bias_ref)
@@ -379,13 +420,69 @@ class ConvFn(Function):
                 dw = None
             if bbuf is not None:
                 db = None
-        return dx, dw, db, None, None, None, None, None, None, None
+        note_done(ctx.noted)
+        return dx, dw, db, None, None, None, None, None, None, None, None
 
 
 def conv(x, weight, bias=None, *, geom: ConvGeom, sn=None, colscale=None, out_dtype=None, stats_out=None,
-         training=True):
+         training=True, sn_pre=None):
     u, v = sn if sn is not None else (None, None)
-    return ConvFn.apply(x, weight, bias, u, v, colscale, geom, out_dtype, stats_out, training)
+    return ConvFn.apply(x, weight, bias, u, v, colscale, geom, out_dtype, stats_out, training, sn_pre)
+
+
+def cached_packs(weight, dtype):
+    """(pack_kn, pack_nk) made by the trainer's batched pack (train.WeightPacks) - valid only inside a trainer iteration
+    (the trainer re-packs after every optimizer step) and for the compute dtype they were made in."""
+    if not config.trainer_active:
+        return None
+    pk = getattr(weight, "_vg_packs", None)
+    if pk is None or pk[2] != dtype:
+        return None
+    return pk[0], pk[1]
+
+
+def pack_weights_batched(items, dtype):
+    """items: [(weight fp32 tensor (torch layout), pack_kn, pack_nk, transposed)] -> ONE launch (per 32 weights)."""
+    if not items:
+        return None
+    _lib.ensure_device(items[0][0].device)
+    table = (_lib.VgPackItem * len(items))()
+    for i, (w, kn, nk, transposed) in enumerate(items):
+        taps = 1
+        for dim in w.shape[2:]:
+            taps *= dim
+        table[i] = _lib.VgPackItem(ptr(w), ptr(kn), ptr(nk), w.shape[0], w.shape[1], taps, int(transposed))
+    call("vg_conv_pack_weights_batched", table, len(items), vg_dtype(dtype), stream_ptr())
+    return table
+
+
+def spectral_norm_batched(weights, training):
+    """One batched power iteration (README.md:378,383,387; legacy nn.utils.spectral_norm hook: n_power_iterations 1,
+    eps 1e-12) for a list of (weight_orig, weight_u, weight_v): three launches for all of them.  Returns, per weight,
+    (sigma, u_saved, v_saved) - the post-iteration vectors this forward's backward needs."""
+    if not weights:
+        return []
+    dev = weights[0][0].device
+    _lib.ensure_device(dev)
+    n = len(weights)
+    sizes = [(w.shape[0], w.numel() // w.shape[0]) for w, _, _ in weights]
+    total = sum(1 + r + c for r, c in sizes)
+    ws_floats = sum(r + c for r, c in sizes)
+    buf = torch.empty(total + ws_floats + 16, dtype=torch.float32, device=dev)
+    table = (_lib.VgSnItem * n)()
+    out, off = [], 0
+    for i, ((w, u, v), (r, c)) in enumerate(zip(weights, sizes)):
+        sigma = buf[off:off + 1]
+        u_s = buf[off + 1:off + 1 + r]
+        v_s = buf[off + 1 + r:off + 1 + r + c]
+        off += 1 + r + c
+        wd = w.detach()
+        assert wd.is_contiguous()
+        table[i] = _lib.VgSnItem(ptr(wd), ptr(u), ptr(v), ptr(u_s), ptr(v_s), ptr(sigma), r, c)
+        out.append((sigma, u_s, v_s))
+    work = buf[off:]
+    call("vg_spectral_norm_sigma_batched", table, n, int(training), SN_EPS, ptr(work), ws_floats, stream_ptr())
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -495,6 +592,7 @@ class BnActFn(Function):
         d = _bn_desc(x, slope, drop_p if training else 0.0, offset, training)
         y, mr = _bn_act_forward(x, g, b, running_mean, running_var, sums, d, training)
         ctx.d = d
+        ctx.noted = note_use(ctx, ((1, gamma), (2, beta)))
         ctx.save_for_backward(x, mr, g, b, out_colscale, gamma, beta)
         return y
 
@@ -512,6 +610,7 @@ class BnActFn(Function):
         dx, dgamma, dbeta = _bn_backward(dy, x, mr, g, b, ctx.d, out_colscale=ocs,
                                          need_dx=ctx.needs_input_grad[0], need_params=ctx.needs_input_grad[1],
                                          gbuf=live_grad_buf(gamma), bbuf=live_grad_buf(beta))
+        note_done(ctx.noted)
         return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
@@ -529,6 +628,7 @@ class BnActForkFn(Function):
         d = _bn_desc(x, slope, drop_p if training else 0.0, offset, training)
         y, mr = _bn_act_forward(x, g, b, running_mean, running_var, sums, d, training)
         ctx.d = d
+        ctx.noted = note_use(ctx, ((1, gamma), (2, beta)))
         ctx.save_for_backward(x, mr, g, b, gamma, beta)
         return y, x.view_as(x)
 
@@ -545,12 +645,14 @@ class BnActForkFn(Function):
                 dx = dpass.to(x.dtype) if dx is None else dx + dpass.to(dx.dtype)
             return (dx,) + (None,) * 9
         if dy is None:                       # only the pass-through branch was used
+            note_done(ctx.noted)
             return (as_act(dpass, x.dtype) if dpass is not None else None,) + (None,) * 9
         dy = as_act(dy, x.dtype)
         addend = as_act(dpass, x.dtype) if dpass is not None else None
         dx, dgamma, dbeta = _bn_backward(dy, x, mr, g, b, ctx.d, addend=addend, need_dx=ctx.needs_input_grad[0],
                                          need_params=ctx.needs_input_grad[1], gbuf=live_grad_buf(gamma),
                                          bbuf=live_grad_buf(beta))
+        note_done(ctx.noted)
         return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
@@ -603,6 +705,7 @@ class BnAddFn(Function):
              C.byref(chb) if chb is not None else None, C.byref(d), ptr(out), ptr(stats_out), stream_ptr())
         ctx.d = d
         ctx.slope = slope
+        ctx.noted = note_use(ctx, ((2, ga_p), (3, ba_p), (7, gb_p), (8, bb_p)))
         ctx.save_for_backward(a if mra is not None else None, mra, ga, ba, b if mrb is not None else None, mrb, gb, bb,
                               out if slope != 1.0 else None, ga_p, ba_p, gb_p, bb_p)
         return out
@@ -646,6 +749,7 @@ class BnAddFn(Function):
                                         bbuf=live_grad_buf(bb_p))
         elif ctx.needs_input_grad[1]:
             db = dpre
+        note_done(ctx.noted)
         return da, db, dga, dba, None, None, None, dgb, dbb, None, None, None, None, None, None
 
 
@@ -773,6 +877,7 @@ class LinearFn(Function):
         call("vg_linear_forward", ptr(x), ptr(w), ptr(b), m, n, k, vg_dtype(wdtype), float(slope), ptr(y), s)
         ctx.dims, ctx.slope, ctx.wdtype, ctx.has_bias = (m, n, k), slope, wdtype, bias is not None
         ctx.weight_ref, ctx.bias_ref = weight, bias
+        ctx.noted = note_use(ctx, ((1, weight), (2, bias)))
         ctx.save_for_backward(x, w, y if slope != 1.0 else None, weight)
         return y
 
@@ -804,6 +909,7 @@ class LinearFn(Function):
             call("vg_linear_wgrad", ptr(x), ptr(dy), m, n, k, vg_dtype(ctx.wdtype), ptr(dw), ptr(db), s)
             if fused:
                 dw = db = None
+        note_done(ctx.noted)
         return dx, dw, db, None, None
 
 
@@ -845,6 +951,7 @@ def linear(x, weight, bias, slope, wdtype):
         if gb is not None:
             wv._vg_grad_buf = gb.view(n, k, 1, 1)      # wgrad accumulates straight into the flat buffer
             wv._vg_owner = weight                      # ... while weight.grad still IS that buffer (live_grad_buf)
+        wv._vg_packs = getattr(weight, "_vg_packs", None)
         y = conv(xa, wv, bias, geom=ConvGeom(1, 1, 0, False), out_dtype=torch.float32)
         if slope != 1.0:
             y = LeakyReluFn.apply(y, slope)

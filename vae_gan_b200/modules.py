@@ -80,8 +80,9 @@ class SpectralNormConv2d(_NoForward, nn.Conv2d):
 
 def _conv_apply(mod, x, geom, *, colscale=None, stats_out=None, training=True, out_dtype=None):
     if isinstance(mod, SpectralNormConv2d):
+        # `_vg_sn`: (sigma, u, v) of the batched power iteration the enclosing Discriminator ran for this forward
         return VF.conv(x, mod.weight_orig, mod.bias, geom=geom, sn=(mod.weight_u, mod.weight_v), colscale=colscale,
-                       stats_out=stats_out, training=training, out_dtype=out_dtype)
+                       stats_out=stats_out, training=training, out_dtype=out_dtype, sn_pre=getattr(mod, "_vg_sn", None))
     return VF.conv(x, mod.weight, mod.bias, geom=geom, colscale=colscale, stats_out=stats_out, training=training,
                    out_dtype=out_dtype)
 
@@ -313,10 +314,20 @@ class Discriminator(nn.Module):
             tr = self.training
             slope = self.activation_fun.negative_slope
             c1 = self.bn1.num_features
-            s1 = _new_stats(c1, x.device, tr)
-            out = _conv_apply(self.conv1, x, ConvGeom(3, self.num_stride_conv1, 1, False), stats_out=s1, training=tr)
-            out = VF.bn_act(out, self.bn1, slope=slope, training=tr, sums=s1)
-            out = self.res_layers(out)
+            # ONE batched power iteration for every spectral-normed convolution of this forward (the hooks of the
+            # reference fire once per module call, in any order: the weights are independent)
+            sn_convs = [m for m in self.res_layers.modules() if isinstance(m, SpectralNormConv2d)]
+            pre = VF.spectral_norm_batched([(m.weight_orig, m.weight_u, m.weight_v) for m in sn_convs], tr)
+            for m, p in zip(sn_convs, pre):
+                m._vg_sn = p
+            try:
+                s1 = _new_stats(c1, x.device, tr)
+                out = _conv_apply(self.conv1, x, ConvGeom(3, self.num_stride_conv1, 1, False), stats_out=s1, training=tr)
+                out = VF.bn_act(out, self.bn1, slope=slope, training=tr, sums=s1)
+                out = self.res_layers(out)
+            finally:
+                for m in sn_convs:
+                    m._vg_sn = None
             out = VF.AvgPoolFlattenFn.apply(out, 4)
             wd = VF.config.compute_dtype
             out = VF.linear(out, self.linear_1.weight, self.linear_1.bias, slope, wd)

@@ -14,6 +14,7 @@ data-parallel all-reduce is one NCCL call per network, and the optimizer is one 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -57,6 +58,112 @@ class FlatParams:
     def set_requires_grad(self, flag: bool):
         for p in self.params:
             p.requires_grad_(flag)
+
+
+class WeightPacks:
+    """The GEMM-layout copies (`pack_kn`, `pack_nk`, compute dtype) of every convolution / Linear weight of one network
+    in persistent buffers, re-made by ONE batched launch (functional.pack_weights_batched) instead of one pack kernel per
+    layer per forward.  ConvFn picks them up through `weight._vg_packs` while a trainer iteration is active; the
+    spectral norm (a per-forward scalar) is applied in the convolution epilogue, so the discriminator's three forwards of
+    an iteration share the packs made after its optimizer step."""
+
+    def __init__(self, net: nn.Module, dtype):
+        self.dtype = dtype
+        self.items = []
+        for m in net.modules():
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                w = m.weight_orig if isinstance(m, M.SpectralNormConv2d) else m.weight
+                transposed = isinstance(m, nn.ConvTranspose2d)
+                wv = w
+            elif isinstance(m, nn.Linear) and dtype == torch.bfloat16 and m.in_features % 64 == 0 and m.out_features % 64 == 0:
+                w, transposed = m.weight, False           # runs as a 1x1 convolution on the tensor cores (functional.linear)
+                wv = w.view(m.out_features, m.in_features, 1, 1)
+            else:
+                continue
+            kn = torch.empty(w.numel(), dtype=dtype, device=w.device)
+            nk = torch.empty(w.numel(), dtype=dtype, device=w.device)
+            w._vg_packs = (kn, nk, dtype)
+            self.items.append((wv.detach(), kn, nk, transposed))
+        self.table = None
+
+    def repack(self):
+        self.table = VF.pack_weights_batched(self.items, self.dtype)
+
+
+class GradBuckets:
+    """Bucketed, backward-overlapped gradient all-reduce over one network's flat gradient buffer (SURVEY.md section 8e,
+    collective 2; north_star: "bucketed NCCL allreduce ... overlapped with backward on side streams").
+
+    The flat buffer is cut into contiguous buckets of ~`bucket_mb` in REVERSE parameter order (the order in which
+    the backward finishes them: the discriminator's Linear layers - 80 % of its bytes - come first).  Every Function
+    that accumulates a weight gradient into the flat buffer reports `use` at forward and `done` at backward
+    (functional.note_use / note_done); when the last pending contribution of a bucket has been ENQUEUED on the compute
+    stream, an event is recorded there, the communication stream waits for it and launches NCCL's all-reduce of that
+    bucket, so the transfer runs under the remaining backward kernels.  `flush()` (called where the un-overlapped
+    all-reduce used to be) reduces whatever is left and makes the compute stream wait for the communication stream.
+    All of it is captured in the iteration's CUDA graph as a fork/join of the two streams."""
+
+    def __init__(self, flat: "FlatParams", pg, comm_stream, bucket_mb: float = 25.0):
+        self.flat, self.pg, self.comm = flat, pg, comm_stream
+        cap = int(bucket_mb * (1 << 20) / 4)
+        self.ranges = []               # (start, end) element ranges of flat.g, in launch order
+        self.bucket_of = {}            # id(param) -> bucket index
+        end = flat.total
+        cur_start, cur_end, members = end, end, []
+        for p, o in zip(reversed(flat.params), reversed(flat.offsets)):
+            if cur_end - o > cap and members:
+                self.ranges.append((cur_start, cur_end))
+                for q in members:
+                    self.bucket_of[id(q)] = len(self.ranges) - 1
+                cur_end, members = cur_start, []
+            cur_start = o
+            members.append(p)
+        if members:
+            self.ranges.append((cur_start, cur_end))
+            for q in members:
+                self.bucket_of[id(q)] = len(self.ranges) - 1
+        self.pending = [0] * len(self.ranges)
+        self.sent = [False] * len(self.ranges)
+        self.armed = False
+
+    def begin(self):
+        """Start of a forward whose backward will be overlapped."""
+        self.pending = [0] * len(self.ranges)
+        self.sent = [False] * len(self.ranges)
+        self.armed = True
+
+    def use(self, param):
+        if self.armed:
+            b = self.bucket_of.get(id(param))
+            if b is not None:
+                self.pending[b] += 1
+
+    def done(self, param):
+        if not self.armed:
+            return
+        b = self.bucket_of.get(id(param))
+        if b is None:
+            return
+        self.pending[b] -= 1
+        if self.pending[b] == 0 and not self.sent[b]:
+            self._send(b)
+
+    def _send(self, b):
+        self.sent[b] = True
+        s, e = self.ranges[b]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.comm.wait_event(ev)
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(self.flat.g[s:e], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def flush(self):
+        """Reduce every bucket not sent yet (e.g. parameters without a fused gradient path), then join the streams."""
+        for b in range(len(self.ranges)):
+            if not self.sent[b]:
+                self._send(b)
+        torch.cuda.current_stream().wait_stream(self.comm)
+        self.armed = False
 
 
 class VaeGanTrainer:
@@ -111,6 +218,21 @@ class VaeGanTrainer:
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
                 if int(ok) == 0:
                     self.peer = None
+        # persistent weight packs, re-made by one batched launch per network (VG_PACK_CACHE=0: per-layer packs as before)
+        self.packs_g = self.packs_d = None
+        if os.environ.get("VG_PACK_CACHE", "1") == "1":
+            self.packs_g = WeightPacks(generator, VF.config.compute_dtype)
+            self.packs_d = WeightPacks(discriminator, VF.config.compute_dtype)
+        # data parallel: bucketed gradient all-reduce on a side stream, overlapped with the backward (GradBuckets).
+        # The gradient-penalty mode accumulates part of its gradients through stock autograd (double backward), so it
+        # keeps the single all-reduce after the backward.
+        self.buckets_g = self.buckets_d = None
+        import os as _os
+        if self.world > 1 and _os.environ.get("VG_GRAD_BUCKETS", "1") == "1" and loss_mode != "wgan_gp":
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+            mb = float(_os.environ.get("VG_BUCKET_MB", "25"))
+            self.buckets_g = GradBuckets(self.fg, process_group, self.comm_stream, mb)
+            self.buckets_d = GradBuckets(self.fd, process_group, self.comm_stream, mb)
         # num_batches_tracked of every BatchNorm: G's are used once per iteration, D's three times
         self._nbt_g = [m.num_batches_tracked for m in generator.modules() if isinstance(m, nn.BatchNorm2d)]
         self._nbt_d = [m.num_batches_tracked for m in discriminator.modules() if isinstance(m, nn.BatchNorm2d)]
@@ -120,12 +242,17 @@ class VaeGanTrainer:
         VF.optimizer_step(flat.p, flat.g, flat.m, flat.v, kind=self.opt_kind, lr=self.lr, betas=self.betas,
                           weight_decay=self.weight_decay, clamp=clamp, step_tensor=self.opt_step)
 
-    def _allreduce(self, flat: FlatParams):
+    def _allreduce(self, flat: FlatParams, buckets: Optional[GradBuckets] = None):
         import os
         if os.environ.get("VG_DIAG_NO_GRAD_AR", "0") == "1":     # timing diagnosis only (wrong numerics)
+            if buckets is not None:
+                buckets.armed = False
             return
         if self.world > 1:
-            dist.all_reduce(flat.g, op=dist.ReduceOp.SUM, group=self.pg)
+            if buckets is not None:
+                buckets.flush()          # most buckets were launched from inside the backward already
+            else:
+                dist.all_reduce(flat.g, op=dist.ReduceOp.SUM, group=self.pg)
 
     def _step_impl(self, real: torch.Tensor, g_step: bool = True):
         dev = self.device
@@ -145,6 +272,9 @@ class VaeGanTrainer:
         if self.peer is not None:
             self.peer.reset()
         VF.arena.begin(dev)           # ONE memset for every fp64 accumulator of the iteration
+        if self.packs_g is not None:  # (also picks up weights modified from outside between two iterations)
+            self.packs_g.repack()
+            self.packs_d.repack()
         try:
             return self._iteration(real, adv_mode, g_step)
         finally:
@@ -157,10 +287,17 @@ class VaeGanTrainer:
         with M._scope():
             with M._scope():          # depth >= 1 everywhere: modules hand over internal activations
                 # ---- generator forward (graph kept for the G step) ----
+                if self.buckets_g is not None and g_step:
+                    self.buckets_g.begin()
+                    VF.config.grad_tracker = self.buckets_g
                 gen, mu, log_var = self.G(real)
+                VF.config.grad_tracker = None
                 # ---- discriminator step ----
                 self.fd.set_requires_grad(True)
                 self.fd.zero_grad()
+                if self.buckets_d is not None and os.environ.get("VG_DIAG_NO_GRAD_AR", "0") != "1":
+                    self.buckets_d.begin()
+                    VF.config.grad_tracker = self.buckets_d
                 d_real = self.D(real)
                 d_fake = self.D(gen.detach())
                 d_total, d_rl, d_fl = VF.DiscriminatorLossFn.apply(d_real, d_fake, adv_mode)
@@ -176,8 +313,11 @@ class VaeGanTrainer:
                     # a mean over the LOCAL samples: 1/world of it is this rank's share of the global mean
                     d_total = d_total + (self.lambda_gp / self.world) * gp_term
                 d_total.backward()
-                self._allreduce(self.fd)
+                VF.config.grad_tracker = None
+                self._allreduce(self.fd, self.buckets_d)
                 self._opt(self.fd, self.clip)
+                if self.packs_d is not None and g_step:
+                    self.packs_d.repack()          # D(gen) below runs with the UPDATED discriminator (README.md:816)
                 # ---- generator step (README.md:812: every n_critics-th iteration) ----
                 d_gen = None
                 if g_step:
@@ -186,8 +326,10 @@ class VaeGanTrainer:
                     d_gen = self.D(gen)
                     g_total, recon, kl, adv = VF.GeneratorLossFn.apply(gen, real, mu, log_var, d_gen, adv_mode,
                                                                        self.weights[0], self.weights[1], self.weights[2])
+                    VF.config.grad_tracker = self.buckets_g          # G's uses were counted during its forward
                     g_total.backward()
-                    self._allreduce(self.fg)
+                    VF.config.grad_tracker = None
+                    self._allreduce(self.fg, self.buckets_g)
                     self._opt(self.fg, 0.0)
                     self.fd.set_requires_grad(True)
         self.losses = dict(d_loss=d_total.detach(), real_loss=d_rl.detach(), fake_loss=d_fl.detach())
