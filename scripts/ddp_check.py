@@ -89,14 +89,20 @@ def main():
         lim = 2e-3 if cdt == torch.float32 else 0.08
         tol_pre = 2e-5 if cdt == torch.float32 else 2e-2
         tol_post = 5e-3 if cdt == torch.float32 else 5e-2
-        gtol = 2e-3 if cdt == torch.float32 else 5e-2      # stated bound on the first-step gradient rel-L2 between partitions
+        # Stated bounds on the first-step gradient rel-L2 between the 2-rank and the 1-rank run.  fp32: 2e-3.  bf16: G 5e-3;
+        # D 1e-1 - D's gradient at random initialisation amplifies bf16 rounding noise to ~1e-1 against the exact gradient
+        # (tests/test_gpu_round2.py::test_train_step_bs64_bf16_flat_tolerance: ours and torch's bf16 autocast both), and a
+        # different partition de-correlates the roundings (different fp32 summation order -> a few bf16 ties break the
+        # other way -> saturates at the bf16 noise floor within a few layers), so two bf16 runs differ by that much
+        gtol = 2e-3 if cdt == torch.float32 else 1e-1
+        gtol_g = 2e-3 if cdt == torch.float32 else 5e-3
         if opt == "rmsprop":
             # RMSprop's first steps move EVERY element by ~10*lr*sign(g) (v = 0.01 g^2) and the clamp keeps all of D
             # within +-0.01, so elements whose gradient is summation-order noise flip freely in any implementation
             # and later steps diverge chaotically; judge the first-step gradients and D's parameters instead
-            params_ok = gl2_g <= gtol and gl2_d <= gtol and frac_d <= lim
+            params_ok = gl2_g <= gtol_g and gl2_d <= gtol and frac_d <= lim
         else:
-            params_ok = frac_g <= lim and frac_d <= lim and gl2_d <= gtol and gl2_g <= gtol
+            params_ok = frac_g <= lim and frac_d <= lim and gl2_d <= gtol and gl2_g <= gtol_g
         ok = ok and worst_pre <= tol_pre and worst <= tol_post and params_ok and same
     if rank == 0:
         print(json.dumps(dict(world=world, ok=ok, **results)))

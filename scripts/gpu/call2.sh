@@ -21,6 +21,11 @@ for b in 64 32; do
 done
 VG_PACK_CACHE=0 timeout 600 python bench.py --steps 20 --warmup 5 --global-batch 32 --skip-cpu-baseline --skip-lib-baseline > gpurun_out/c2_bench_b32_nocache.log 2>&1
 python -c "import json;d=json.loads(open('gpurun_out/c2_bench_b32_nocache.log').read().strip().splitlines()[-1]);print('b32 nocache',d['value'],d['ms_per_step'],d['launches_per_step'])"
+for b in 256 64; do
+VG_TC_FUSE_STATS=0 timeout 600 python bench.py --steps 20 --warmup 5 --global-batch $b --skip-cpu-baseline --skip-lib-baseline > gpurun_out/c2_bench_b${b}_nofuse.log 2>&1
+python -c "import json;d=json.loads(open('gpurun_out/c2_bench_b${b}_nofuse.log').read().strip().splitlines()[-1]);print('b$b nofuse',d['value'],d['ms_per_step'],d['launches_per_step'])"
+done
+timeout 300 python scripts/sweep_conv.py > gpurun_out/c2_sweep_conv.txt 2>&1; tail -20 gpurun_out/c2_sweep_conv.txt
 for b in 64 32; do
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/c2_launches_b$b.csv python scripts/profile_step.py $b > gpurun_out/c2_ncu_b$b.log 2>&1
 python scripts/summarize_launches.py gpurun_out/c2_launches_b$b.csv > gpurun_out/c2_launches_b${b}_summary.txt 2>&1

@@ -39,7 +39,7 @@ def timeit(fn, iters=8):
     return sum(ts[1:-1]) / (len(ts) - 2)
 
 print(f"batch {B}  VG_TC_BN={os.environ.get('VG_TC_BN', 'auto')}")
-tot = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
+tot = {"fwd": 0.0, "fwd+stats": 0.0, "dgrad": 0.0, "wgrad": 0.0}
 for name, cin, cout, h, k, st, pad, tr in SHAPES:
     geom = VF.ConvGeom(k, st, pad, tr)
     x = VF.as_act(torch.randn(B, cin, h, h, generator=g).to(dev), torch.bfloat16)
@@ -55,8 +55,10 @@ for name, cin, cout, h, k, st, pad, tr in SHAPES:
     wsb = torch.empty(w.numel(), dtype=torch.float32, device=dev)
     flops = 2.0 * B * (h * h if tr else ho * wo) * cin * cout * k * k
     t_f = timeit(lambda: _lib.call("vg_conv_forward", C.byref(d), x.data_ptr(), pk.data_ptr(), pn.data_ptr(), None, None, y.data_ptr(), None, s))
+    st = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+    t_fs = timeit(lambda: _lib.call("vg_conv_forward", C.byref(d), x.data_ptr(), pk.data_ptr(), pn.data_ptr(), None, None, y.data_ptr(), st.data_ptr(), s))
     t_d = timeit(lambda: _lib.call("vg_conv_dgrad", C.byref(d), dy.data_ptr(), pk.data_ptr(), pn.data_ptr(), dx.data_ptr(), s))
     t_w = timeit(lambda: _lib.call("vg_conv_wgrad", C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), None, wsb.data_ptr(), s))
-    tot["fwd"] += t_f; tot["dgrad"] += t_d; tot["wgrad"] += t_w
-    print(f"{name:26s} {flops/1e9:7.1f} GF  fwd {t_f*1e3:7.1f} us {flops/t_f/1e9:7.0f} TF/s | dgrad {t_d*1e3:7.1f} us {flops/t_d/1e9:7.0f} | wgrad {t_w*1e3:7.1f} us {flops/t_w/1e9:7.0f}")
+    tot["fwd"] += t_f; tot["fwd+stats"] += t_fs; tot["dgrad"] += t_d; tot["wgrad"] += t_w
+    print(f"{name:26s} {flops/1e9:7.1f} GF  fwd {t_f*1e3:7.1f} us {flops/t_f/1e9:7.0f} TF/s (+BN stats {t_fs*1e3:7.1f} us) | dgrad {t_d*1e3:7.1f} us {flops/t_d/1e9:7.0f} | wgrad {t_w*1e3:7.1f} us {flops/t_w/1e9:7.0f}")
 print("sum ms", {k: round(v, 3) for k, v in tot.items()})

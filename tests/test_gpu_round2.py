@@ -348,9 +348,12 @@ def test_stock_optimizer_after_trainer_gets_real_gradients():
             if net is D:
                 opt.zero_grad()                        # set_to_none=True: p.grad no longer is the flat view
             net(x).sum().backward()
+        gmax = max(float(q.grad.abs().max()) for q in D2.parameters())
         for (k, p), (_, q) in zip(D.named_parameters(), D2.named_parameters()):
             assert p.grad is not None, f"{k}: gradient swallowed by the hidden flat buffer"
             assert q.grad is not None
+            if float(q.grad.abs().max()) <= 1e-6 * gmax:
+                continue          # zero in exact arithmetic (a BatchNorm bias that only feeds BatchNorms): rounding noise
             assert_close(p.grad, q.grad, 1e-5, k)
         # and a second backward (same state, same masks) accumulates the ordinary way
         D.load_state_dict(sd0)
@@ -358,6 +361,8 @@ def test_stock_optimizer_after_trainer_gets_real_gradients():
         g0 = {k: p.grad.clone() for k, p in D.named_parameters()}
         D(x).sum().backward()
         for k, p in D.named_parameters():
+            if float(g0[k].abs().max()) <= 1e-6 * gmax:
+                continue
             assert_close(p.grad, 2 * g0[k], 2e-5, k + " (accumulated)")
 
 
@@ -534,3 +539,110 @@ def test_input_pipeline_double_buffering_and_edge_cases():
     out = v.normalize_images(const.to(dev()))
     assert bool(torch.isnan(out).all())
     assert pipe.h2d_bytes == B * S * S
+
+
+# ------------------------------------------------------------------------------------------------
+# batched entry points
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_batched_pack_matches_per_layer_pack_bit_exact(dtype):
+    """vg_conv_pack_weights_batched (every weight of a network in one launch) == vg_conv_pack_weights per layer, bit for
+    bit, for 3x3 / 4x4-transposed / 1x1 / Linear-as-1x1 / 5x5 (generic tap count) / single-channel / ragged shapes."""
+    vf = VF()
+    from vae_gan_b200 import _lib
+    g = torch.Generator().manual_seed(77)
+    shapes = [((128, 64, 3, 3), False), ((256, 128, 4, 4), True), ((256, 128, 1, 1), False), ((1024, 18432, 1, 1), False),
+              ((24, 40, 5, 5), False), ((64, 1, 3, 3), False), ((1, 64, 3, 3), False), ((100, 72, 3, 3), False), ((72, 100, 4, 4), True),
+              ((512, 512, 3, 3), False)] + [((64, 64, 3, 3), False)] * 30          # > VG_PACK_MAX items: two launches
+    items, want = [], []
+    for shape, transposed in shapes:
+        w = torch.randn(shape, generator=g).to(dev())
+        kn = torch.empty(w.numel(), dtype=dtype, device=dev())
+        nk = torch.empty(w.numel(), dtype=dtype, device=dev())
+        items.append((w, kn, nk, transposed))
+        c_in, c_out = (shape[0], shape[1]) if transposed else (shape[1], shape[0])
+        k = shape[2]
+        d, _, _ = vf._conv_desc((1, c_in, 8, 8), c_out, vf.ConvGeom(k, 1, k // 2 if not transposed else 1, transposed), dtype, dtype)
+        rkn, rnk = torch.empty_like(kn), torch.empty_like(nk)
+        _lib.call("vg_conv_pack_weights", C.byref(d), w.data_ptr(), None, rkn.data_ptr(), rnk.data_ptr(), _lib.stream_ptr())
+        want.append((rkn, rnk))
+    vf.pack_weights_batched(items, dtype)
+    for i, ((w, kn, nk, _), (rkn, rnk)) in enumerate(zip(items, want)):
+        assert torch.equal(kn, rkn), f"item {i} {tuple(w.shape)}: pack_kn"
+        assert torch.equal(nk, rnk), f"item {i} {tuple(w.shape)}: pack_nk"
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_batched_spectral_norm_matches_oracle(training):
+    """vg_spectral_norm_sigma_batched: u, v, sigma of all weights at once vs the oracle's restatement of the legacy hook."""
+    vf = VF()
+    g = torch.Generator().manual_seed(12)
+    ws, P = [], {}
+    for i, (rows, cin, k) in enumerate([(128, 64, 3), (128, 128, 3), (128, 64, 1), (256, 128, 3), (512, 512, 3), (16, 6, 3)]):
+        w = torch.randn(rows, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+        u = F.normalize(torch.randn(rows, generator=g), dim=0)
+        v = F.normalize(torch.randn(cin * k * k, generator=g), dim=0)
+        P[f"c{i}.weight_orig"], P[f"c{i}.weight_u"], P[f"c{i}.weight_v"] = w.clone(), u.clone(), v.clone()
+        ws.append((w.to(dev()), u.to(dev()), v.to(dev())))
+    out = vf.spectral_norm_batched(ws, training)
+    for i, ((w, u, v), (sigma, u_s, v_s)) in enumerate(zip(ws, out)):
+        wn = O.spectral_normed_weight(P, f"c{i}", training)
+        sig_ref = float((P[f"c{i}.weight_orig"].flatten()[0] / wn.flatten()[0]))
+        assert abs(float(sigma) - sig_ref) <= 2e-6 * abs(sig_ref), (i, float(sigma), sig_ref)
+        assert_close(u, P[f"c{i}.weight_u"], 2e-6, f"u{i}")
+        assert_close(v, P[f"c{i}.weight_v"], 2e-6, f"v{i}")
+        assert torch.equal(u_s, u) and torch.equal(v_s, v), "saved copies"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,k", [((2, 512, 24, 24), 4), ((3, 64, 16, 16), 2), ((2, 16, 10, 10), 4)])
+def test_avgpool_flatten_shapes(dtype, shape, k):
+    """F.avg_pool2d(k) + view(B, -1) (README.md:471-473), forward and backward: the row-staged backward kernel and the
+    per-pixel fallback (10 % 4 != 0: border rows get zero gradient)."""
+    vf = VF()
+    g = torch.Generator().manual_seed(4)
+    xa = vf.as_act(torch.randn(shape, generator=g).to(dev()), dtype)
+    xi = xa.detach().clone().requires_grad_(True)
+    y = vf.AvgPoolFlattenFn.apply(xi, k)
+    gy = torch.randn(y.shape, generator=g).to(dev())
+    y.backward(gy)
+    xr = xa.detach().float().clone().requires_grad_(True)
+    yr = F.avg_pool2d(xr, k).reshape(shape[0], -1)
+    yr.backward(gy)
+    assert_close(y, yr, 1e-6, "pool")
+    assert_close(xi.grad, xr.grad, 1e-6 if dtype == torch.float32 else 4e-3, "dpool")
+
+
+def test_conv_sigma_in_epilogue_equals_sigma_in_pack():
+    """vg_conv_forward_scaled / vg_conv_dgrad_scaled (spectral norm applied in the epilogue, what the trainer's cached packs
+    use) against the sigma-folded pack path, tensor-core and CUDA-core kernels: same result within bf16 / fp32 rounding."""
+    vf = VF()
+    from vae_gan_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    for dtype, tol in ((torch.bfloat16, 1e-2), (torch.float32, 2e-6)):
+        for (cin, cout, k, st, n, h) in [(64, 128, 3, 1, 2, 16), (128, 256, 3, 2, 2, 16), (128, 256, 1, 2, 2, 16), (8, 16, 3, 1, 2, 8)]:
+            x = vf.as_act(torch.randn(n, cin, h, h, generator=g).to(dev()), dtype)
+            w = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(dev())
+            sigma = torch.tensor([1.7], device=dev())
+            geom = vf.ConvGeom(k, st, k // 2, False)
+            d, ho, wo = vf._conv_desc(x.shape, cout, geom, dtype, dtype)
+            packs = []
+            for sg in (sigma, None):
+                kn = torch.empty(w.numel(), dtype=dtype, device=dev())
+                nk = torch.empty(w.numel(), dtype=dtype, device=dev())
+                _lib.call("vg_conv_pack_weights", C.byref(d), w.data_ptr(), sg.data_ptr() if sg is not None else None, kn.data_ptr(),
+                          nk.data_ptr(), _lib.stream_ptr())
+                packs.append((kn, nk))
+            y0 = vf.empty_act(n, cout, ho, wo, dtype, dev())
+            y1 = torch.empty_like(y0)
+            _lib.call("vg_conv_forward", C.byref(d), x.data_ptr(), packs[0][0].data_ptr(), packs[0][1].data_ptr(), None, None, y0.data_ptr(),
+                      None, _lib.stream_ptr())
+            _lib.call("vg_conv_forward_scaled", C.byref(d), x.data_ptr(), packs[1][0].data_ptr(), packs[1][1].data_ptr(), None, None,
+                      sigma.data_ptr(), 0, y1.data_ptr(), None, _lib.stream_ptr())
+            assert_close(y1, y0, tol, f"fwd {cin}->{cout} k{k} s{st} {dtype}")
+            dy = vf.as_act(torch.randn(n, cout, ho, wo, generator=g).to(dev()), dtype)
+            dx0, dx1 = torch.empty_like(x), torch.empty_like(x)
+            _lib.call("vg_conv_dgrad", C.byref(d), dy.data_ptr(), packs[0][0].data_ptr(), packs[0][1].data_ptr(), dx0.data_ptr(), _lib.stream_ptr())
+            _lib.call("vg_conv_dgrad_scaled", C.byref(d), dy.data_ptr(), packs[1][0].data_ptr(), packs[1][1].data_ptr(), sigma.data_ptr(), 0,
+                      dx1.data_ptr(), _lib.stream_ptr())
+            assert_close(dx1, dx0, tol, f"dgrad {cin}->{cout} k{k} s{st} {dtype}")

@@ -59,6 +59,7 @@ struct Args {
   int cg;                // channel groups per row (c / 8; 1 when folded)
   int tpb;               // consumer threads in use = (256 / cg) * cg
   int fold;              // single-channel tensor viewed as [rows / 8][8]
+  int reverse;           // walk the tiles from the END of the tensor (see bn_stream_reverse())
   int hw;
   Chan A, B;
   // reductions
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_stream_kernel(const __grid_con
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       ptx::mbar_wait(&empty[stage], phase ^ 1u);
       if (ptx::elect_one()) {
-        const long long v0 = tile * tile_vecs;
+        const long long v0 = (a.reverse ? a.ntiles - 1 - tile : tile) * tile_vecs;
         const long long nv = min((long long)tile_vecs, a.nvec - v0);
         const uint32_t bytes = (uint32_t)(nv * VB);
         ptx::mbar_arrive_expect_tx(&full[stage], bytes * NIN);
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_stream_kernel(const __grid_con
 #pragma unroll
       for (int k = 0; k < KT; ++k) {
         const int lv = tid + k * a.tpb;
-        const long long v = tile * tile_vecs + lv;
+        const long long v = (a.reverse ? a.ntiles - 1 - tile : tile) * tile_vecs + lv;
         if (v < a.nvec) {
           Vec8<T> x0, x1;
           x0.load(reinterpret_cast<const T*>(sb + (size_t)lv * VB));
@@ -421,6 +422,16 @@ static int launch_drop(const Args& a, cudaStream_t s) {
 
 }  // namespace bs
 
+// L2 reuse between consecutive passes over the same tensor: a producer (convolution, previous pass) leaves the END of
+// the tensor it wrote / read last in the 126 MB L2.  The reduction-type passes (statistics, backward reduce, residual
+// add) therefore walk the tensor backwards - they start on the freshest lines - and the apply passes that follow them
+// walk forwards, starting on what the reduction touched last.  VG_BN_REVERSE=0 disables it (A/B).
+static bool bn_stream_reverse() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VG_BN_REVERSE"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
 bool bn_stream_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("VG_BN_STREAM"); v = e ? atoi(e) : 1; }
@@ -504,6 +515,7 @@ int bn_stream_stats(const void* x, const VgBnDesc* d, double* sums, cudaStream_t
   a.in0 = x;
   a.sums_out = sums;
   a.thr16 = 0;
+  a.reverse = bn_stream_reverse();
   return dispatch<bs::kStats>(a, d, s);
 }
 
@@ -527,6 +539,7 @@ int bn_stream_bwd_reduce(const void* dy, const void* x, const float* mean_rstd, 
   a.A.gamma = gamma;
   a.A.beta = beta;
   a.sums_out = sums;
+  a.reverse = bn_stream_reverse();
   return dispatch<bs::kBwdReduce>(a, d, s);
 }
 
@@ -564,6 +577,7 @@ int bn_stream_add(const void* x0, const VgBnChannel* bn_a, const void* x1, const
   set_chan(a.B, bn_b, d->training);
   a.sums_out = stats;
   a.thr16 = 0;
+  a.reverse = bn_stream_reverse();
   if (stats != nullptr) return dispatch<bs::kAddStats>(a, d, s);
   return dispatch<bs::kAdd>(a, d, s);
 }

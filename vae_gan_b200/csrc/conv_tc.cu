@@ -72,24 +72,52 @@ struct alignas(64) TcWgradParams {
   float* dw;
 };
 
-constexpr int kStatsSmemBytes = 4 * 16 * 33 * 4;   // per epilogue warp: a [16][33] fp32 transpose buffer
 constexpr int kTcThreads = 256;
 constexpr int kABytes = 128 * 128;   // 128 rows x 64 bf16
+constexpr int kStageBytes = 32 * 64;  // per epilogue warp: 32 rows x 32 bf16 of one output chunk (coalescing transpose)
 
 template <int BN, int MT, int STAGES>
 struct ConvSmem {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 1) * 8 + 16 + 1024 + kStatsSmemBytes;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 1) * 8 + 16 + 1024 + 4 * kStageBytes + 16;
 };
 
 
-// Finishes one 32-column chunk of one accumulator row per thread: bias, Dropout2d column scale, store
-// (bf16 / fp32 / split-K atomics / single channel) and - when `tbuf` is given - adds this warp's
-// per-column sum and sum of squares of the values AS STORED to (st_sum, st_sq): lane l owns column l.
-// Those feed the BatchNorm that follows the convolution (README.md:192), saving a full read of y.
+// Column sums of a 32 x 32 block held one ROW per lane (v[j] = column j): recursive halving over the lane bits - in step H
+// the lanes with bit H set keep the upper H columns of what they hold and receive the lower lanes' share of them (and vice
+// versa), so after the steps 16, 8, 4, 2, 1 lane l holds the sum of column l over all 32 rows.  31 shuffles, all register
+// indices static.  (Round 1 transposed through shared memory instead: 1.5 k shared accesses per chunk, measured +35..60 %.)
+template <int H>
+__device__ __forceinline__ void fold_cols(float (&v)[32], bool up) {
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    const float send = up ? v[k] : v[k + H];
+    const float keep = up ? v[k + H] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+  }
+}
+__device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
+  fold_cols<16>(v, (lane & 16) != 0);
+  fold_cols<8>(v, (lane & 8) != 0);
+  fold_cols<4>(v, (lane & 4) != 0);
+  fold_cols<2>(v, (lane & 2) != 0);
+  fold_cols<1>(v, (lane & 1) != 0);
+  return v[0];
+}
+
+// Finishes one 32-column chunk of one accumulator row per thread: 1/sigma, bias, Dropout2d column scale, store
+// (bf16 / fp32 / split-K vector reductions / single channel) and - with `do_stats` - adds this warp's per-column sum
+// and sum of squares of the values AS STORED to (st_sum, st_sq): lane l owns column l.  Those feed the BatchNorm
+// that follows the convolution (README.md:192), saving a full read of y by a separate statistics kernel.
+//
+// bf16 outputs go through `stage` (a 2 KB per-warp shared-memory buffer) when it is given: lane = pixel row holds 64 B of
+// consecutive channels, so a direct 16-byte store per lane touches 32 different 128-byte lines per instruction - the
+// store path, not the issue rate, bounded the epilogue (8 epilogue warps instead of 4 changed nothing on the 64-wide
+// layers).  The warp writes its 32 x 64 B block into shared memory (XOR-swizzled 16-byte units, conflict-free both ways),
+// reads it back transposed and stores with FOUR consecutive lanes covering one row's 64 bytes: 8 lines per instruction.
 __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint32_t (&r)[32], bool valid, bool add_bias,
-                                               long long opix, int gn, int ncol, bool first_chunk, float* tbuf, int lane,
-                                               float& st_sum, float& st_sq) {
+                                               long long opix, int gn, int ncol, bool first_chunk, bool do_stats, int lane,
+                                               float& st_sum, float& st_sq, uint8_t* stage = nullptr) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -108,7 +136,30 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
   }
-  if (valid) {
+  const bool staged = stage != nullptr && !p.out_f32 && p.ksplit <= 1 && p.n_store != 1;
+  if (staged) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    uint4* srow = reinterpret_cast<uint4*>(stage + lane * 64);
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) srow[q ^ sw] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    __syncwarp();
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 8 + (lane >> 2), q = lane & 3;
+      const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 64 + ((q ^ ((row >> 1) & 3)) << 4));
+      const long long op = __shfl_sync(0xffffffffu, opix, row);
+      const int ok = __shfl_sync(0xffffffffu, (int)valid, row);
+      if (ok) *reinterpret_cast<uint4*>(ob + op * p.n_out + ncol + q * 8) = val;
+    }
+    __syncwarp();                      // the buffer is rewritten by this warp's next chunk
+  } else if (valid) {
     if (p.n_store == 1) {
       // single-channel output (Conv2d C->1 forward / Conv2d 1->C dgrad): only column 0 is real
       // (static register index - a dynamic one would push v[] into local memory)
@@ -142,28 +193,16 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint
       }
     }
   }
-  if (tbuf != nullptr) {
-    float s1 = 0.f, s2 = 0.f;
+  if (do_stats) {
+    float q[32];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      if ((lane >> 4) == half) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = valid ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16_rn(v[j]))) : 0.f;
-          tbuf[(lane & 15) * 33 + j] = a;
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a = tbuf[i * 33 + lane];
-        s1 += a;
-        s2 = fmaf(a, a, s2);
-      }
-      __syncwarp();
+    for (int j = 0; j < 32; ++j) {
+      const float a = valid ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16_rn(v[j]))) : 0.f;
+      v[j] = a;
+      q[j] = a * a;
     }
-    st_sum += s1;
-    st_sq += s2;
+    st_sq += colsum32(q, lane);
+    st_sum += colsum32(v, lane);
   }
 }
 
@@ -186,7 +225,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* stats_buf = reinterpret_cast<float*>(tmem_slot + 4);
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : blockIdx.z];
@@ -292,7 +331,6 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
       ptx::tc_fence_after();
     }
     const bool do_stats = p.stats != nullptr && p.ksplit <= 1 && num_k > 0;
-    float* tbuf = do_stats ? stats_buf + q * 16 * 33 : nullptr;
     float st_s[BN / 32], st_q[BN / 32];
 #pragma unroll
     for (int c = 0; c < BN / 32; ++c) st_s[c] = st_q[c] = 0.f;
@@ -312,7 +350,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
-        epilogue_chunk(p, r, valid, p.ksplit <= 1 || blockIdx.z == 0, opix, gn, ncol0 + c0, c == 0, tbuf, lane, st_s[c], st_q[c]);
+        epilogue_chunk(p, r, valid, p.ksplit <= 1 || blockIdx.z == 0, opix, gn, ncol0 + c0, c == 0, do_stats, lane, st_s[c], st_q[c],
+                       stage_base + q * kStageBytes);
       }
     }
     if (do_stats) {
@@ -350,7 +389,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 template <int BN, int MT, int STAGES, int EW>
 struct ConvPersistSmem {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024 + EW * 16 * 33 * 4;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024 + EW * kStageBytes + 16;
 };
 
 // EW = number of epilogue warps (4 or 8).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so with
@@ -377,7 +416,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
   uint64_t* acc_full = empty + STAGES;       // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* stats_buf = reinterpret_cast<float*>(tmem_slot + 4);
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
@@ -539,7 +578,6 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
     const int nl = row >> (p.tw_log2 + p.th_log2);
     int it = 0;
     const bool do_stats = p.stats != nullptr && p.ksplit <= 1;
-    float* tbuf = do_stats ? stats_buf + ew * 16 * 33 : nullptr;
     float st_s[BN / 32], st_q[BN / 32];
 #pragma unroll
     for (int c = 0; c < BN / 32; ++c) st_s[c] = st_q[c] = 0.f;
@@ -597,7 +635,8 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
-          epilogue_chunk(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, tbuf, lane, st_s[c], st_q[c]);
+          epilogue_chunk(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, do_stats && has_k, lane, st_s[c], st_q[c],
+                         stage_base + ew * kStageBytes);
         }
       }
       if (has_k) {
@@ -632,7 +671,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
 template <int BN, int MT, int STAGES, int EW>
 struct ConvPairSmem {
   static constexpr int kBBytes = (BN / 2) * 128;
-  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024 + EW * kStageBytes + 16;
 };
 
 template <int BN, int MT, int STAGES, int EW>
@@ -655,6 +694,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
   uint64_t* acc_full = empty + STAGES;       // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -788,7 +828,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
     const int yl = (row >> p.tw_log2) & (p.TH - 1);
     const int nl = row >> (p.tw_log2 + p.th_log2);
     int it = 0;
-    float unused_s = 0.f, unused_q = 0.f;
+    // BatchNorm statistics of the stored output, accumulated per lane (= column of the chunk) across this CTA's work
+    // items and flushed with fp64 atomics whenever the N tile changes
+    const bool do_stats = p.stats != nullptr && p.ksplit <= 1;
+    float st_s[BN / 32], st_q[BN / 32];
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) st_s[c] = st_q[c] = 0.f;
+    int st_nt = -1;
+    auto flush_stats = [&]() {
+      if (st_nt < 0) return;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        if ((c % kChunkGroups) != cgrp) continue;
+        const int col = st_nt * BN + c * 32 + lane;
+        if (col < p.n_out) {
+          atomicAdd(p.stats + col, (double)st_s[c]);
+          atomicAdd(p.stats + p.n_out + col, (double)st_q[c]);
+        }
+        st_s[c] = st_q[c] = 0.f;
+      }
+    };
     for (int w = pair; w < n_work; w += n_pairs) {
       int z, nt, g;
       decode(w, z, nt, g);
@@ -800,6 +859,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
       const int tile0 = (g * 2 + (int)rank) * MT;
       const int ncol0 = nt * BN;
       const int as = it & 1;
+      if (do_stats && nt != st_nt) {
+        flush_stats();
+        st_nt = nt;
+      }
       if (has_k) {
         ptx::mbar_wait(&acc_full[as], (uint32_t)((it >> 1) & 1));
         ptx::tc_fence_after();
@@ -824,7 +887,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
-          epilogue_chunk(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, nullptr, lane, unused_s, unused_q);
+          epilogue_chunk(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, do_stats && has_k, lane, st_s[c], st_q[c],
+                         stage_base + ew * kStageBytes);
         }
       }
       if (has_k) {
@@ -834,6 +898,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
         ++it;
       }
     }
+    if (do_stats) flush_stats();
   }
   // neither CTA may retire while the other can still signal its barriers or read its shared memory
   ptx::tc_fence_before();
@@ -1322,14 +1387,19 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   // kernels (parity-tested), but it is OPT-IN (VG_TC_FUSE_STATS=1): measured on B200 the per-chunk smem
   // transposes cost the L2/smem-bound main loop more (+35 % per launch with 8 epilogue warps, +60 % with
   // 4) than the separate 20 us statistics kernel they replace.
-  if (fuse_stats && stats != nullptr && p.ksplit == 1 && n_out % 32 == 0 && use_persist && BN >= 128) {
+  // Round 2 replaced the shared-memory transpose by a 31-shuffle recursive halving per 32 x 32 chunk and enabled it in
+  // every kernel form - measured on B200 (scripts/sweep_conv.py, batch 64) it is STILL a loss: 64->64 @96 74.9 -> 163 us,
+  // 128->128 @96 151 -> 217 us, 512->512 @24 110 -> 125 us, whole step 63.7 -> 68.2 ms, against the 17 us streaming
+  // statistics kernel it replaces: the epilogue warps are the bottleneck of the short-reduction layers and ~350 extra
+  // instructions per chunk double their work.  Kept opt-in (VG_TC_FUSE_STATS=1) and parity-tested.
+  if (fuse_stats && stats != nullptr && p.ksplit == 1 && n_out % 32 == 0 && p.n_store != 1) {
     p.stats = stats;
     if (stats_fused) *stats_fused = true;
   }
   // CTA pairs (cta_group::2) halve the per-SM shared-memory operand reads that bound the narrow tiles
   static int pair_on = -1;
   if (pair_on < 0) { const char* e = getenv("VG_TC_PAIR"); pair_on = e ? atoi(e) : 6; }   // bit0: BN=64, bit1: BN=128, bit2: BN=256
-  if (use_persist && pair_on && p.stats == nullptr && p.n_store != 1) {
+  if (use_persist && pair_on && p.n_store != 1) {
     const int mt = BN == 64 ? 4 : (BN == 128 ? 2 : 1);
     if (grid.x % (2 * mt) == 0 && (pair_on & (BN == 64 ? 1 : (BN == 128 ? 2 : 4)))) {
       if ((rc = make_weight_map(&p.w_map, wpack, (long long)k * k * n_out, in_c, BN / 2))) return rc;
@@ -1343,9 +1413,16 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   }
   static int grp2 = -1;
   if (grp2 < 0) { const char* e = getenv("VG_TC_GROUP"); grp2 = e ? (atoi(e) == 2) : 0; }
+  // 64-wide tiles are EPILOGUE-bound (9 k-blocks of N=64 MMAs per 128 x 64 outputs).  Eight epilogue warps instead of four
+  // (VG_TC_EW64=82: <64,2,4,8>) measured NO gain on B200 (64->64 @96: 74.4 vs 74.9 us): the bound was the store path
+  // (32 lines per store instruction), addressed by the staged, coalesced stores of epilogue_chunk.
+  static int ew64 = -1;
+  if (ew64 < 0) { const char* e = getenv("VG_TC_EW64"); ew64 = e ? atoi(e) : 4; }
   if (use_persist) {
     switch (BN) {
-      case 64: return launch_conv_persist<64, 4, 3, 4, 1>(p, grid, s);
+      case 64:
+        if (ew64 == 82) return launch_conv_persist<64, 2, 4, 8, 1>(p, grid, s);
+        return launch_conv_persist<64, 4, 3, 4, 1>(p, grid, s);
       case 128: return grp2 ? launch_conv_persist<128, 2, 4, 8, 2>(p, grid, s) : launch_conv_persist<128, 2, 4, 8, 1>(p, grid, s);
       case 256: return grp2 ? launch_conv_persist<256, 1, 4, 8, 2>(p, grid, s) : launch_conv_persist<256, 1, 4, 8, 1>(p, grid, s);
       default: break;

@@ -202,7 +202,6 @@ class VaeGanTrainer:
         self.peer = None
         if process_group is not None:
             VF.config.process_group = process_group
-            import os
             if peer_syncbn is None:
                 peer_syncbn = os.environ.get("VG_PEER_SYNCBN", "1") == "1"
             if peer_syncbn and self.world > 1:
@@ -227,10 +226,9 @@ class VaeGanTrainer:
         # The gradient-penalty mode accumulates part of its gradients through stock autograd (double backward), so it
         # keeps the single all-reduce after the backward.
         self.buckets_g = self.buckets_d = None
-        import os as _os
-        if self.world > 1 and _os.environ.get("VG_GRAD_BUCKETS", "1") == "1" and loss_mode != "wgan_gp":
+        if self.world > 1 and os.environ.get("VG_GRAD_BUCKETS", "1") == "1" and loss_mode != "wgan_gp":
             self.comm_stream = torch.cuda.Stream(device=self.device)
-            mb = float(_os.environ.get("VG_BUCKET_MB", "25"))
+            mb = float(os.environ.get("VG_BUCKET_MB", "25"))
             self.buckets_g = GradBuckets(self.fg, process_group, self.comm_stream, mb)
             self.buckets_d = GradBuckets(self.fd, process_group, self.comm_stream, mb)
         # num_batches_tracked of every BatchNorm: G's are used once per iteration, D's three times
@@ -243,7 +241,6 @@ class VaeGanTrainer:
                           weight_decay=self.weight_decay, clamp=clamp, step_tensor=self.opt_step)
 
     def _allreduce(self, flat: FlatParams, buckets: Optional[GradBuckets] = None):
-        import os
         if os.environ.get("VG_DIAG_NO_GRAD_AR", "0") == "1":     # timing diagnosis only (wrong numerics)
             if buckets is not None:
                 buckets.armed = False
