@@ -102,6 +102,38 @@ int vg_conv_forward_scaled(const VgConvDesc* d, const void* x, const void* pack_
                            void* y, double* stats, vg_stream_t stream);
 int vg_conv_dgrad_scaled(const VgConvDesc* d, const void* dy, const void* pack_kn, const void* pack_nk,
                          const float* sigma, int sigma_group_n, void* dx, vg_stream_t stream);
+/* General forward epilogue - what the eval-mode / sampling path (README.md:661-664 decode, :1215-1226
+ * visualize_reconstructions: generator.eval()) needs once the BatchNorms are folded into the weights:
+ *   t  = conv(x, W) / sigma + bias ; t *= colscale ; [t = bf16(t) + residual] ; y = leaky_relu(t, act_slope)
+ *   y2 = leaky_relu(post_scale[c] * y + post_shift[c], post_slope)          (second output, nullable)
+ * so a pre-activation block becomes three convolution launches with no elementwise pass: conv1 carries the folded
+ * bn2 as bias + LeakyReLU, the shortcut carries its folded BatchNorm as bias, conv2 adds the shortcut (`residual`)
+ * and also emits the NEXT block's leaky_relu(bn1(.)) as y2.  act_slope / residual / y2 need a bf16 output on the
+ * tensor-core path (channels % 64 == 0); otherwise VG_EUNSUPPORTED. */
+typedef struct {
+  const float* bias;
+  const float* colscale;
+  const float* sigma;
+  int sigma_group_n;
+  float act_slope;          /* 1 = no activation */
+  const void* residual;     /* nullable; y's shape and dtype */
+  void* y2;                 /* nullable; y's shape and dtype */
+  const float* post_scale;  /* float[c_out], required with y2 */
+  const float* post_shift;
+  float post_slope;
+} VgConvEpilogue;
+int vg_conv_forward_fused(const VgConvDesc* d, const void* x, const void* pack_kn, const void* pack_nk,
+                          const VgConvEpilogue* ep, void* y, double* stats, vg_stream_t stream);
+/* Fold an eval-mode BatchNorm that FOLLOWS a convolution into it (sampling path): w_out = w * s[c_out],
+ * bias_out = beta - running_mean * s (+ s * bias_in), s = gamma / sqrt(running_var + eps).  w in torch layout
+ * ([c_out][c_in][k][k], or [c_in][c_out][k][k] when transposed); inner = elements per (c_out, c_in) pair = k*k. */
+int vg_fold_bn_into_conv(const float* w, const float* bias_in, const float* gamma, const float* beta,
+                         const float* running_mean, const float* running_var, float eps, int c_out, int c_in,
+                         int inner, int transposed, float* w_out, float* bias_out, vg_stream_t stream);
+/* (scale, shift) of an eval-mode BatchNorm as two float[c] vectors: scale = gamma / sqrt(running_var + eps),
+ * shift = beta - running_mean * scale  (the post_scale / post_shift of VgConvEpilogue) */
+int vg_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float eps, int c, float* scale, float* shift, vg_stream_t stream);
 /* dw += x (*) dy in torch's weight layout, fp32 (caller zeroes dw for a fresh gradient);
  * dbias (nullable) += per-channel sum of dy.
  * workspace (nullable): float[kh*kw*c_in*c_out] scratch.  When given, the tensor-core kernel
@@ -198,6 +230,11 @@ int vg_bn_act_backward_apply_fused(const void* dy, const void* x, const float* m
                                    float param_scale, vg_stream_t stream);
 /* dgamma += scale * sum g*xhat, dbeta += scale * sum g (vg_bn_param_grads with the 1/world factor) */
 int vg_bn_param_grads_scaled(const double* sums, int c, float scale, float* dgamma, float* dbeta, vg_stream_t stream);
+/* Eval / sampling path: out = leaky_relu(a + b, d->slope) and, from out AS STORED, out2 = leaky_relu(post_scale[c] *
+ * out + post_shift[c], post_slope) - the residual add of one block (README.md:195) and the next block's eval-mode
+ * bn1 + LeakyReLU (README.md:188-189) in one pass (4 streams instead of 3 + 2). */
+int vg_add_dual_forward(const void* a, const void* b, const float* post_scale, const float* post_shift, float post_slope,
+                        const VgBnDesc* d, void* out, void* out2, vg_stream_t stream);
 /* y = leaky_relu(x) on a flat fp32 tensor (discriminator head, README.md:475-481) */
 int vg_lrelu_forward(const void* x, long long n, int dtype, float slope, void* y, vg_stream_t stream);
 /* dx = dy * (y_ref > 0 ? 1 : slope) */

@@ -41,9 +41,10 @@ def dry(monkeypatch):
     chk = _CallChecker()
     import vae_gan_b200.functional as VF
     import vae_gan_b200.gp as GP
-    import vae_gan_b200.data as DATA
-    for mod in (_lib, VF, GP):
+    import vae_gan_b200.sampling as SA
+    for mod in (_lib, VF, GP, SA):
         monkeypatch.setattr(mod, "call", chk, raising=False)
+    monkeypatch.setattr(SA, "stream_ptr", lambda: 0)
     monkeypatch.setattr(_lib, "ensure_device", lambda device: None)
     monkeypatch.setattr(_lib, "stream_ptr", lambda: 0)
     monkeypatch.setattr(VF, "stream_ptr", lambda: 0)
@@ -138,3 +139,18 @@ def test_input_pipeline_table_and_pack_items(dry):
     assert C.sizeof(_lib.VgPackItem) == 3 * 8 + 4 * 4
     assert C.sizeof(_lib.VgSnItem) == 6 * 8 + 2 * 4
     assert C.sizeof(_lib.VgBnChannel) == 4 * 8 + 8 + 3 * 8 + 2 * 4
+
+
+def test_folded_sampler_host_logic(dry):
+    from vae_gan_b200.sampling import FoldedGenerator
+    with V.compute_dtype(torch.bfloat16):
+        torch.manual_seed(0)
+        G, _ = V.build_vae_gan(feature_size=64, image_size=32)
+        G = G.eval()
+        G.set_is_training(False)
+        fg = FoldedGenerator(G)
+        assert [b.tc for b in fg.enc + fg.dec] == [False, True, True, True, True, False]
+        assert fg.decode(torch.randn(2, 256, 8, 8)).shape == (2, 1, 32, 32)
+        assert fg.encode(torch.rand(2, 1, 32, 32)).shape == (2, 256, 8, 8)
+        assert fg.reconstruct(torch.rand(2, 1, 32, 32)).shape == (2, 1, 32, 32)
+    assert dry.calls.get("vg_fold_bn_into_conv", 0) == 8 and dry.calls.get("vg_conv_forward_fused", 0) > 0

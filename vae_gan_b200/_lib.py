@@ -42,6 +42,11 @@ class VgSnItem(C.Structure):
     _fields_ = [("w", c_vp), ("u", c_vp), ("v", c_vp), ("u_out", c_vp), ("v_out", c_vp), ("sigma", c_vp), ("rows", c_int), ("cols", c_int)]
 
 
+class VgConvEpilogue(C.Structure):
+    _fields_ = [("bias", c_vp), ("colscale", c_vp), ("sigma", c_vp), ("sigma_group_n", c_int), ("act_slope", c_f),
+                ("residual", c_vp), ("y2", c_vp), ("post_scale", c_vp), ("post_shift", c_vp), ("post_slope", c_f)]
+
+
 class VgLossDesc(C.Structure):
     _fields_ = [("n_pix", c_ll), ("n_pix_global", c_ll), ("n_lat", c_ll), ("n_logits", c_int),
                 ("n_logits_global", c_int), ("adv_mode", c_int), ("w_adv", c_f), ("w_recon", c_f),
@@ -67,6 +72,9 @@ _PROTOS = {
     "vg_conv_pack_weights": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "vg_conv_pack_weights_batched": (c_int, [c_vp, c_int, c_int, c_vp]),
     "vg_conv_forward_scaled": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "vg_conv_forward_fused": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, C.POINTER(VgConvEpilogue), c_vp, c_vp, c_vp]),
+    "vg_fold_bn_into_conv": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "vg_bn_eval_affine": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f, c_int, c_vp, c_vp, c_vp]),
     "vg_conv_dgrad_scaled": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "vg_spectral_norm_sigma_batched": (c_int, [c_vp, c_int, c_int, c_f, c_vp, C.c_size_t, c_vp]),
     "vg_conv_forward": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -85,6 +93,7 @@ _PROTOS = {
     "vg_bn_act_backward_apply_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, C.POINTER(VgBnDesc), c_vp, c_vp, c_vp,
                                                c_vp, c_vp, c_f, c_vp]),
     "vg_bn_param_grads_scaled": (c_int, [c_vp, c_int, c_f, c_vp, c_vp, c_vp]),
+    "vg_add_dual_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f, C.POINTER(VgBnDesc), c_vp, c_vp, c_vp]),
     "vg_scale": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_vp]),
     "vg_normalize_images": (c_int, [c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp]),
     "vg_lrelu_forward": (c_int, [c_vp, c_ll, c_int, c_f, c_vp, c_vp]),

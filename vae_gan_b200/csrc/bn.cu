@@ -733,6 +733,8 @@ int bn_stream_bwd_apply(const void* dy, const void* x, const float* mean_rstd, c
                         void* dx, float* dgamma, float* dbeta, float param_scale, cudaStream_t s);
 int bn_stream_add(const void* x0, const VgBnChannel* bn_a, const void* x1, const VgBnChannel* bn_b, const VgBnDesc* d, void* out,
                   double* stats, cudaStream_t s);
+int bn_stream_add_dual(const void* x0, const void* x1, const float* post_scale, const float* post_shift, float post_slope,
+                       const VgBnDesc* d, void* out, void* out2, cudaStream_t s);
 }  // namespace vg
 
 static int check_desc(const VgBnDesc* d) {
@@ -1084,6 +1086,21 @@ extern "C" int vg_bn_add_forward_fused(const void* a, const VgBnChannel* bn_a, c
   if (bn_b != nullptr && (rc = channel_mean_rstd(bn_b, d, &mrb, stream))) return rc;
   return vg_bn_add_forward(a, mra, bn_a ? bn_a->gamma : nullptr, bn_a ? bn_a->beta : nullptr, b, mrb, bn_b ? bn_b->gamma : nullptr,
                            bn_b ? bn_b->beta : nullptr, d, out, stats, stream);
+}
+
+extern "C" int vg_add_dual_forward(const void* a, const void* b, const float* post_scale, const float* post_shift, float post_slope,
+                                   const VgBnDesc* d, void* out, void* out2, vg_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  VG_CHECK_ARG(a && b && out && out2 && post_scale && post_shift, "null pointer");
+  if (d->rows == 0) return VG_OK;
+  VgBnDesc dd = *d;
+  dd.drop_p = 0.f;
+  if (!bn_stream_ok(&dd, a, b, out, out2) || d->c % 8 != 0) {
+    set_error("vg_add_dual_forward needs channels %% 8 == 0 (<= 2048) and 16-byte aligned tensors");
+    return VG_EUNSUPPORTED;
+  }
+  return bn_stream_add_dual(a, b, post_scale, post_shift, post_slope, &dd, out, out2, as_stream(stream));
 }
 
 extern "C" int vg_lrelu_backward(const void* dy, const void* y_ref, long long n, int dtype, float slope, void* dx,

@@ -31,7 +31,7 @@ namespace bs {
 constexpr int kConsumers = 256;
 constexpr int kThreads = kConsumers + 32;      // + one producer warp
 
-enum Mode { kStats = 0, kFwd = 1, kBwdReduce = 2, kBwdApply = 3, kBwdApplyAdd = 4, kAdd = 5, kAddStats = 6 };
+enum Mode { kStats = 0, kFwd = 1, kBwdReduce = 2, kBwdApply = 3, kBwdApplyAdd = 4, kAdd = 5, kAddStats = 6, kAddDual = 7 };
 
 // how a kernel obtains (mean, rstd) of one BatchNorm: kind -1 none (identity), 0 read mean_rstd, 1 finalize
 // from the fp64 sums (training), 2 from the running statistics (eval)
@@ -71,6 +71,11 @@ struct Args {
   float* dgamma;
   float* dbeta;
   float param_scale;
+  // kAddDual (eval / sampling path): second output = leaky_relu(post_scale[c] * out + post_shift[c], post_slope)
+  void* out2;
+  const float* post_scale;
+  const float* post_shift;
+  float post_slope;
   // activation / dropout
   float slope, drop_scale;
   uint32_t thr16;
@@ -83,7 +88,7 @@ struct Args {
 template <int MODE> struct ModeTraits {
   static constexpr int NIN = (MODE == kStats || MODE == kFwd) ? 1 : (MODE == kBwdApplyAdd ? 3 : 2);
   static constexpr bool kReduce = MODE == kStats || MODE == kBwdReduce || MODE == kAddStats;
-  static constexpr bool kStore = MODE == kFwd || MODE == kBwdApply || MODE == kBwdApplyAdd || MODE == kAdd || MODE == kAddStats;
+  static constexpr bool kStore = MODE == kFwd || MODE == kBwdApply || MODE == kBwdApplyAdd || MODE == kAdd || MODE == kAddStats || MODE == kAddDual;
 };
 
 template <typename T, int MODE> struct Geo {
@@ -231,6 +236,10 @@ __global__ void __launch_bounds__(kThreads, 2) bn_stream_kernel(const __grid_con
           c0[j] = -aa * k1;
         }
       }
+      if (MODE == kAddDual) {
+        c0[j] = a.post_scale[ch];               // (the add itself is plain: both operands identity)
+        cm[j] = a.post_shift[ch];
+      }
       if (MODE == kAdd || MODE == kAddStats) {
         if (a.B.kind >= 0) {
           float mean, rstd;
@@ -330,6 +339,20 @@ __global__ void __launch_bounds__(kThreads, 2) bn_stream_kernel(const __grid_con
               for (int j = 0; j < 8; ++j) x0.v[j] += ad.v[j];
             }
             x0.store(reinterpret_cast<T*>(a.out) + v * 8);
+          } else if (MODE == kAddDual) {
+            // out = in0 + in1 ; out2 = lrelu(post_scale * out + post_shift) computed from out AS STORED
+            Vec8<T> y2;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float t = x0.v[j] + x1.v[j];
+              t = t > 0.f ? t : t * a.slope;
+              x0.v[j] = t;
+              const float r = sizeof(T) == 2 ? to_f32(from_f32<T>(t)) : t;
+              float u = fmaf(c0[j], r, cm[j]);
+              y2.v[j] = u > 0.f ? u : u * a.post_slope;
+            }
+            x0.store(reinterpret_cast<T*>(a.out) + v * 8);
+            y2.store(reinterpret_cast<T*>(a.out2) + v * 8);
           } else {
             // kAdd / kAddStats: out = lrelu(bnA(in0) + bnB(in1))
 #pragma unroll
@@ -564,6 +587,21 @@ int bn_stream_bwd_apply(const void* dy, const void* x, const float* mean_rstd, c
   a.param_scale = param_scale;
   if (addend != nullptr) return dispatch<bs::kBwdApplyAdd>(a, d, s);
   return dispatch<bs::kBwdApply>(a, d, s);
+}
+
+int bn_stream_add_dual(const void* x0, const void* x1, const float* post_scale, const float* post_shift, float post_slope,
+                       const VgBnDesc* d, void* out, void* out2, cudaStream_t s) {
+  bs::Args a;
+  fill_common(a, d);
+  a.in0 = x0;
+  a.in1 = x1;
+  a.out = out;
+  a.out2 = out2;
+  a.post_scale = post_scale;
+  a.post_shift = post_shift;
+  a.post_slope = post_slope;
+  a.thr16 = 0;
+  return dispatch<bs::kAddDual>(a, d, s);
 }
 
 int bn_stream_add(const void* x0, const VgBnChannel* bn_a, const void* x1, const VgBnChannel* bn_b, const VgBnDesc* d, void* out,

@@ -14,7 +14,8 @@ int simt_pack_weights_batched(const VgPackItem* items, int n_items, int dtype, c
 bool tc_conv_supported(const VgConvDesc*, bool dgrad);
 bool tc_wgrad_supported(const VgConvDesc*);
 int tc_conv_run(const VgConvDesc*, bool dgrad, const void* in, const void* wpack, const float* bias, const float* colscale,
-                const float* sigma, int sigma_group_n, void* out, int out_dtype, double* stats, bool* stats_fused, cudaStream_t);
+                const float* sigma, int sigma_group_n, void* out, int out_dtype, double* stats, bool* stats_fused, cudaStream_t,
+                const VgConvEpilogue* ep = nullptr);
 int tc_wgrad_run(const VgConvDesc*, const void* x, const void* dy, float* dw, float* workspace, cudaStream_t);
 }  // namespace vg
 
@@ -61,16 +62,32 @@ extern "C" int vg_conv_forward(const VgConvDesc* d, const void* x, const void* p
 extern "C" int vg_conv_forward_scaled(const VgConvDesc* d, const void* x, const void* pack_kn, const void* pack_nk, const float* bias,
                                       const float* colscale, const float* sigma, int sigma_group_n, void* y, double* stats,
                                       vg_stream_t stream) {
+  VgConvEpilogue ep{};
+  ep.bias = bias; ep.colscale = colscale; ep.sigma = sigma; ep.sigma_group_n = sigma_group_n;
+  ep.act_slope = 1.0f; ep.post_slope = 1.0f;
+  return vg_conv_forward_fused(d, x, pack_kn, pack_nk, &ep, y, stats, stream);
+}
+
+extern "C" int vg_conv_forward_fused(const VgConvDesc* d, const void* x, const void* pack_kn, const void* pack_nk, const VgConvEpilogue* ep,
+                                     void* y, double* stats, vg_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
+  VG_CHECK_ARG(ep != nullptr, "VgConvEpilogue is null");
   if (d->n == 0) return VG_OK;   // empty batch: nothing to do (pointers of empty tensors may be null)
   VG_CHECK_ARG(x && y && pack_kn && pack_nk, "null pointer");
-  VG_CHECK_ARG(sigma_group_n >= 0, "sigma_group_n must be >= 0");
+  VG_CHECK_ARG(ep->sigma_group_n >= 0, "sigma_group_n must be >= 0");
+  VG_CHECK_ARG(ep->y2 == nullptr || (ep->post_scale && ep->post_shift), "the second output needs post_scale / post_shift");
+  const float* bias = ep->bias; const float* colscale = ep->colscale; const float* sigma = ep->sigma;
+  const int sigma_group_n = ep->sigma_group_n;
+  const bool inference_ep = ep->act_slope != 1.0f || ep->residual != nullptr || ep->y2 != nullptr;
   cudaStream_t s = as_stream(stream);
   bool stats_fused = false;
   if (tc_conv_supported(d, false) && !(d->c_out == 1 && colscale != nullptr))
-    rc = tc_conv_run(d, false, x, pack_kn, bias, colscale, sigma, sigma_group_n, y, d->out_dtype, stats, &stats_fused, s);
-  else
+    rc = tc_conv_run(d, false, x, pack_kn, bias, colscale, sigma, sigma_group_n, y, d->out_dtype, stats, &stats_fused, s, ep);
+  else if (inference_ep) {
+    set_error("the activation / residual / second-output epilogue exists on the tensor-core path only (bf16, channels %% 64 == 0)");
+    return VG_EUNSUPPORTED;
+  } else
     rc = simt_conv_forward(d, x, pack_nk, bias, colscale, sigma, sigma_group_n, y, s);
   if (rc) return rc;
   if (stats != nullptr && !stats_fused) {

@@ -59,6 +59,13 @@ struct alignas(64) TcConvParams {
   const float* sigma;    // nullable: the accumulator is multiplied by 1 / sigma[group] (spectral norm applied in the epilogue,
   int sigma_group_n;     //   so the packed weights stay valid across forwards); group = sample / sigma_group_n (0: one group)
   double* stats;         // nullable: [2*n_out] per-channel sum / sum of squares of the stored output
+  // inference epilogue (BatchNorm-folded sampling path, bf16 outputs only; see VgConvEpilogue in the header)
+  float act_slope;       // LeakyReLU slope of the stored output (1 = none)
+  const void* residual;  // nullable: same shape/dtype as out, added (after rounding the accumulator to bf16) before the activation
+  void* out2;            // nullable second output: leaky_relu(post_scale[c] * out + post_shift[c], post_slope)
+  const float* post_scale;
+  const float* post_shift;
+  float post_slope;
 };
 
 struct alignas(64) TcWgradParams {
@@ -115,6 +122,7 @@ __device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
 // store path, not the issue rate, bounded the epilogue (8 epilogue warps instead of 4 changed nothing on the 64-wide
 // layers).  The warp writes its 32 x 64 B block into shared memory (XOR-swizzled 16-byte units, conflict-free both ways),
 // reads it back transposed and stores with FOUR consecutive lanes covering one row's 64 bytes: 8 lines per instruction.
+template <bool INF>
 __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint32_t (&r)[32], bool valid, bool add_bias,
                                                long long opix, int gn, int ncol, bool first_chunk, bool do_stats, int lane,
                                                float& st_sum, float& st_sq, uint8_t* stage = nullptr) {
@@ -138,6 +146,10 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint
   }
   const bool staged = stage != nullptr && !p.out_f32 && p.ksplit <= 1 && p.n_store != 1;
   if (staged) {
+    if (INF && p.act_slope != 1.0f && p.residual == nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.act_slope;
+    }
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -150,13 +162,61 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint
     for (int q = 0; q < 4; ++q) srow[q ^ sw] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
     __syncwarp();
     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
+    const bool post = INF && (p.residual != nullptr || p.out2 != nullptr);       // kernel-uniform; compiled out of the training kernels
+    float ps[8], pt[8];
+    if (INF && p.out2 != nullptr) {
+      const int c0 = ncol + (lane & 3) * 8;       // this lane's 8 channels are the same for all four row groups
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ps[j] = __ldg(p.post_scale + c0 + j); pt[j] = __ldg(p.post_shift + c0 + j); }
+    }
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int row = it * 8 + (lane >> 2), q = lane & 3;
-      const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 64 + ((q ^ ((row >> 1) & 3)) << 4));
+      uint4 val = *reinterpret_cast<const uint4*>(stage + row * 64 + ((q ^ ((row >> 1) & 3)) << 4));
       const long long op = __shfl_sync(0xffffffffu, opix, row);
       const int ok = __shfl_sync(0xffffffffu, (int)valid, row);
-      if (ok) *reinterpret_cast<uint4*>(ob + op * p.n_out + ncol + q * 8) = val;
+      if (ok) {
+        const long long e = op * p.n_out + ncol + q * 8;
+        if (INF && post) {
+          float f[8];
+          const uint32_t wv[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(wv[i] << 16); f[2 * i + 1] = __uint_as_float(wv[i] & 0xffff0000u); }
+          if (p.residual != nullptr) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + e);
+            const uint32_t rv[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { f[2 * i] += __uint_as_float(rv[i] << 16); f[2 * i + 1] += __uint_as_float(rv[i] & 0xffff0000u); }
+            if (p.act_slope != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.act_slope;
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+              o[i] = *reinterpret_cast<uint32_t*>(&h);
+              // the second output is computed from the value AS STORED (what a separate elementwise pass would read)
+              f[2 * i] = __uint_as_float(o[i] << 16);
+              f[2 * i + 1] = __uint_as_float(o[i] & 0xffff0000u);
+            }
+            val = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          if (p.out2 != nullptr) {
+            uint32_t o2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float a0 = fmaf(ps[2 * i], f[2 * i], pt[2 * i]), a1 = fmaf(ps[2 * i + 1], f[2 * i + 1], pt[2 * i + 1]);
+              a0 = a0 > 0.f ? a0 : a0 * p.post_slope;
+              a1 = a1 > 0.f ? a1 : a1 * p.post_slope;
+              __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+              o2[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + e) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+          }
+        }
+        *reinterpret_cast<uint4*>(ob + e) = val;
+      }
     }
     __syncwarp();                      // the buffer is rewritten by this warp's next chunk
   } else if (valid) {
@@ -212,7 +272,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint
 // MT pixel tiles (128 rows each) per CTA share every weight tile: B traffic per FLOP drops by MT
 // (the implicit GEMM re-reads its operands from L2 for every tap, so it is L2-bandwidth bound
 // unless each staged byte feeds enough MMAs).
-template <int BN, int MT, int STAGES>
+template <int BN, int MT, int STAGES, bool INF>
 __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int kBBytes = BN * 128;
@@ -350,7 +410,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
-        epilogue_chunk(p, r, valid, p.ksplit <= 1 || blockIdx.z == 0, opix, gn, ncol0 + c0, c == 0, do_stats, lane, st_s[c], st_q[c],
+        epilogue_chunk<INF>(p, r, valid, p.ksplit <= 1 || blockIdx.z == 0, opix, gn, ncol0 + c0, c == 0, do_stats, lane, st_s[c], st_q[c],
                        stage_base + q * kStageBytes);
       }
     }
@@ -395,7 +455,7 @@ struct ConvPersistSmem {
 // EW = number of epilogue warps (4 or 8).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so with
 // eight warps two warps share each lane quarter and split the 32-column chunks between them; that
 // doubles the epilogue throughput, which is what makes the fused BatchNorm statistics free.
-template <int BN, int MT, int STAGES, int EW, int G>
+template <int BN, int MT, int STAGES, int EW, int G, bool INF>
 __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const __grid_constant__ TcConvParams p, int n_ntiles,
                                                                             int n_groups, int n_z, int n_work) {
   static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
@@ -635,7 +695,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
-          epilogue_chunk(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, do_stats && has_k, lane, st_s[c], st_q[c],
+          epilogue_chunk<INF>(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, do_stats && has_k, lane, st_s[c], st_q[c],
                          stage_base + ew * kStageBytes);
         }
       }
@@ -674,7 +734,7 @@ struct ConvPairSmem {
   static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024 + EW * kStageBytes + 16;
 };
 
-template <int BN, int MT, int STAGES, int EW>
+template <int BN, int MT, int STAGES, int EW, bool INF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
     tc_conv_pair_kernel(const __grid_constant__ TcConvParams p, int n_ntiles, int n_groups, int n_z, int n_work) {
   static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
@@ -887,7 +947,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
-          epilogue_chunk(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, do_stats && has_k, lane, st_s[c], st_q[c],
+          epilogue_chunk<INF>(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, do_stats && has_k, lane, st_s[c], st_q[c],
                          stage_base + ew * kStageBytes);
         }
       }
@@ -1190,24 +1250,24 @@ bool tc_wgrad_supported(const VgConvDesc* d) {
   return get_encode() != nullptr;
 }
 
-template <int BN, int MT, int STAGES>
-static int launch_conv(const TcConvParams& p, dim3 grid, cudaStream_t s) {
+template <int BN, int MT, int STAGES, bool INF>
+static int launch_conv_t(const TcConvParams& p, dim3 grid, cudaStream_t s) {
   static std::once_flag once;          // autograd worker threads call in concurrently
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_conv_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_conv_kernel<BN, MT, STAGES, INF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  ConvSmem<BN, MT, STAGES>::kBytes); });
   VG_CUDA(attr_err);
   grid.x = (unsigned)cdiv(grid.x, MT);
-  tc_conv_kernel<BN, MT, STAGES><<<grid, kTcThreads, ConvSmem<BN, MT, STAGES>::kBytes, s>>>(p);
+  tc_conv_kernel<BN, MT, STAGES, INF><<<grid, kTcThreads, ConvSmem<BN, MT, STAGES>::kBytes, s>>>(p);
   VG_LAUNCHED();
   return VG_OK;
 }
 
-template <int BN, int MT, int STAGES, int EW, int G>
-static int launch_conv_persist(const TcConvParams& p, dim3 grid, cudaStream_t s) {
+template <int BN, int MT, int STAGES, int EW, int G, bool INF>
+static int launch_conv_persist_t(const TcConvParams& p, dim3 grid, cudaStream_t s) {
   static std::once_flag once;          // autograd worker threads call in concurrently
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_conv_persist_kernel<BN, MT, STAGES, EW, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_conv_persist_kernel<BN, MT, STAGES, EW, G, INF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  ConvPersistSmem<BN, MT, STAGES, EW>::kBytes); });
   VG_CUDA(attr_err);
   const int n_groups = (int)cdiv(grid.x, MT);
@@ -1215,17 +1275,17 @@ static int launch_conv_persist(const TcConvParams& p, dim3 grid, cudaStream_t s)
   const int n_z = (int)grid.z;
   const long long n_work = (long long)n_groups * n_ntiles * n_z;
   const int ctas = (int)std::min<long long>(n_work, num_sms());
-  tc_conv_persist_kernel<BN, MT, STAGES, EW, G><<<ctas, 128 + 32 * EW, ConvPersistSmem<BN, MT, STAGES, EW>::kBytes, s>>>(
+  tc_conv_persist_kernel<BN, MT, STAGES, EW, G, INF><<<ctas, 128 + 32 * EW, ConvPersistSmem<BN, MT, STAGES, EW>::kBytes, s>>>(
       p, n_ntiles, n_groups, n_z, (int)n_work);
   VG_LAUNCHED();
   return VG_OK;
 }
 
-template <int BN, int MT, int STAGES, int EW>
-static int launch_conv_pair(const TcConvParams& p, dim3 grid, cudaStream_t s) {
+template <int BN, int MT, int STAGES, int EW, bool INF>
+static int launch_conv_pair_t(const TcConvParams& p, dim3 grid, cudaStream_t s) {
   static std::once_flag once;          // autograd worker threads call in concurrently
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_conv_pair_kernel<BN, MT, STAGES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_conv_pair_kernel<BN, MT, STAGES, EW, INF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  ConvPairSmem<BN, MT, STAGES, EW>::kBytes); });
   VG_CUDA(attr_err);
   const int n_groups = (int)(grid.x / (2 * MT));      // the caller checked divisibility
@@ -1233,10 +1293,28 @@ static int launch_conv_pair(const TcConvParams& p, dim3 grid, cudaStream_t s) {
   const int n_z = (int)grid.z;
   const long long n_work = (long long)n_groups * n_ntiles * n_z;
   const int pairs = (int)std::min<long long>(n_work, num_sms() / 2);
-  tc_conv_pair_kernel<BN, MT, STAGES, EW><<<2 * pairs, 128 + 32 * EW, ConvPairSmem<BN, MT, STAGES, EW>::kBytes, s>>>(
+  tc_conv_pair_kernel<BN, MT, STAGES, EW, INF><<<2 * pairs, 128 + 32 * EW, ConvPairSmem<BN, MT, STAGES, EW>::kBytes, s>>>(
       p, n_ntiles, n_groups, n_z, (int)n_work);
   VG_LAUNCHED();
   return VG_OK;
+}
+
+// the inference epilogue (activation / residual / second output) lives in its OWN instantiations: compiled into the
+// training kernels it cost them 12 % (b256 step 59.8 -> 67.3 ms: registers at the launch-bound cap, spills in the epilogue)
+template <int BN, int MT, int STAGES>
+static int launch_conv(const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  const bool inf = p.act_slope != 1.0f || p.residual != nullptr || p.out2 != nullptr;
+  return inf ? launch_conv_t<BN, MT, STAGES, true>(p, grid, s) : launch_conv_t<BN, MT, STAGES, false>(p, grid, s);
+}
+template <int BN, int MT, int STAGES, int EW, int G>
+static int launch_conv_persist(const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  const bool inf = p.act_slope != 1.0f || p.residual != nullptr || p.out2 != nullptr;
+  return inf ? launch_conv_persist_t<BN, MT, STAGES, EW, G, true>(p, grid, s) : launch_conv_persist_t<BN, MT, STAGES, EW, G, false>(p, grid, s);
+}
+template <int BN, int MT, int STAGES, int EW>
+static int launch_conv_pair(const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  const bool inf = p.act_slope != 1.0f || p.residual != nullptr || p.out2 != nullptr;
+  return inf ? launch_conv_pair_t<BN, MT, STAGES, EW, true>(p, grid, s) : launch_conv_pair_t<BN, MT, STAGES, EW, false>(p, grid, s);
 }
 
 template <int NB, int STAGES>
@@ -1302,7 +1380,8 @@ static int pick_bn(int n_out) {
 
 // dgrad=false: y = conv(x).  dgrad=true: dx from dy.  `in` is the tensor being read.
 int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpack, const float* bias, const float* colscale,
-                const float* sigma, int sigma_group_n, void* out, int out_dtype, double* stats, bool* stats_fused, cudaStream_t s) {
+                const float* sigma, int sigma_group_n, void* out, int out_dtype, double* stats, bool* stats_fused, cudaStream_t s,
+                const VgConvEpilogue* ep) {
   if (stats_fused) *stats_fused = false;
   TcConvParams p;
   memset(&p, 0, sizeof(p));
@@ -1321,6 +1400,11 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   p.out = out; p.out_f32 = out_dtype == VG_F32;
   p.bias = bias; p.colscale = colscale;
   p.sigma = sigma; p.sigma_group_n = sigma_group_n;
+  p.act_slope = 1.0f; p.post_slope = 1.0f;
+  if (ep != nullptr) {
+    p.act_slope = ep->act_slope; p.residual = ep->residual; p.out2 = ep->y2;
+    p.post_scale = ep->post_scale; p.post_shift = ep->post_shift; p.post_slope = ep->post_slope;
+  }
   p.stats = nullptr;
   int nphase = 1;
   if (gather) {
@@ -1350,6 +1434,10 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   if ((rc = make_weight_map(&p.w_map, wpack, (long long)k * k * n_out, in_c, BN))) return rc;
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.tiles_n), (unsigned)std::max(1, n_out / BN), (unsigned)nphase);
   if (grid.x == 0) return VG_OK;
+  if (ep != nullptr && (ep->act_slope != 1.0f || ep->residual != nullptr || ep->y2 != nullptr) && (p.out_f32 || p.n_store == 1)) {
+    set_error("the activation / residual / second-output epilogue needs a bf16 output with c_out %% 64 == 0");
+    return VG_EUNSUPPORTED;
+  }
   p.ksplit = 1;
   p.k_per_split = p.phases[0].ntaps * p.k_chunks;
   {

@@ -626,6 +626,31 @@ __global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, lo
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = from_f32<TD>(to_f32(src[i]));
 }
+__global__ void fold_bn_into_conv_kernel(const float* __restrict__ w, const float* __restrict__ bias_in, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                         int c_out, int c_in, int inner, int transposed, float* __restrict__ w_out,
+                                         float* __restrict__ bias_out) {
+  const long long total = (long long)c_out * c_in * inner;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pair = i / inner;
+    const int co = transposed ? (int)(pair % c_out) : (int)(pair / c_in);
+    const float sc = (float)((double)gamma[co] / sqrt((double)rv[co] + (double)eps));
+    w_out[i] = w[i] * sc;
+  }
+  for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < c_out; co += gridDim.x * blockDim.x) {
+    const float sc = (float)((double)gamma[co] / sqrt((double)rv[co] + (double)eps));
+    bias_out[co] = beta[co] - rm[co] * sc + (bias_in ? bias_in[co] * sc : 0.f);
+  }
+}
+__global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rm,
+                                      const float* __restrict__ rv, float eps, int c, float* __restrict__ scale, float* __restrict__ shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const float sc = (float)((double)gamma[ch] / sqrt((double)rv[ch] + (double)eps));
+  scale[ch] = sc;
+  shift[ch] = beta[ch] - rm[ch] * sc;
+}
+
 template <typename T>
 __global__ void scale_kernel(const T* __restrict__ src, const float* __restrict__ scale, long long n, T* __restrict__ dst) {
   const float sc = *scale;
@@ -1003,6 +1028,25 @@ extern "C" int vg_nhwc_to_nchw(const void* src, int src_dtype, int n, int c, int
   dim3 grid((unsigned)cdiv(h * w, 32), (unsigned)cdiv(c, 32), (unsigned)n), block(32, 8);
   if (src_dtype == VG_BF16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, c, h * w, dst);
   else nhwc_to_nchw_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)src, c, h * w, dst);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_fold_bn_into_conv(const float* w, const float* bias_in, const float* gamma, const float* beta, const float* running_mean,
+                                    const float* running_var, float eps, int c_out, int c_in, int inner, int transposed, float* w_out,
+                                    float* bias_out, vg_stream_t stream) {
+  VG_CHECK_ARG(w && gamma && beta && running_mean && running_var && w_out && bias_out && c_out > 0 && c_in > 0 && inner > 0, "bad args");
+  const long long total = (long long)c_out * c_in * inner;
+  fold_bn_into_conv_kernel<<<ew_grid(total), 256, 0, as_stream(stream)>>>(w, bias_in, gamma, beta, running_mean, running_var, eps, c_out, c_in,
+                                                                          inner, transposed, w_out, bias_out);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+extern "C" int vg_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, int c,
+                                 float* scale, float* shift, vg_stream_t stream) {
+  VG_CHECK_ARG(gamma && beta && running_mean && running_var && scale && shift && c > 0, "bad args");
+  bn_eval_affine_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(gamma, beta, running_mean, running_var, eps, c, scale, shift);
   VG_LAUNCHED();
   return VG_OK;
 }

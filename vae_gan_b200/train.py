@@ -222,6 +222,8 @@ class VaeGanTrainer:
         if os.environ.get("VG_PACK_CACHE", "1") == "1":
             self.packs_g = WeightPacks(generator, VF.config.compute_dtype)
             self.packs_d = WeightPacks(discriminator, VF.config.compute_dtype)
+        self._packs_stale = True      # packs are re-made right after each optimizer step; stale only before the first iteration,
+                                      # after a state restore, or after weights_changed()
         # data parallel: bucketed gradient all-reduce on a side stream, overlapped with the backward (GradBuckets).
         # The gradient-penalty mode accumulates part of its gradients through stock autograd (double backward), so it
         # keeps the single all-reduce after the backward.
@@ -269,9 +271,10 @@ class VaeGanTrainer:
         if self.peer is not None:
             self.peer.reset()
         VF.arena.begin(dev)           # ONE memset for every fp64 accumulator of the iteration
-        if self.packs_g is not None:  # (also picks up weights modified from outside between two iterations)
+        if self.packs_g is not None and self._packs_stale:
             self.packs_g.repack()
             self.packs_d.repack()
+            self._packs_stale = False
         try:
             return self._iteration(real, adv_mode, g_step)
         finally:
@@ -313,8 +316,8 @@ class VaeGanTrainer:
                 VF.config.grad_tracker = None
                 self._allreduce(self.fd, self.buckets_d)
                 self._opt(self.fd, self.clip)
-                if self.packs_d is not None and g_step:
-                    self.packs_d.repack()          # D(gen) below runs with the UPDATED discriminator (README.md:816)
+                if self.packs_d is not None:
+                    self.packs_d.repack()          # D(gen) below and the next iteration run with the UPDATED discriminator (README.md:816)
                 # ---- generator step (README.md:812: every n_critics-th iteration) ----
                 d_gen = None
                 if g_step:
@@ -328,6 +331,8 @@ class VaeGanTrainer:
                     VF.config.grad_tracker = None
                     self._allreduce(self.fg, self.buckets_g)
                     self._opt(self.fg, 0.0)
+                    if self.packs_g is not None:
+                        self.packs_g.repack()      # for the next iteration's generator forward
                     self.fd.set_requires_grad(True)
         self.losses = dict(d_loss=d_total.detach(), real_loss=d_rl.detach(), fake_loss=d_fl.detach())
         if g_step:
@@ -364,6 +369,7 @@ class VaeGanTrainer:
                 b.copy_(saved)
         self.iteration = snap["iteration"]
         self._last_g_losses = snap["last_g"]
+        self._packs_stale = True
 
     def capture(self, real_example: torch.Tensor, warmup: int = 3):
         """Capture the whole iteration (fwd + bwd + collectives + optimizers) in one CUDA graph (two when
@@ -394,8 +400,18 @@ class VaeGanTrainer:
                 self._step_impl(self.static_real, g_step=False)
             self._losses_d_only = self.losses
         self._state_restore(snap)
+        self.weights_changed()
         torch.cuda.synchronize(self.device)
         return self
+
+    def weights_changed(self):
+        """Call after modifying parameters from OUTSIDE the trainer (load_state_dict, manual clamps, ...): the cached GEMM
+        packs of the weights are re-made (immediately, so that a captured graph - which only re-packs after its own
+        optimizer steps - sees them too)."""
+        if self.packs_g is not None:
+            self.packs_g.repack()
+            self.packs_d.repack()
+            self._packs_stale = False
 
     def step(self, real: torch.Tensor):
         g_step = (self.iteration % self.n_critics) == 0
