@@ -170,3 +170,63 @@ def test_gradient_penalty_data_parallel_contract_world2_gloo():
         assert p.exitcode == 0
     for rank, worst in res:
         assert worst < 1e-8, f"rank {rank}: DP gradient penalty / its summed gradients differ from the global batch by {worst:.2e}"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# bucketed, backward-overlapped gradient all-reduce (train.GradBuckets): host logic under gloo, world_size 2
+# ----------------------------------------------------------------------------------------------------------------------
+def _bucket_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch.nn as nn
+    from vae_gan_b200.train import FlatParams, GradBuckets
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(300, 400), nn.Linear(400, 50), nn.Linear(50, 2000), nn.Linear(2000, 3))
+    flat = FlatParams(net)
+    # 0.25 MB buckets over ~0.9 MB of parameters: several buckets, the 400x300 weight alone exceeds one
+    gb = GradBuckets(flat, dist.group.WORLD, None, bucket_mb=0.25)
+    covered = sorted(gb.ranges)
+    ok = covered[0][0] == 0 and covered[-1][1] == flat.total and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    ok = ok and all(gb.ranges[i][0] >= gb.ranges[i + 1][1] for i in range(len(gb.ranges) - 1))     # launch order = reverse parameter order
+    params = list(net.parameters())
+    results = []
+    for uses in (1, 2):                          # 2 = the discriminator step: D(real) and D(fake) both contribute
+        gb.begin()
+        for p in params:
+            for _ in range(uses):
+                gb.use(p)
+        g_local = torch.arange(flat.total, dtype=torch.float32) * (rank + 1) * 1e-3
+        flat.g.copy_(g_local)
+        early = 0
+        for u in range(uses):                    # backward: last layer first; the second pass completes the counts
+            for p in reversed(params):
+                before = len(gb.order)
+                gb.done(p)
+                early += len(gb.order) - before
+        sent_before_flush = len(gb.order)
+        gb.flush()
+        want = torch.arange(flat.total, dtype=torch.float32) * 1e-3 * sum(r + 1 for r in range(world))
+        results.append((bool(torch.allclose(flat.g, want, rtol=1e-6, atol=0)), sent_before_flush, len(gb.ranges), list(gb.order)))
+    if rank == 0:
+        out_q.put((ok, results))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_buckets_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + (os.getpid() % 500) + 600
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, results = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok, "bucket ranges must tile the flat buffer in reverse parameter order"
+    for summed, sent_early, n_buckets, order in results:
+        assert summed, "all-reduced gradient != sum over ranks"
+        assert n_buckets >= 3
+        assert sent_early == n_buckets, "every bucket should have been launched from inside the backward"
+        assert order == list(range(n_buckets)), f"buckets launched out of backward order: {order}"

@@ -1470,7 +1470,10 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   // 256-wide tiles go persistent as soon as there is more than one work item per SM (288 tiles of the 24x24 layers at
   // batch 64 ran as one-shot CTAs without epilogue overlap: 38-85 us for 31 us of tensor work)
   const bool use_persist = persist && ((BN == 256 && ctas1 > (long long)num_sms()) ||
-                                       (ctas1 >= 2LL * num_sms() && ctas1 >= (long long)mt_min * num_sms() && (BN == 64 || BN == 128)));
+                                       // 128-wide: the CTA-pair kernel (1000+ TFLOP/s) from two work items per pair on; below 6 x SMs tiles
+                                       // these layers ran as one-shot CTAs (G 128->128 @48 at 32 images: 496 TFLOP/s)
+                                       (BN == 128 && ctas1 >= 2LL * num_sms()) ||
+                                       (BN == 64 && ctas1 >= 2LL * num_sms() && ctas1 >= (long long)mt_min * num_sms()));
   // BatchNorm statistics of the output can be accumulated by the epilogue warps of the 8-warp persistent
   // kernels (parity-tested), but it is OPT-IN (VG_TC_FUSE_STATS=1): measured on B200 the per-chunk smem
   // transposes cost the L2/smem-bound main loop more (+35 % per launch with 8 epilogue warps, +60 % with

@@ -124,12 +124,14 @@ class GradBuckets:
                 self.bucket_of[id(q)] = len(self.ranges) - 1
         self.pending = [0] * len(self.ranges)
         self.sent = [False] * len(self.ranges)
+        self.order = []                # buckets in the order they were launched (diagnostics / tests)
         self.armed = False
 
     def begin(self):
         """Start of a forward whose backward will be overlapped."""
         self.pending = [0] * len(self.ranges)
         self.sent = [False] * len(self.ranges)
+        self.order = []
         self.armed = True
 
     def use(self, param):
@@ -150,7 +152,11 @@ class GradBuckets:
 
     def _send(self, b):
         self.sent[b] = True
+        self.order.append(b)
         s, e = self.ranges[b]
+        if self.comm is None:          # host-only use (gloo tests): no streams to fork / join
+            dist.all_reduce(self.flat.g[s:e], op=dist.ReduceOp.SUM, group=self.pg)
+            return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self.comm.wait_event(ev)
@@ -162,7 +168,8 @@ class GradBuckets:
         for b in range(len(self.ranges)):
             if not self.sent[b]:
                 self._send(b)
-        torch.cuda.current_stream().wait_stream(self.comm)
+        if self.comm is not None:
+            torch.cuda.current_stream().wait_stream(self.comm)
         self.armed = False
 
 
