@@ -11,7 +11,8 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libvaegan_sm100.so"
+# VG_LIB: an alternative build of the same library (kernel A/B experiments); the default is the in-tree build
+LIB_PATH = Path(os.environ["VG_LIB"]) if os.environ.get("VG_LIB") else _PKG / "lib" / "libvaegan_sm100.so"
 
 VG_F32, VG_BF16 = 0, 1
 

@@ -128,6 +128,7 @@ __device__ __forceinline__ void block_reduce_to_global(float (&acc)[NV][8], cons
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_vec_kernel(const T* __restrict__ x, long long rows, int c,
                                                                    bool fold, double* __restrict__ sums) {
+  vg::pdl_entry();
   extern __shared__ float smem[];
   const int cv = fold ? 8 : c;
   const RowMap m = make_rowmap(cv);
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_vec_kernel(const T* __res
 
 template <typename T>
 __global__ void bn_stats_scalar_kernel(const T* __restrict__ x, long long total, int c, double* __restrict__ sums) {
+  vg::pdl_entry();
   extern __shared__ double dsm[];  // [2*c]
   for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) dsm[i] = 0.0;
   __syncthreads();
@@ -175,6 +177,7 @@ __global__ void bn_stats_scalar_kernel(const T* __restrict__ x, long long total,
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int c, float eps, float momentum,
                                    float* running_mean, float* running_var, float* __restrict__ mean_rstd) {
+  vg::pdl_entry();
   int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   double mean = sums[ch] / count;
@@ -191,6 +194,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int c, float eps,
                                      float* __restrict__ mean_rstd) {
+  vg::pdl_entry();
   int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   mean_rstd[ch] = rm[ch];
@@ -198,6 +202,7 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* 
 }
 
 __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int c, double scale, float* dgamma, float* dbeta) {
+  vg::pdl_entry();
   int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   if (dbeta) dbeta[ch] += (float)(sums[ch] * scale);
@@ -236,6 +241,7 @@ template <typename T, bool DROP>
 __global__ void __launch_bounds__(kBnThreads) bn_act_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ mean_rstd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                      BnK k, T* __restrict__ y) {
+  vg::pdl_entry();
   const int cv = k.fold ? 8 : k.c;
   const RowMap m = make_rowmap(cv);
   const int tid = threadIdx.x;
@@ -286,6 +292,7 @@ template <typename T>
 __global__ void bn_act_fwd_scalar_kernel(const T* __restrict__ x, const float* __restrict__ mean_rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, BnK k,
                                          T* __restrict__ y) {
+  vg::pdl_entry();
   Philox ph(k.seed, eff_offset(k.offset, k.step_ptr));
   const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
   const long long total = k.rows * k.c;
@@ -310,6 +317,7 @@ __global__ void __launch_bounds__(kBnThreads, APPLY ? 1 : 3) bn_act_bwd_vec_kern
                                                                      const double* __restrict__ sums_in /* apply */, double count,
                                                                      const float* __restrict__ out_colscale,
                                                                      const T* __restrict__ addend, T* __restrict__ dx) {
+  vg::pdl_entry();
   extern __shared__ float smem[];
   const int cv = k.fold ? 8 : k.c;
   const RowMap m = make_rowmap(cv);
@@ -424,6 +432,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_dbl_bwd_vec_kernel(const T* __r
                                                                     BnK k, const float* __restrict__ colscale,
                                                                     double* __restrict__ sums_out, const double* __restrict__ sums_in,
                                                                     double count, T* __restrict__ g_dy, T* __restrict__ g_x) {
+  vg::pdl_entry();
   extern __shared__ float smem[];
   const int cv = k.c;
   const RowMap m = make_rowmap(cv);
@@ -505,6 +514,7 @@ __global__ void bn_act_bwd_scalar_kernel(const T* __restrict__ dy, const T* __re
                                          double* __restrict__ sums_out, const double* __restrict__ sums_in, double count,
                                          const float* __restrict__ out_colscale, const T* __restrict__ addend,
                                          T* __restrict__ dx) {
+  vg::pdl_entry();
   extern __shared__ double dsm[];
   if (!APPLY) {
     for (int i = threadIdx.x; i < 2 * k.c; i += blockDim.x) dsm[i] = 0.0;
@@ -549,6 +559,7 @@ __global__ void __launch_bounds__(kBnThreads, 3) bn_add_vec_kernel(const T* __re
                                                                  const T* __restrict__ B, const float* __restrict__ mrB,
                                                                  const float* __restrict__ gB, const float* __restrict__ bB, BnK k,
                                                                  T* __restrict__ out, double* __restrict__ stats) {
+  vg::pdl_entry();
   extern __shared__ float smem[];
   const int cv = k.fold ? 8 : k.c;
   const RowMap m = make_rowmap(cv);
@@ -607,6 +618,7 @@ __global__ void bn_add_scalar_kernel(const T* __restrict__ A, const float* __res
                                      const float* __restrict__ bA, const T* __restrict__ B, const float* __restrict__ mrB,
                                      const float* __restrict__ gB, const float* __restrict__ bB, BnK k, T* __restrict__ out,
                                      double* __restrict__ stats) {
+  vg::pdl_entry();
   extern __shared__ double dsm[];
   if (stats) {
     for (int i = threadIdx.x; i < 2 * k.c; i += blockDim.x) dsm[i] = 0.0;
@@ -637,16 +649,19 @@ __global__ void bn_add_scalar_kernel(const T* __restrict__ A, const float* __res
 // elementwise helpers -----------------------------------------------------------------------
 template <typename T>
 __global__ void lrelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ yref, long long n, float slope, T* __restrict__ dx) {
+  vg::pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dx[i] = from_f32<T>(to_f32(dy[i]) * (to_f32(yref[i]) > 0.f ? 1.f : slope));
 }
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, long long n, T* __restrict__ out) {
+  vg::pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = from_f32<T>(to_f32(a[i]) + to_f32(b[i]));
 }
 template <typename T>
 __global__ void add_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, long long nvec, T* __restrict__ out) {
+  vg::pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     Vec8<T> va, vb;
     va.load(a + i * 8);
@@ -658,6 +673,7 @@ __global__ void add_vec_kernel(const T* __restrict__ a, const T* __restrict__ b,
 }
 
 __global__ void dropout_mask_kernel(BnK k, uint8_t* __restrict__ mask) {
+  vg::pdl_entry();
   Philox ph(k.seed, eff_offset(k.offset, k.step_ptr));
   const unsigned long long ebase = (unsigned long long)k.sample_offset * (unsigned long long)k.hw * (unsigned long long)k.c;
   const long long total = k.rows * k.c;
@@ -667,6 +683,7 @@ __global__ void dropout_mask_kernel(BnK k, uint8_t* __restrict__ mask) {
 
 __global__ void dropout2d_scale_kernel(float* __restrict__ scale, long long total, int c, float p, unsigned long long seed,
                                        unsigned long long offset, const unsigned long long* step_ptr, long long sample_offset) {
+  vg::pdl_entry();
   Philox ph(seed, eff_offset(offset, step_ptr));
   uint32_t thr = drop_threshold(p);
   float sc = 1.0f / (1.0f - p);
@@ -678,6 +695,7 @@ __global__ void dropout2d_scale_kernel(float* __restrict__ scale, long long tota
 
 __global__ void philox_normal_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
                                      const unsigned long long* step_ptr, long long start) {
+  vg::pdl_entry();
   Philox ph(seed, eff_offset(offset, step_ptr));
   const long long nblk = (n + 3) / 4;
   for (long long bidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; bidx < nblk; bidx += (long long)gridDim.x * blockDim.x) {
@@ -705,6 +723,7 @@ __global__ void philox_normal_kernel(float* __restrict__ out, long long n, unsig
 // u[i] = (word(start + i) >> 8) * 2^-24 in [0, 1): the gradient-penalty interpolation weights (README.md:719)
 __global__ void philox_uniform_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
                                       const unsigned long long* step_ptr, long long start) {
+  vg::pdl_entry();
   Philox ph(seed, eff_offset(offset, step_ptr));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const unsigned long long e = (unsigned long long)(start + i);
@@ -772,18 +791,18 @@ extern "C" int vg_bn_stats(const void* x, const VgBnDesc* d, double* sums, vg_st
     RowMap m = make_rowmap(cv);
     int grid = grid_for(rows, m.rpb, kUnrollWide * 2, kReduceBlocksPerSm);
     if (d->dtype == VG_BF16)
-      bn_stats_vec_kernel<__nv_bfloat16><<<grid, kBnThreads, vec_smem(), s>>>((const __nv_bfloat16*)x, rows, d->c, fold, sums);
+      vg::Launch(grid, kBnThreads, vec_smem(), s)(bn_stats_vec_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, rows, d->c, fold, sums);
     else
-      bn_stats_vec_kernel<float><<<grid, kBnThreads, vec_smem(), s>>>((const float*)x, rows, d->c, fold, sums);
+      vg::Launch(grid, kBnThreads, vec_smem(), s)(bn_stats_vec_kernel<float>, (const float*)x, rows, d->c, fold, sums);
   } else {
     long long total = d->rows * d->c;
     int grid = (int)std::min<long long>(cdiv(total, 256 * 8), (long long)num_sms() * 4);
     size_t sm = (size_t)2 * d->c * sizeof(double);
     VG_CHECK_ARG(sm <= 48 * 1024, "scalar BN path supports c <= 3072 (c=%d)", d->c);
     if (d->dtype == VG_BF16)
-      bn_stats_scalar_kernel<__nv_bfloat16><<<grid, 256, sm, s>>>((const __nv_bfloat16*)x, total, d->c, sums);
+      vg::Launch(grid, 256, sm, s)(bn_stats_scalar_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, total, d->c, sums);
     else
-      bn_stats_scalar_kernel<float><<<grid, 256, sm, s>>>((const float*)x, total, d->c, sums);
+      vg::Launch(grid, 256, sm, s)(bn_stats_scalar_kernel<float>, (const float*)x, total, d->c, sums);
   }
   VG_LAUNCHED();
   return VG_OK;
@@ -793,7 +812,7 @@ extern "C" int vg_bn_finalize(const double* sums, double count, int c, float eps
                               float* running_var, float* mean_rstd, vg_stream_t stream) {
   VG_CHECK_ARG(sums && mean_rstd && c > 0 && count > 0, "bad args");
   VG_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "running_mean/var must both be given or both null");
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, count, c, eps, momentum, running_mean, running_var, mean_rstd);
+  vg::Launch((c + 127) / 128, 128, 0, as_stream(stream))(bn_finalize_kernel, sums, count, c, eps, momentum, running_mean, running_var, mean_rstd);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -801,14 +820,14 @@ extern "C" int vg_bn_finalize(const double* sums, double count, int c, float eps
 extern "C" int vg_bn_eval_stats(const float* running_mean, const float* running_var, int c, float eps, float* mean_rstd,
                                 vg_stream_t stream) {
   VG_CHECK_ARG(running_mean && running_var && mean_rstd && c > 0, "bad args");
-  bn_eval_stats_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(running_mean, running_var, c, eps, mean_rstd);
+  vg::Launch((c + 127) / 128, 128, 0, as_stream(stream))(bn_eval_stats_kernel, running_mean, running_var, c, eps, mean_rstd);
   VG_LAUNCHED();
   return VG_OK;
 }
 
 extern "C" int vg_bn_param_grads_scaled(const double* sums, int c, float scale, float* dgamma, float* dbeta, vg_stream_t stream) {
   VG_CHECK_ARG(sums && c > 0, "bad args");
-  bn_param_grads_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, c, (double)scale, dgamma, dbeta);
+  vg::Launch((c + 127) / 128, 128, 0, as_stream(stream))(bn_param_grads_kernel, sums, c, (double)scale, dgamma, dbeta);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -829,13 +848,13 @@ static int bn_act_forward_t(const T* x, const float* mr, const float* gamma, con
     RowMap m = make_rowmap(k.fold ? 8 : d->c);
     int grid = grid_for(rows, m.rpb, kUnrollWide * 2);
     if (k.thr16)
-      bn_act_fwd_vec_kernel<T, true><<<grid, kBnThreads, 0, s>>>(x, mr, gamma, beta, k, y);
+      vg::Launch(grid, kBnThreads, 0, s)(bn_act_fwd_vec_kernel<T, true>, x, mr, gamma, beta, k, y);
     else
-      bn_act_fwd_vec_kernel<T, false><<<grid, kBnThreads, 0, s>>>(x, mr, gamma, beta, k, y);
+      vg::Launch(grid, kBnThreads, 0, s)(bn_act_fwd_vec_kernel<T, false>, x, mr, gamma, beta, k, y);
   } else {
     long long total = d->rows * d->c;
     int grid = (int)std::min<long long>(cdiv(total, 256 * 4), (long long)num_sms() * 8);
-    bn_act_fwd_scalar_kernel<T><<<grid, 256, 0, s>>>(x, mr, gamma, beta, k, y);
+    vg::Launch(grid, 256, 0, s)(bn_act_fwd_scalar_kernel<T>, x, mr, gamma, beta, k, y);
   }
   VG_LAUNCHED();
   return VG_OK;
@@ -908,15 +927,15 @@ static int bn_act_backward_t(const T* dy, const T* x, const float* mr, const flo
     int grid = grid_for(rows, m.rpb, APPLY ? kUnroll : kUnrollWide, APPLY ? apply_blocks_per_sm() : kReduceBlocksPerSm);
     size_t sm = APPLY ? 0 : vec_smem();
     if (k.thr16)
-      bn_act_bwd_vec_kernel<T, true, APPLY><<<grid, kBnThreads, sm, s>>>(dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
+      vg::Launch(grid, kBnThreads, sm, s)(bn_act_bwd_vec_kernel<T, true, APPLY>, dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
     else
-      bn_act_bwd_vec_kernel<T, false, APPLY><<<grid, kBnThreads, sm, s>>>(dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
+      vg::Launch(grid, kBnThreads, sm, s)(bn_act_bwd_vec_kernel<T, false, APPLY>, dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
   } else {
     long long total = d->rows * d->c;
     int grid = (int)std::min<long long>(cdiv(total, 256 * 4), (long long)num_sms() * 8);
     size_t sm = APPLY ? 0 : (size_t)2 * d->c * sizeof(double);
     VG_CHECK_ARG(sm <= 48 * 1024, "scalar BN path supports c <= 3072 (c=%d)", d->c);
-    bn_act_bwd_scalar_kernel<T, APPLY><<<grid, 256, sm, s>>>(dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
+    vg::Launch(grid, 256, sm, s)(bn_act_bwd_scalar_kernel<T, APPLY>, dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
   }
   VG_LAUNCHED();
   return VG_OK;
@@ -983,7 +1002,7 @@ static int bn_dbl_bwd_t(const T* dy, const T* x, const T* G, const float* mean_r
   RowMap m = make_rowmap(d->c);
   int grid = grid_for(d->rows, m.rpb, kUnroll, APPLY ? apply_blocks_per_sm() : kReduceBlocksPerSm);
   const size_t smem = APPLY ? 0 : (size_t)5 * 8 * kBnThreads * sizeof(float);
-  bn_dbl_bwd_vec_kernel<T, APPLY><<<grid, kBnThreads, smem, s>>>(dy, x, G, mean_rstd, gamma, beta, k, colscale, sums_out, sums_in, count,
+  vg::Launch(grid, kBnThreads, smem, s)(bn_dbl_bwd_vec_kernel<T, APPLY>, dy, x, G, mean_rstd, gamma, beta, k, colscale, sums_out, sums_in, count,
                                                                  g_dy, g_x);
   VG_LAUNCHED();
   return VG_OK;
@@ -1036,15 +1055,15 @@ static int bn_add_t(const T* a, const float* mra, const float* ga, const float* 
     RowMap m = make_rowmap(k.fold ? 8 : d->c);
     int grid = grid_for(rows, m.rpb, kUnroll, stats ? kReduceBlocksPerSm : apply_blocks_per_sm());
     if (stats)
-      bn_add_vec_kernel<T, true><<<grid, kBnThreads, vec_smem(), s>>>(a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
+      vg::Launch(grid, kBnThreads, vec_smem(), s)(bn_add_vec_kernel<T, true>, a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
     else
-      bn_add_vec_kernel<T, false><<<grid, kBnThreads, 0, s>>>(a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
+      vg::Launch(grid, kBnThreads, 0, s)(bn_add_vec_kernel<T, false>, a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
   } else {
     long long total = d->rows * d->c;
     int grid = (int)std::min<long long>(cdiv(total, 256 * 4), (long long)num_sms() * 8);
     size_t sm = stats ? (size_t)2 * d->c * sizeof(double) : 0;
     VG_CHECK_ARG(sm <= 48 * 1024, "scalar BN path supports c <= 3072 (c=%d)", d->c);
-    bn_add_scalar_kernel<T><<<grid, 256, sm, s>>>(a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
+    vg::Launch(grid, 256, sm, s)(bn_add_scalar_kernel<T>, a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
   }
   VG_LAUNCHED();
   return VG_OK;
@@ -1109,10 +1128,10 @@ extern "C" int vg_lrelu_backward(const void* dy, const void* y_ref, long long n,
   if (n == 0) return VG_OK;
   int grid = (int)std::min<long long>(cdiv(n, 256 * 4), (long long)num_sms() * 8);
   if (dtype == VG_BF16)
-    lrelu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y_ref, n, slope,
+    vg::Launch(grid, 256, 0, as_stream(stream))(lrelu_bwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y_ref, n, slope,
                                                                          (__nv_bfloat16*)dx);
   else
-    lrelu_bwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)dy, (const float*)y_ref, n, slope, (float*)dx);
+    vg::Launch(grid, 256, 0, as_stream(stream))(lrelu_bwd_kernel<float>, (const float*)dy, (const float*)y_ref, n, slope, (float*)dx);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1126,15 +1145,15 @@ extern "C" int vg_add(const void* a, const void* b, long long n, int dtype, void
     long long nv = n / 8;
     int grid = (int)std::min<long long>(cdiv(nv, 256 * 2), (long long)num_sms() * 8);
     if (dtype == VG_BF16)
-      add_vec_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nv, (__nv_bfloat16*)out);
+      vg::Launch(grid, 256, 0, s)(add_vec_kernel<__nv_bfloat16>, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nv, (__nv_bfloat16*)out);
     else
-      add_vec_kernel<float><<<grid, 256, 0, s>>>((const float*)a, (const float*)b, nv, (float*)out);
+      vg::Launch(grid, 256, 0, s)(add_vec_kernel<float>, (const float*)a, (const float*)b, nv, (float*)out);
   } else {
     int grid = (int)std::min<long long>(cdiv(n, 256 * 4), (long long)num_sms() * 8);
     if (dtype == VG_BF16)
-      add_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, (__nv_bfloat16*)out);
+      vg::Launch(grid, 256, 0, s)(add_kernel<__nv_bfloat16>, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, (__nv_bfloat16*)out);
     else
-      add_kernel<float><<<grid, 256, 0, s>>>((const float*)a, (const float*)b, n, (float*)out);
+      vg::Launch(grid, 256, 0, s)(add_kernel<float>, (const float*)a, (const float*)b, n, (float*)out);
   }
   VG_LAUNCHED();
   return VG_OK;
@@ -1148,7 +1167,7 @@ extern "C" int vg_dropout_mask(const VgBnDesc* d, uint8_t* mask, vg_stream_t str
   BnK k = make_bnk(d);
   long long total = d->rows * d->c;
   int grid = (int)std::min<long long>(cdiv(total, 256 * 4), (long long)num_sms() * 8);
-  dropout_mask_kernel<<<grid, 256, 0, as_stream(stream)>>>(k, mask);
+  vg::Launch(grid, 256, 0, as_stream(stream))(dropout_mask_kernel, k, mask);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1159,16 +1178,17 @@ extern "C" int vg_dropout2d_scale(float* scale, int n, int c, float p, unsigned 
   long long total = (long long)n * c;
   if (total == 0) return VG_OK;
   int grid = (int)std::min<long long>(cdiv(total, 256), (long long)num_sms() * 4);
-  dropout2d_scale_kernel<<<grid, 256, 0, as_stream(stream)>>>(scale, total, c, p, seed, offset, step_ptr, sample_offset);
+  vg::Launch(grid, 256, 0, as_stream(stream))(dropout2d_scale_kernel, scale, total, c, p, seed, offset, step_ptr, sample_offset);
   VG_LAUNCHED();
   return VG_OK;
 }
 
-__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) {
+  vg::pdl_entry(); *c += inc; }
 
 extern "C" int vg_counter_add(unsigned long long* counter, unsigned long long inc, vg_stream_t stream) {
   VG_CHECK_ARG(counter, "null pointer");
-  counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, inc);
+  vg::Launch(1, 1, 0, as_stream(stream))(counter_add_kernel, counter, inc);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1178,7 +1198,7 @@ extern "C" int vg_philox_uniform(float* out, long long n, unsigned long long see
   VG_CHECK_ARG(out && n >= 0 && start >= 0, "bad args");
   if (n == 0) return VG_OK;
   int grid = (int)std::min<long long>(cdiv(n, 256), (long long)num_sms() * 8);
-  philox_uniform_kernel<<<grid, 256, 0, as_stream(stream)>>>(out, n, seed, offset, step_ptr, start);
+  vg::Launch(grid, 256, 0, as_stream(stream))(philox_uniform_kernel, out, n, seed, offset, step_ptr, start);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1189,7 +1209,7 @@ extern "C" int vg_philox_normal(float* out, long long n, unsigned long long seed
   if (n == 0) return VG_OK;
   long long nblk = (n + 3) / 4;
   int grid = (int)std::min<long long>(cdiv(nblk, 256), (long long)num_sms() * 8);
-  philox_normal_kernel<<<grid, 256, 0, as_stream(stream)>>>(out, n, seed, offset, step_ptr, start);
+  vg::Launch(grid, 256, 0, as_stream(stream))(philox_normal_kernel, out, n, seed, offset, step_ptr, start);
   VG_LAUNCHED();
   return VG_OK;
 }

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_stream_kernel(const __grid_con
     ptx::fence_barrier_init();
   }
   __syncthreads();
+  vg::pdl_entry();   // the barrier set-up above overlaps the previous kernel's tail; everything below reads global memory
 
   const int tile_vecs = KT * a.tpb;
 
@@ -430,7 +431,7 @@ static int launch(const Args& a, cudaStream_t s) {
   VG_CUDA(attr_err);
   const long long cap = (long long)num_sms() * ctas_per_sm();
   const int grid = (int)std::max<long long>(1, std::min<long long>(a.ntiles, cap));
-  bn_stream_kernel<T, MODE, DROP><<<grid, kThreads, G::kSmemBytes, s>>>(a);
+  vg::Launch(grid, kThreads, G::kSmemBytes, s)(bn_stream_kernel<T, MODE, DROP>, a);
   VG_LAUNCHED();
   return VG_OK;
 }

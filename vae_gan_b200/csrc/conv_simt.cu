@@ -24,6 +24,7 @@ struct ConvGeom {
 template <typename T>
 __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int c_out, int c_in, int taps,
                                     int transposed, T* __restrict__ pack_kn, T* __restrict__ pack_nk) {
+  vg::pdl_entry();
   const long long total = (long long)taps * c_out * c_in;
   const float inv = sigma ? 1.0f / *sigma : 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -48,6 +49,7 @@ constexpr int kPackR0 = 16, kPackR1 = 32;
 template <typename T, int TAPS>
 __global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int n0, int n1,
                                                                  int transposed, T* __restrict__ pack_kn, T* __restrict__ pack_nk) {
+  vg::pdl_entry();
   constexpr int TP = TAPS | 1;                      // odd strides: no bank conflicts
   constexpr int ROW = kPackR1 * TP + 1;
   __shared__ float tile[kPackR0 * ROW];
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const float* __
 template <typename T>
 __global__ void __launch_bounds__(256) pack_weights_1x1_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int n0, int n1,
                                                                T* __restrict__ same, T* __restrict__ transp) {
+  vg::pdl_entry();
   __shared__ float tile[32][33];
   const float inv = sigma ? 1.0f / *sigma : 1.0f;
   const int r0b = blockIdx.y * 32, r1b = blockIdx.x * 32;
@@ -162,6 +165,7 @@ __device__ __forceinline__ void pack_tile_body(float* tile, const float* __restr
 
 template <typename T>
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const __grid_constant__ PackTable tb) {
+  vg::pdl_entry();
   __shared__ float tile[kPackR0 * (kPackR1 * 17 + 1)];      // sized for TAPS = 16; the 1x1 body uses it as [32][33]
   int i = 0;
   while (i + 1 < tb.n && (int)blockIdx.x >= tb.first_block[i + 1]) ++i;
@@ -236,8 +240,8 @@ int simt_pack_weights_batched(const VgPackItem* items, int n_items, int dtype, c
     }
     tb.first_block[tb.n] = blocks;
     if (blocks == 0) continue;
-    if (dtype == VG_BF16) pack_weights_batched_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(tb);
-    else pack_weights_batched_kernel<float><<<blocks, 256, 0, s>>>(tb);
+    if (dtype == VG_BF16) vg::Launch(blocks, 256, 0, s)(pack_weights_batched_kernel<__nv_bfloat16>, tb);
+    else vg::Launch(blocks, 256, 0, s)(pack_weights_batched_kernel<float>, tb);
     VG_LAUNCHED();
   }
   return VG_OK;
@@ -250,6 +254,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const TI* __restrict__
                                                           const float* __restrict__ bias, const float* __restrict__ colscale,
                                                           const float* __restrict__ sigma, int sigma_group_n,
                                                           ConvGeom g, TO* __restrict__ out) {
+  vg::pdl_entry();
   const unsigned cog = (unsigned)(g.co / CO_T);
   const unsigned total = (unsigned)g.n * g.ho * g.wo * cog;      // host guarantees < 2^31
   for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -347,6 +352,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const TI* __restrict__
 template <typename TI, typename TO, bool SCATTER, int TAPS>
 __global__ void __launch_bounds__(256) conv_reduce1_kernel(const TI* __restrict__ in, const TI* __restrict__ W,
                                                            const float* __restrict__ bias, ConvGeom g, TO* __restrict__ out) {
+  vg::pdl_entry();
   const int sub = threadIdx.x & 7;            // channel group within the pixel
   float w[TAPS][8];
 #pragma unroll
@@ -401,6 +407,7 @@ template <typename TI, typename TO, bool SCATTER>
 __global__ void __launch_bounds__(256) conv_expand1_kernel(const TI* __restrict__ in, const TI* __restrict__ W,
                                                            const float* __restrict__ bias, const float* __restrict__ colscale,
                                                            ConvGeom g, TO* __restrict__ out) {
+  vg::pdl_entry();
   const unsigned cog = (unsigned)g.co / 8;
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned nthr = gridDim.x * blockDim.x;          // multiple of cog (host guarantees)
@@ -475,6 +482,7 @@ template <typename TI, typename TO, bool FLIP>
 __global__ void __launch_bounds__(256) conv_expand1_strip_kernel(const TI* __restrict__ in, const TI* __restrict__ W,
                                                                  const float* __restrict__ bias, const float* __restrict__ colscale,
                                                                  ConvGeom g, TO* __restrict__ out) {
+  vg::pdl_entry();
   const unsigned cog = (unsigned)g.co / 8;
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned nthr = gridDim.x * blockDim.x;
@@ -525,6 +533,7 @@ __global__ void __launch_bounds__(256) conv_expand1_strip_kernel(const TI* __res
 template <typename T, bool FLIP>
 __global__ void __launch_bounds__(256) wgrad_degenerate_strip_kernel(const T* __restrict__ V, const T* __restrict__ S, int n, int h,
                                                                      int w, int c, unsigned strips_per_block, float* __restrict__ dw) {
+  vg::pdl_entry();
   extern __shared__ float sacc[];   // [9 * c]
   for (int i = threadIdx.x; i < 9 * c; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
@@ -643,6 +652,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 template <typename T, bool FLIP>
 __global__ void __launch_bounds__(degs::kThreads, 1) wgrad_degenerate_stream_kernel(const __grid_constant__ degs::Args a) {
+  vg::pdl_entry();
   using namespace degs;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -796,11 +806,11 @@ static int try_degenerate_stream(bool flip, const void* V, const void* S, int n,
   if (flip) {
     e = cudaFuncSetAttribute(wgrad_degenerate_stream_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) { cudaGetLastError(); return VG_OK; }
-    wgrad_degenerate_stream_kernel<T, true><<<grid, degs::kThreads, smem, s>>>(a);
+    vg::Launch(grid, degs::kThreads, smem, s)(wgrad_degenerate_stream_kernel<T, true>, a);
   } else {
     e = cudaFuncSetAttribute(wgrad_degenerate_stream_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) { cudaGetLastError(); return VG_OK; }
-    wgrad_degenerate_stream_kernel<T, false><<<grid, degs::kThreads, smem, s>>>(a);
+    vg::Launch(grid, degs::kThreads, smem, s)(wgrad_degenerate_stream_kernel<T, false>, a);
   }
   VG_LAUNCHED();
   *taken = true;
@@ -814,6 +824,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256, 2) wgrad_degenerate_kernel(const T* __restrict__ V, const T* __restrict__ S, int n, int hv,
                                                                int wv, int c, int hs, int ws, int kh, int kw, int stride, int pad,
                                                                bool a_mode, unsigned pix_per_block, float* __restrict__ dw) {
+  vg::pdl_entry();
   extern __shared__ float sacc[];   // [taps * c]
   const int taps = kh * kw;
   for (int i = threadIdx.x; i < taps * c; i += blockDim.x) sacc[i] = 0.f;
@@ -924,6 +935,7 @@ struct WgradGeom {
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(const T* __restrict__ U, const T* __restrict__ S, WgradGeom g,
                                                           float* __restrict__ dw) {
+  vg::pdl_entry();
   __shared__ float su[32][33];
   __shared__ float ss[32][33];
   const int tiles_s = (g.cs + 31) / 32;
@@ -983,6 +995,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const T* __restrict__ U
 // dbias[c] += sum over rows of dy[row][c]
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, long long rows, int c, long long rows_per_block, float* __restrict__ out) {
+  vg::pdl_entry();
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
@@ -1004,8 +1017,8 @@ static int launch_direct(bool scatter, const TI* in, const TI* W, const float* b
   if (sigma == nullptr && g.co == 1 && g.cr == 64 && g.kh == 3 && g.kw == 3 && colscale == nullptr) {
     const long long thr = (long long)g.n * g.ho * g.wo * 8;
     int grid1 = (int)std::min<long long>(cdiv(thr, 256), (long long)num_sms() * 16);
-    if (scatter) conv_reduce1_kernel<TI, TO, true, 9><<<grid1, 256, 0, s>>>(in, W, bias, g, out);
-    else         conv_reduce1_kernel<TI, TO, false, 9><<<grid1, 256, 0, s>>>(in, W, bias, g, out);
+    if (scatter) vg::Launch(grid1, 256, 0, s)(conv_reduce1_kernel<TI, TO, true, 9>, in, W, bias, g, out);
+    else         vg::Launch(grid1, 256, 0, s)(conv_reduce1_kernel<TI, TO, false, 9>, in, W, bias, g, out);
     VG_LAUNCHED();
     return VG_OK;
   }
@@ -1013,25 +1026,25 @@ static int launch_direct(bool scatter, const TI* in, const TI* W, const float* b
       g.wo == g.wi && 256 % (g.co / 8) == 0) {
     const long long thr = (long long)g.n * g.ho * (g.wo / 8) * (g.co / 8);
     int grid1 = (int)std::min<long long>(cdiv(thr, 256), (long long)num_sms() * 8);
-    if (scatter) conv_expand1_strip_kernel<TI, TO, true><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
-    else         conv_expand1_strip_kernel<TI, TO, false><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
+    if (scatter) vg::Launch(grid1, 256, 0, s)(conv_expand1_strip_kernel<TI, TO, true>, in, W, bias, colscale, g, out);
+    else         vg::Launch(grid1, 256, 0, s)(conv_expand1_strip_kernel<TI, TO, false>, in, W, bias, colscale, g, out);
     VG_LAUNCHED();
     return VG_OK;
   }
   if (sigma == nullptr && g.cr == 1 && v8 && g.kh == 3 && g.kw == 3 && 256 % (g.co / 8) == 0) {
     int grid1 = (int)std::min<long long>(cdiv(total, 256 * 2), (long long)num_sms() * 16);
-    if (scatter) conv_expand1_kernel<TI, TO, true><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
-    else         conv_expand1_kernel<TI, TO, false><<<grid1, 256, 0, s>>>(in, W, bias, colscale, g, out);
+    if (scatter) vg::Launch(grid1, 256, 0, s)(conv_expand1_kernel<TI, TO, true>, in, W, bias, colscale, g, out);
+    else         vg::Launch(grid1, 256, 0, s)(conv_expand1_kernel<TI, TO, false>, in, W, bias, colscale, g, out);
     VG_LAUNCHED();
     return VG_OK;
   }
   int grid = (int)std::min<long long>(cdiv(total, 256), (long long)num_sms() * 32);
   if (scatter) {
-    if (v8) conv_direct_kernel<TI, TO, true, 8><<<grid, 256, 0, s>>>(in, W, bias, colscale, sigma, sigma_group_n, g, out);
-    else    conv_direct_kernel<TI, TO, true, 1><<<grid, 256, 0, s>>>(in, W, bias, colscale, sigma, sigma_group_n, g, out);
+    if (v8) vg::Launch(grid, 256, 0, s)(conv_direct_kernel<TI, TO, true, 8>, in, W, bias, colscale, sigma, sigma_group_n, g, out);
+    else    vg::Launch(grid, 256, 0, s)(conv_direct_kernel<TI, TO, true, 1>, in, W, bias, colscale, sigma, sigma_group_n, g, out);
   } else {
-    if (v8) conv_direct_kernel<TI, TO, false, 8><<<grid, 256, 0, s>>>(in, W, bias, colscale, sigma, sigma_group_n, g, out);
-    else    conv_direct_kernel<TI, TO, false, 1><<<grid, 256, 0, s>>>(in, W, bias, colscale, sigma, sigma_group_n, g, out);
+    if (v8) vg::Launch(grid, 256, 0, s)(conv_direct_kernel<TI, TO, false, 8>, in, W, bias, colscale, sigma, sigma_group_n, g, out);
+    else    vg::Launch(grid, 256, 0, s)(conv_direct_kernel<TI, TO, false, 1>, in, W, bias, colscale, sigma, sigma_group_n, g, out);
   }
   VG_LAUNCHED();
   return VG_OK;
@@ -1103,11 +1116,11 @@ int simt_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* d
       blocks = cdiv(nstrips, spb);
       size_t sm2 = (size_t)9 * c * sizeof(float);
       if (d->act_dtype == VG_BF16) {
-        if (a_mode) wgrad_degenerate_strip_kernel<__nv_bfloat16, false><<<(unsigned)blocks, 256, sm2, s>>>((const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, spb, dw);
-        else        wgrad_degenerate_strip_kernel<__nv_bfloat16, true><<<(unsigned)blocks, 256, sm2, s>>>((const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, spb, dw);
+        if (a_mode) vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<__nv_bfloat16, false>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, spb, dw);
+        else        vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<__nv_bfloat16, true>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, spb, dw);
       } else {
-        if (a_mode) wgrad_degenerate_strip_kernel<float, false><<<(unsigned)blocks, 256, sm2, s>>>((const float*)V, (const float*)Sx, d->n, hv, wv, c, spb, dw);
-        else        wgrad_degenerate_strip_kernel<float, true><<<(unsigned)blocks, 256, sm2, s>>>((const float*)V, (const float*)Sx, d->n, hv, wv, c, spb, dw);
+        if (a_mode) vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<float, false>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, spb, dw);
+        else        vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<float, true>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, spb, dw);
       }
       VG_LAUNCHED();
       return VG_OK;
@@ -1119,11 +1132,11 @@ int simt_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* d
     blocks = cdiv(npix, ppb);
     size_t sm = (size_t)d->kh * d->kw * c * sizeof(float);
     if (d->act_dtype == VG_BF16) {
-      if (vec == 8) wgrad_degenerate_kernel<__nv_bfloat16, 8><<<(unsigned)blocks, 256, sm, s>>>((const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
-      else          wgrad_degenerate_kernel<__nv_bfloat16, 1><<<(unsigned)blocks, 256, sm, s>>>((const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
+      if (vec == 8) vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<__nv_bfloat16, 8>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
+      else          vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<__nv_bfloat16, 1>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
     } else {
-      if (vec == 8) wgrad_degenerate_kernel<float, 8><<<(unsigned)blocks, 256, sm, s>>>((const float*)V, (const float*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
-      else          wgrad_degenerate_kernel<float, 1><<<(unsigned)blocks, 256, sm, s>>>((const float*)V, (const float*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
+      if (vec == 8) vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<float, 8>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
+      else          vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<float, 1>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
     }
     VG_LAUNCHED();
     return VG_OK;
@@ -1137,9 +1150,9 @@ int simt_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* d
   splits = cdiv(qtot, g.q_per_split);
   dim3 grid(tiles, taps, (unsigned)splits);
   if (d->act_dtype == VG_BF16)
-    wgrad_simt_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)U, (const __nv_bfloat16*)S, g, dw);
+    vg::Launch(grid, 256, 0, s)(wgrad_simt_kernel<__nv_bfloat16>, (const __nv_bfloat16*)U, (const __nv_bfloat16*)S, g, dw);
   else
-    wgrad_simt_kernel<float><<<grid, 256, 0, s>>>((const float*)U, (const float*)S, g, dw);
+    vg::Launch(grid, 256, 0, s)(wgrad_simt_kernel<float>, (const float*)U, (const float*)S, g, dw);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1151,9 +1164,9 @@ int simt_colsum(const void* x, long long rows, int c, int dtype, float* out, cud
   blocks = cdiv(rows, rpb);
   int threads = std::min(1024, ((c + 31) / 32) * 32);
   if (dtype == VG_BF16)
-    colsum_kernel<__nv_bfloat16><<<(int)blocks, threads, 0, s>>>((const __nv_bfloat16*)x, rows, c, rpb, out);
+    vg::Launch((int)blocks, threads, 0, s)(colsum_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, rows, c, rpb, out);
   else
-    colsum_kernel<float><<<(int)blocks, threads, 0, s>>>((const float*)x, rows, c, rpb, out);
+    vg::Launch((int)blocks, threads, 0, s)(colsum_kernel<float>, (const float*)x, rows, c, rpb, out);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1170,16 +1183,16 @@ int simt_pack_weights(const VgConvDesc* d, const float* w, const float* sigma, v
       void* same = d->transposed ? pack_nk : pack_kn;
       void* transp = d->transposed ? pack_kn : pack_nk;
       dim3 tg((unsigned)cdiv(n1, 32), (unsigned)cdiv(n0, 32));
-      if (bf) pack_weights_1x1_kernel<__nv_bfloat16><<<tg, 256, 0, s>>>(w, sigma, n0, n1, (__nv_bfloat16*)same, (__nv_bfloat16*)transp);
-      else pack_weights_1x1_kernel<float><<<tg, 256, 0, s>>>(w, sigma, n0, n1, (float*)same, (float*)transp);
+      if (bf) vg::Launch(tg, 256, 0, s)(pack_weights_1x1_kernel<__nv_bfloat16>, w, sigma, n0, n1, (__nv_bfloat16*)same, (__nv_bfloat16*)transp);
+      else vg::Launch(tg, 256, 0, s)(pack_weights_1x1_kernel<float>, w, sigma, n0, n1, (float*)same, (float*)transp);
     } else {
       dim3 tg((unsigned)cdiv(n1, kPackR1), (unsigned)cdiv(n0, kPackR0));
       if (taps == 9) {
-        if (bf) pack_weights_tiled_kernel<__nv_bfloat16, 9><<<tg, 256, 0, s>>>(w, sigma, n0, n1, d->transposed, (__nv_bfloat16*)pack_kn, (__nv_bfloat16*)pack_nk);
-        else pack_weights_tiled_kernel<float, 9><<<tg, 256, 0, s>>>(w, sigma, n0, n1, d->transposed, (float*)pack_kn, (float*)pack_nk);
+        if (bf) vg::Launch(tg, 256, 0, s)(pack_weights_tiled_kernel<__nv_bfloat16, 9>, w, sigma, n0, n1, d->transposed, (__nv_bfloat16*)pack_kn, (__nv_bfloat16*)pack_nk);
+        else vg::Launch(tg, 256, 0, s)(pack_weights_tiled_kernel<float, 9>, w, sigma, n0, n1, d->transposed, (float*)pack_kn, (float*)pack_nk);
       } else {
-        if (bf) pack_weights_tiled_kernel<__nv_bfloat16, 16><<<tg, 256, 0, s>>>(w, sigma, n0, n1, d->transposed, (__nv_bfloat16*)pack_kn, (__nv_bfloat16*)pack_nk);
-        else pack_weights_tiled_kernel<float, 16><<<tg, 256, 0, s>>>(w, sigma, n0, n1, d->transposed, (float*)pack_kn, (float*)pack_nk);
+        if (bf) vg::Launch(tg, 256, 0, s)(pack_weights_tiled_kernel<__nv_bfloat16, 16>, w, sigma, n0, n1, d->transposed, (__nv_bfloat16*)pack_kn, (__nv_bfloat16*)pack_nk);
+        else vg::Launch(tg, 256, 0, s)(pack_weights_tiled_kernel<float, 16>, w, sigma, n0, n1, d->transposed, (float*)pack_kn, (float*)pack_nk);
       }
     }
     VG_LAUNCHED();
@@ -1187,10 +1200,10 @@ int simt_pack_weights(const VgConvDesc* d, const float* w, const float* sigma, v
   }
   int grid = (int)std::min<long long>(cdiv(total, 256), (long long)num_sms() * 8);
   if (d->act_dtype == VG_BF16)
-    pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(w, sigma, d->c_out, d->c_in, taps, d->transposed, (__nv_bfloat16*)pack_kn,
+    vg::Launch(grid, 256, 0, s)(pack_weights_kernel<__nv_bfloat16>, w, sigma, d->c_out, d->c_in, taps, d->transposed, (__nv_bfloat16*)pack_kn,
                                                             (__nv_bfloat16*)pack_nk);
   else
-    pack_weights_kernel<float><<<grid, 256, 0, s>>>(w, sigma, d->c_out, d->c_in, taps, d->transposed, (float*)pack_kn, (float*)pack_nk);
+    vg::Launch(grid, 256, 0, s)(pack_weights_kernel<float>, w, sigma, d->c_out, d->c_in, taps, d->transposed, (float*)pack_kn, (float*)pack_nk);
   VG_LAUNCHED();
   return VG_OK;
 }

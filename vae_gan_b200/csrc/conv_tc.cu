@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  vg::pdl_entry();   // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail; nothing above touches global memory
   const uint32_t tmem_base = *tmem_slot;
 
   if (num_k > 0) {
@@ -500,6 +501,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  vg::pdl_entry();   // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail; nothing above touches global memory
   const uint32_t tmem_base = *tmem_slot;
 
   // work item -> (z, n tile, pixel-tile group); groups vary fastest so that concurrently running
@@ -780,6 +782,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
   ptx::tc_fence_before();
   ptx::cluster_sync();                         // barriers of BOTH CTAs exist before anyone signals them
   ptx::tc_fence_after();
+  vg::pdl_entry();   // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail; nothing above touches global memory
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode = [&](int w, int& z, int& nt, int& g) {
@@ -1012,6 +1015,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_wgrad_kernel(const __grid_const
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  vg::pdl_entry();   // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail; nothing above touches global memory
   const uint32_t tmem_base = *tmem_slot;
 
   if (num_k > 0) {
@@ -1108,6 +1112,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_wgrad_kernel(const __grid_const
 
 // dw[cu][cs][tap] += ws[tap][cs][cu]  (32x32 smem-tile transpose between cu and r = cs*taps+tap)
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const float* __restrict__ ws, int cu_n, int cs_n, int taps, float* __restrict__ dw) {
+  vg::pdl_entry();
   __shared__ float tile[32][33];
   const int R = cs_n * taps;
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -1258,7 +1263,7 @@ static int launch_conv_t(const TcConvParams& p, dim3 grid, cudaStream_t s) {
                                  ConvSmem<BN, MT, STAGES>::kBytes); });
   VG_CUDA(attr_err);
   grid.x = (unsigned)cdiv(grid.x, MT);
-  tc_conv_kernel<BN, MT, STAGES, INF><<<grid, kTcThreads, ConvSmem<BN, MT, STAGES>::kBytes, s>>>(p);
+  vg::Launch(grid, kTcThreads, ConvSmem<BN, MT, STAGES>::kBytes, s)(tc_conv_kernel<BN, MT, STAGES, INF>, p);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1275,7 +1280,7 @@ static int launch_conv_persist_t(const TcConvParams& p, dim3 grid, cudaStream_t 
   const int n_z = (int)grid.z;
   const long long n_work = (long long)n_groups * n_ntiles * n_z;
   const int ctas = (int)std::min<long long>(n_work, num_sms());
-  tc_conv_persist_kernel<BN, MT, STAGES, EW, G, INF><<<ctas, 128 + 32 * EW, ConvPersistSmem<BN, MT, STAGES, EW>::kBytes, s>>>(
+  vg::Launch(ctas, 128 + 32 * EW, ConvPersistSmem<BN, MT, STAGES, EW>::kBytes, s)(tc_conv_persist_kernel<BN, MT, STAGES, EW, G, INF>, 
       p, n_ntiles, n_groups, n_z, (int)n_work);
   VG_LAUNCHED();
   return VG_OK;
@@ -1293,7 +1298,7 @@ static int launch_conv_pair_t(const TcConvParams& p, dim3 grid, cudaStream_t s) 
   const int n_z = (int)grid.z;
   const long long n_work = (long long)n_groups * n_ntiles * n_z;
   const int pairs = (int)std::min<long long>(n_work, num_sms() / 2);
-  tc_conv_pair_kernel<BN, MT, STAGES, EW, INF><<<2 * pairs, 128 + 32 * EW, ConvPairSmem<BN, MT, STAGES, EW>::kBytes, s>>>(
+  vg::Launch(2 * pairs, 128 + 32 * EW, ConvPairSmem<BN, MT, STAGES, EW>::kBytes, s)(tc_conv_pair_kernel<BN, MT, STAGES, EW, INF>, 
       p, n_ntiles, n_groups, n_z, (int)n_work);
   VG_LAUNCHED();
   return VG_OK;
@@ -1323,7 +1328,7 @@ static int launch_wgrad(const TcWgradParams& p, dim3 grid, cudaStream_t s) {
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tc_wgrad_kernel<NB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<NB, STAGES>::kBytes); });
   VG_CUDA(attr_err);
-  tc_wgrad_kernel<NB, STAGES><<<grid, kTcThreads, WgradSmem<NB, STAGES>::kBytes, s>>>(p);
+  vg::Launch(grid, kTcThreads, WgradSmem<NB, STAGES>::kBytes, s)(tc_wgrad_kernel<NB, STAGES>, p);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1592,7 +1597,7 @@ int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, 
   }
   if (rc || !p.packed) return rc;
   dim3 ug((unsigned)cdiv((long long)cs * p.ntaps, 32), (unsigned)cdiv(cu, 32));
-  wgrad_unpack_kernel<<<ug, 256, 0, s>>>(workspace, cu, cs, p.ntaps, dw);
+  vg::Launch(ug, 256, 0, s)(wgrad_unpack_kernel, workspace, cu, cs, p.ntaps, dw);
   VG_LAUNCHED();
   return VG_OK;
 }

@@ -7,6 +7,7 @@ namespace vg {
 std::atomic<unsigned long long> g_launches{0};
 int g_num_sms = 0;
 int g_force_simt = 0;
+int g_pdl = 1;
 static thread_local char t_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -40,6 +41,8 @@ extern "C" int vg_init(int device) {
   vg::g_num_sms = prop.multiProcessorCount;
   const char* e = getenv("VG_FORCE_SIMT");
   if (e && atoi(e)) vg::g_force_simt = 1;
+  e = getenv("VG_PDL");
+  if (e) vg::g_pdl = atoi(e) ? 1 : 0;
   return VG_OK;
 }
 

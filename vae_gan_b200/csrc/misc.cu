@@ -16,6 +16,7 @@ template <typename TA, typename TB>
 __global__ void __launch_bounds__(256) gemm_small_kernel(const TA* __restrict__ A, long long sai, long long sal,
                                                           const TB* __restrict__ B, long long sbl, long long sbj, int I, int J,
                                                           int L, int l_per_split, float* __restrict__ C, int mode) {
+  vg::pdl_entry();
   __shared__ float sa[32][33];   // [l][i]
   __shared__ float sb[32][33];   // [l][j]
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
@@ -69,12 +70,14 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(const TA* __restrict__ 
 }
 
 __global__ void bias_lrelu_kernel(float* __restrict__ y, const float* __restrict__ bias, long long total, int n, float slope) {
+  vg::pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float v = y[i] + (bias ? bias[i % n] : 0.f);
     y[i] = v > 0.f ? v : v * slope;
   }
 }
 __global__ void colsum_f32_kernel(const float* __restrict__ x, int rows, int c, float* __restrict__ out) {
+  vg::pdl_entry();
   int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   float s = 0.f;
@@ -89,7 +92,7 @@ static int launch_gemm(const TA* A, long long sai, long long sal, const TB* B, l
   if (lps < 32) lps = 32;
   splits = (int)cdiv(L, lps);
   dim3 grid((unsigned)cdiv(J, 32), (unsigned)cdiv(I, 32), (unsigned)splits);
-  gemm_small_kernel<TA, TB><<<grid, 256, 0, s>>>(A, sai, sal, B, sbl, sbj, I, J, L, lps, C, mode);
+  vg::Launch(grid, 256, 0, s)(gemm_small_kernel<TA, TB>, A, sai, sal, B, sbl, sbj, I, J, L, lps, C, mode);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -99,6 +102,7 @@ static int launch_gemm(const TA* A, long long sai, long long sal, const TB* B, l
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void avgpool_flatten_fwd_kernel(const T* __restrict__ x, int n, int h, int w, int c, int k, float* __restrict__ out) {
+  vg::pdl_entry();
   const int ph = h / k, pw = w / k;
   const long long total = (long long)n * ph * pw * c;
   const float inv = 1.0f / (float)(k * k);
@@ -117,6 +121,7 @@ __global__ void avgpool_flatten_fwd_kernel(const T* __restrict__ x, int n, int h
 // one thread per 8 consecutive channels of an input pixel: 16-byte stores, 32-bit index math
 template <typename T>
 __global__ void avgpool_flatten_bwd_kernel(const float* __restrict__ dout, int n, int h, int w, int c, int k, T* __restrict__ dx) {
+  vg::pdl_entry();
   const int ph = h / k, pw = w / k;
   const float inv = 1.0f / (float)(k * k);
   if ((c & 7) == 0) {
@@ -160,6 +165,7 @@ __global__ void avgpool_flatten_bwd_kernel(const float* __restrict__ dout, int n
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_flatten_bwd_rows_kernel(const float* __restrict__ dout, int h, int w, int c, int k,
                                                                        T* __restrict__ dx) {
+  vg::pdl_entry();
   extern __shared__ float tile[];      // [pw][c]
   const int ph = h / k, pw = w / k;
   const int n = blockIdx.x / ph, py = blockIdx.x % ph;
@@ -190,6 +196,7 @@ __global__ void __launch_bounds__(256) avgpool_flatten_bwd_rows_kernel(const flo
 // t[j] += sum_{i in slice} W[i][j] u[i]
 __global__ void sn_wt_u_kernel(const float* __restrict__ W, const float* __restrict__ u, int rows, int cols, int rows_per_slice,
                                float* __restrict__ t) {
+  vg::pdl_entry();
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cols) return;
   int r0 = blockIdx.y * rows_per_slice, r1 = min(rows, r0 + rows_per_slice);
@@ -209,6 +216,7 @@ __global__ void sn_wt_u_kernel(const float* __restrict__ W, const float* __restr
 // the block of row 0 also writes v = t / max(||t||, eps)
 __global__ void __launch_bounds__(128) sn_w_v_kernel(const float* __restrict__ W, const float* __restrict__ t, int rows, int cols,
                                                      int normalize, float eps, float* __restrict__ v_out, float* __restrict__ s_out) {
+  vg::pdl_entry();
   const int row = blockIdx.x;
   float dot = 0.f, nt = 0.f;
   const float* wr = W + (long long)row * cols;
@@ -239,6 +247,7 @@ __global__ void __launch_bounds__(128) sn_w_v_kernel(const float* __restrict__ W
 // single block: training: u = s / max(||s||, eps); sigma = sum u*s.  eval: sigma = sum u*s.
 __global__ void sn_finish_kernel(const float* __restrict__ s, float* __restrict__ u, int rows, int training, float eps,
                                  float* __restrict__ sigma) {
+  vg::pdl_entry();
   __shared__ float red[32];
   __shared__ float bc;
   int tid = threadIdx.x;
@@ -280,6 +289,7 @@ struct SnTable {
   int n;
 };
 __global__ void sn_wt_u_batched_kernel(const __grid_constant__ SnTable tb, float* __restrict__ ws) {
+  vg::pdl_entry();
   const VgSnItem& it = tb.it[blockIdx.z];
   const int rows = it.rows, cols = it.cols;
   const int slices = max(1, min(rows / 8, 64));
@@ -305,6 +315,7 @@ __global__ void sn_wt_u_batched_kernel(const __grid_constant__ SnTable tb, float
 // block (row, item): s[row] = (W[row] . t) / max(||t||, eps) (training; t = W^T u) or W[row] . v (eval);
 // row 0 also writes v = t / max(||t||, eps) into the module buffer and into the saved copy
 __global__ void __launch_bounds__(128) sn_w_v_batched_kernel(const __grid_constant__ SnTable tb, float* __restrict__ ws, int training, float eps) {
+  vg::pdl_entry();
   const VgSnItem& it = tb.it[blockIdx.y];
   const int row = blockIdx.x;
   if (row >= it.rows) return;
@@ -342,6 +353,7 @@ __global__ void __launch_bounds__(128) sn_w_v_batched_kernel(const __grid_consta
 }
 // one block per item: training: u = s / max(||s||, eps); sigma = u . s; the saved copy of u
 __global__ void sn_finish_batched_kernel(const __grid_constant__ SnTable tb, const float* __restrict__ ws, int training, float eps) {
+  vg::pdl_entry();
   const VgSnItem& it = tb.it[blockIdx.x];
   const float* s = ws + tb.s_off[blockIdx.x];
   const int rows = it.rows;
@@ -381,6 +393,7 @@ __global__ void sn_finish_batched_kernel(const __grid_constant__ SnTable tb, con
   }
 }
 __global__ void sn_bwd_dot_kernel(const float* __restrict__ dwh, const float* __restrict__ w, long long n, float* __restrict__ acc) {
+  vg::pdl_entry();
   float part = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     part = fmaf(dwh[i], w[i], part);
@@ -397,6 +410,7 @@ __global__ void sn_bwd_dot_kernel(const float* __restrict__ dwh, const float* __
 __global__ void sn_bwd_apply_kernel(const float* __restrict__ dwh, const float* __restrict__ u, const float* __restrict__ v,
                                     const float* __restrict__ sigma, const float* __restrict__ dot, int rows, int cols,
                                     float* __restrict__ dw) {
+  vg::pdl_entry();
   const long long n = (long long)rows * cols;
   const float inv = 1.0f / *sigma;
   const float c = *dot * inv;   // <dw_hat, W> / sigma
@@ -412,6 +426,7 @@ __global__ void sn_bwd_apply_kernel(const float* __restrict__ dwh, const float* 
 template <typename T>
 __global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv_raw, const float* __restrict__ eps,
                                    long long n, int training, T* __restrict__ z, float* __restrict__ lv) {
+  vg::pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float l = fminf(fmaxf(lv_raw[i], -50.f), 50.f);
     lv[i] = l;
@@ -424,6 +439,7 @@ template <typename T>
 __global__ void reparam_bwd_kernel(const T* __restrict__ dz, const float* __restrict__ lv_raw, const float* __restrict__ eps,
                                    const float* __restrict__ dlv_in, long long n, int training, float* __restrict__ d_mu,
                                    float* __restrict__ d_lv) {
+  vg::pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float g = to_f32(dz[i]);
     d_mu[i] = g;
@@ -461,6 +477,7 @@ __global__ void __launch_bounds__(256) generator_loss_kernel(const T* __restrict
                                                               const float* __restrict__ logits, VgLossDesc d, T* __restrict__ d_xhat,
                                                               float* __restrict__ d_mu, float* __restrict__ d_lv,
                                                               float* __restrict__ d_logits, double* __restrict__ losses) {
+  vg::pdl_entry();
   const long long gsz = (long long)gridDim.x * blockDim.x;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   // reconstruction: mean|d| + mean d^2 over the GLOBAL pixel count
@@ -504,6 +521,7 @@ __global__ void __launch_bounds__(256) generator_loss_kernel(const T* __restrict
 __global__ void discriminator_loss_kernel(const float* __restrict__ d_real, const float* __restrict__ d_fake, int n, int n_global,
                                           int adv_mode, float* __restrict__ g_real, float* __restrict__ g_fake,
                                           double* __restrict__ losses) {
+  vg::pdl_entry();
   double lr = 0.0, lf = 0.0;
   const float inv = 1.0f / (float)n_global;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -533,6 +551,7 @@ __global__ void discriminator_loss_kernel(const float* __restrict__ d_real, cons
 __global__ void __launch_bounds__(256) optimizer_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                          float* __restrict__ v, long long n4, long long n, VgOptDesc d,
                                                          const unsigned long long* __restrict__ step_ptr) {
+  vg::pdl_entry();
   if (step_ptr != nullptr && d.kind == 0) {
     const float t = (float)(*step_ptr);
     d.bias_corr1 = 1.f - powf(d.beta1, t);
@@ -578,6 +597,7 @@ __global__ void __launch_bounds__(256) optimizer_kernel(float* __restrict__ p, c
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* __restrict__ vec, int n, VgPeerDesc pd, int slot,
                                                                  const unsigned long long* __restrict__ epoch_ptr) {
+  vg::pdl_entry();
   const unsigned long long epoch = *epoch_ptr;
   const int tid = threadIdx.x;
   const size_t slot_off = ((size_t)slot * pd.world + pd.rank) * VG_PEER_MAX_N;
@@ -623,6 +643,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(double* __restr
 // ------------------------------------------------------------------------------------------
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n) {
+  vg::pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = from_f32<TD>(to_f32(src[i]));
 }
@@ -630,6 +651,7 @@ __global__ void fold_bn_into_conv_kernel(const float* __restrict__ w, const floa
                                          const float* __restrict__ beta, const float* __restrict__ rm, const float* __restrict__ rv, float eps,
                                          int c_out, int c_in, int inner, int transposed, float* __restrict__ w_out,
                                          float* __restrict__ bias_out) {
+  vg::pdl_entry();
   const long long total = (long long)c_out * c_in * inner;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long pair = i / inner;
@@ -644,6 +666,7 @@ __global__ void fold_bn_into_conv_kernel(const float* __restrict__ w, const floa
 }
 __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rm,
                                       const float* __restrict__ rv, float eps, int c, float* __restrict__ scale, float* __restrict__ shift) {
+  vg::pdl_entry();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   const float sc = (float)((double)gamma[ch] / sqrt((double)rv[ch] + (double)eps));
@@ -653,6 +676,7 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
 
 template <typename T>
 __global__ void scale_kernel(const T* __restrict__ src, const float* __restrict__ scale, long long n, T* __restrict__ dst) {
+  vg::pdl_entry();
   const float sc = *scale;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = from_f32<T>(to_f32(src[i]) * sc);
@@ -667,6 +691,7 @@ template <typename TR> __device__ __forceinline__ double raw_to_f64(TR v) { retu
 template <typename TR>
 __global__ void __launch_bounds__(256) normalize_images_kernel(const TR* __restrict__ raw, long long pixels, float* __restrict__ out_f32,
                                                                __nv_bfloat16* __restrict__ out_bf16) {
+  vg::pdl_entry();
   const TR* img = raw + (long long)blockIdx.x * pixels;
   double lo = 1e300, hi = -1e300;
   bool has_nan = false;
@@ -704,6 +729,7 @@ __global__ void __launch_bounds__(256) normalize_images_kernel(const TR* __restr
 // tiled transpose of [c][hw] <-> [hw][c] per image
 template <typename TD>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int c, int hw, TD* __restrict__ dst) {
+  vg::pdl_entry();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -721,6 +747,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int c, int hw
 }
 template <typename TS>
 __global__ void nhwc_to_nchw_kernel(const TS* __restrict__ src, int c, int hw, float* __restrict__ dst) {
+  vg::pdl_entry();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -769,7 +796,7 @@ extern "C" int vg_linear_forward(const void* x, const void* w, const float* bias
   if (rc) return rc;
   if (bias != nullptr || slope != 1.0f) {
     long long total = (long long)m * n;
-    bias_lrelu_kernel<<<ew_grid(total, 1), 256, 0, s>>>((float*)y, bias, total, n, slope);
+    vg::Launch(ew_grid(total, 1), 256, 0, s)(bias_lrelu_kernel, (float*)y, bias, total, n, slope);
     VG_LAUNCHED();
   }
   return VG_OK;
@@ -780,7 +807,7 @@ extern "C" int vg_lrelu_forward(const void* x, long long n, int dtype, float slo
   VG_CHECK_ARG(dtype == VG_F32, "vg_lrelu_forward: fp32 only (head activations)");
   if (n == 0) return VG_OK;
   if (x != y) VG_CUDA(cudaMemcpyAsync(y, x, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
-  bias_lrelu_kernel<<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>((float*)y, nullptr, n, 1, slope);
+  vg::Launch(ew_grid(n, 1), 256, 0, as_stream(stream))(bias_lrelu_kernel, (float*)y, nullptr, n, 1, slope);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -805,7 +832,7 @@ extern "C" int vg_linear_wgrad(const void* x, const void* dy, int m, int n, int 
   int rc = launch_gemm<float, float>((const float*)dy, 1, n, (const float*)x, k, 1, n, k, m, dw, 1, 1, s);
   if (rc) return rc;
   if (dbias != nullptr) {
-    colsum_f32_kernel<<<(n + 127) / 128, 128, 0, s>>>((const float*)dy, m, n, dbias);
+    vg::Launch((n + 127) / 128, 128, 0, s)(colsum_f32_kernel, (const float*)dy, m, n, dbias);
     VG_LAUNCHED();
   }
   return VG_OK;
@@ -816,9 +843,9 @@ extern "C" int vg_avgpool_flatten_forward(const void* x, int n, int h, int w, in
   long long total = (long long)n * (h / k) * (w / k) * c;
   if (total == 0) return VG_OK;
   if (dtype == VG_BF16)
-    avgpool_flatten_fwd_kernel<__nv_bfloat16><<<ew_grid(total, 1), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, n, h, w, c, k, (float*)out);
+    vg::Launch(ew_grid(total, 1), 256, 0, as_stream(stream))(avgpool_flatten_fwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, n, h, w, c, k, (float*)out);
   else
-    avgpool_flatten_fwd_kernel<float><<<ew_grid(total, 1), 256, 0, as_stream(stream)>>>((const float*)x, n, h, w, c, k, (float*)out);
+    vg::Launch(ew_grid(total, 1), 256, 0, as_stream(stream))(avgpool_flatten_fwd_kernel<float>, (const float*)x, n, h, w, c, k, (float*)out);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -831,16 +858,16 @@ extern "C" int vg_avgpool_flatten_backward(const void* dout, int n, int h, int w
   if (h % k == 0 && w % k == 0 && c % 8 == 0 && tile_bytes <= 48 * 1024 && (long long)n * (h / k) < (1LL << 31)) {
     const unsigned blocks = (unsigned)(n * (h / k));
     if (dtype == VG_BF16)
-      avgpool_flatten_bwd_rows_kernel<__nv_bfloat16><<<blocks, 256, tile_bytes, as_stream(stream)>>>((const float*)dout, h, w, c, k, (__nv_bfloat16*)dx);
+      vg::Launch(blocks, 256, tile_bytes, as_stream(stream))(avgpool_flatten_bwd_rows_kernel<__nv_bfloat16>, (const float*)dout, h, w, c, k, (__nv_bfloat16*)dx);
     else
-      avgpool_flatten_bwd_rows_kernel<float><<<blocks, 256, tile_bytes, as_stream(stream)>>>((const float*)dout, h, w, c, k, (float*)dx);
+      vg::Launch(blocks, 256, tile_bytes, as_stream(stream))(avgpool_flatten_bwd_rows_kernel<float>, (const float*)dout, h, w, c, k, (float*)dx);
     VG_LAUNCHED();
     return VG_OK;
   }
   if (dtype == VG_BF16)
-    avgpool_flatten_bwd_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, as_stream(stream)>>>((const float*)dout, n, h, w, c, k, (__nv_bfloat16*)dx);
+    vg::Launch(ew_grid(total), 256, 0, as_stream(stream))(avgpool_flatten_bwd_kernel<__nv_bfloat16>, (const float*)dout, n, h, w, c, k, (__nv_bfloat16*)dx);
   else
-    avgpool_flatten_bwd_kernel<float><<<ew_grid(total), 256, 0, as_stream(stream)>>>((const float*)dout, n, h, w, c, k, (float*)dx);
+    vg::Launch(ew_grid(total), 256, 0, as_stream(stream))(avgpool_flatten_bwd_kernel<float>, (const float*)dout, n, h, w, c, k, (float*)dx);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -856,15 +883,15 @@ extern "C" int vg_spectral_norm_sigma(const float* w_orig, int rows, int cols, f
     int slices = std::max(1, std::min(rows / 8, 64));
     int rps = (int)cdiv(rows, slices);
     dim3 g1((unsigned)cdiv(cols, 128), (unsigned)cdiv(rows, rps));
-    sn_wt_u_kernel<<<g1, 128, 0, s>>>(w_orig, u, rows, cols, rps, t);
+    vg::Launch(g1, 128, 0, s)(sn_wt_u_kernel, w_orig, u, rows, cols, rps, t);
     VG_LAUNCHED();
-    sn_w_v_kernel<<<(unsigned)rows, 128, 0, s>>>(w_orig, t, rows, cols, 1, eps, v, sv);
+    vg::Launch((unsigned)rows, 128, 0, s)(sn_w_v_kernel, w_orig, t, rows, cols, 1, eps, v, sv);
     VG_LAUNCHED();
   } else {
-    sn_w_v_kernel<<<(unsigned)rows, 128, 0, s>>>(w_orig, v, rows, cols, 0, eps, nullptr, sv);
+    vg::Launch((unsigned)rows, 128, 0, s)(sn_w_v_kernel, w_orig, v, rows, cols, 0, eps, nullptr, sv);
     VG_LAUNCHED();
   }
-  sn_finish_kernel<<<1, 256, 0, s>>>(sv, u, rows, training, eps, sigma);
+  vg::Launch(1, 256, 0, s)(sn_finish_kernel, sv, u, rows, training, eps, sigma);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -893,13 +920,13 @@ extern "C" int vg_spectral_norm_sigma_batched(const VgSnItem* items, int n_items
       VG_CUDA(cudaMemsetAsync(workspace, 0, off * sizeof(float), s));
       const int max_slices = std::max(1, std::min(max_rows / 8, 64));
       dim3 g1((unsigned)cdiv(max_cols, 128), (unsigned)max_slices, (unsigned)tb.n);
-      sn_wt_u_batched_kernel<<<g1, 128, 0, s>>>(tb, workspace);
+      vg::Launch(g1, 128, 0, s)(sn_wt_u_batched_kernel, tb, workspace);
       VG_LAUNCHED();
     }
     dim3 g2((unsigned)max_rows, (unsigned)tb.n);
-    sn_w_v_batched_kernel<<<g2, 128, 0, s>>>(tb, workspace, training, eps);
+    vg::Launch(g2, 128, 0, s)(sn_w_v_batched_kernel, tb, workspace, training, eps);
     VG_LAUNCHED();
-    sn_finish_batched_kernel<<<tb.n, 256, 0, s>>>(tb, workspace, training, eps);
+    vg::Launch(tb.n, 256, 0, s)(sn_finish_batched_kernel, tb, workspace, training, eps);
     VG_LAUNCHED();
   }
   return VG_OK;
@@ -912,9 +939,9 @@ extern "C" int vg_spectral_norm_backward(const float* dw_hat, const float* w_ori
   cudaStream_t s = as_stream(stream);
   long long n = (long long)rows * cols;
   VG_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float), s));
-  sn_bwd_dot_kernel<<<ew_grid(n), 256, 0, s>>>(dw_hat, w_orig, n, workspace);
+  vg::Launch(ew_grid(n), 256, 0, s)(sn_bwd_dot_kernel, dw_hat, w_orig, n, workspace);
   VG_LAUNCHED();
-  sn_bwd_apply_kernel<<<ew_grid(n), 256, 0, s>>>(dw_hat, u, v, sigma, workspace, rows, cols, dw_orig);
+  vg::Launch(ew_grid(n), 256, 0, s)(sn_bwd_apply_kernel, dw_hat, u, v, sigma, workspace, rows, cols, dw_orig);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -924,9 +951,9 @@ extern "C" int vg_reparam_forward(const float* mu, const float* lv_raw, const fl
   VG_CHECK_ARG(mu && lv_raw && z && lv_clamped && n >= 0 && (!training || eps), "bad args");
   if (n == 0) return VG_OK;
   if (z_dtype == VG_BF16)
-    reparam_fwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, as_stream(stream)>>>(mu, lv_raw, eps, n, training, (__nv_bfloat16*)z, lv_clamped);
+    vg::Launch(ew_grid(n), 256, 0, as_stream(stream))(reparam_fwd_kernel<__nv_bfloat16>, mu, lv_raw, eps, n, training, (__nv_bfloat16*)z, lv_clamped);
   else
-    reparam_fwd_kernel<float><<<ew_grid(n), 256, 0, as_stream(stream)>>>(mu, lv_raw, eps, n, training, (float*)z, lv_clamped);
+    vg::Launch(ew_grid(n), 256, 0, as_stream(stream))(reparam_fwd_kernel<float>, mu, lv_raw, eps, n, training, (float*)z, lv_clamped);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -936,9 +963,9 @@ extern "C" int vg_reparam_backward(const void* dz, const float* lv_raw, const fl
   VG_CHECK_ARG(dz && lv_raw && d_mu && d_lv_raw && n >= 0 && (!training || eps), "bad args");
   if (n == 0) return VG_OK;
   if (z_dtype == VG_BF16)
-    reparam_bwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dz, lv_raw, eps, dlv_in, n, training, d_mu, d_lv_raw);
+    vg::Launch(ew_grid(n), 256, 0, as_stream(stream))(reparam_bwd_kernel<__nv_bfloat16>, (const __nv_bfloat16*)dz, lv_raw, eps, dlv_in, n, training, d_mu, d_lv_raw);
   else
-    reparam_bwd_kernel<float><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const float*)dz, lv_raw, eps, dlv_in, n, training, d_mu, d_lv_raw);
+    vg::Launch(ew_grid(n), 256, 0, as_stream(stream))(reparam_bwd_kernel<float>, (const float*)dz, lv_raw, eps, dlv_in, n, training, d_mu, d_lv_raw);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -954,10 +981,10 @@ extern "C" int vg_generator_loss(const void* xhat, const float* x, const float* 
   VgLossDesc dd = *d;
   if (dd.n_logits_global <= 0) dd.n_logits_global = 1;
   if (d->xhat_dtype == VG_BF16)
-    generator_loss_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)xhat, x, mu, lv, logits, dd,
+    vg::Launch(grid, 256, 0, as_stream(stream))(generator_loss_kernel<__nv_bfloat16>, (const __nv_bfloat16*)xhat, x, mu, lv, logits, dd,
                                                                                (__nv_bfloat16*)d_xhat, d_mu, d_lv, d_logits, losses);
   else
-    generator_loss_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)xhat, x, mu, lv, logits, dd, (float*)d_xhat, d_mu, d_lv,
+    vg::Launch(grid, 256, 0, as_stream(stream))(generator_loss_kernel<float>, (const float*)xhat, x, mu, lv, logits, dd, (float*)d_xhat, d_mu, d_lv,
                                                                        d_logits, losses);
   VG_LAUNCHED();
   return VG_OK;
@@ -966,7 +993,7 @@ extern "C" int vg_generator_loss(const void* xhat, const float* x, const float* 
 extern "C" int vg_discriminator_loss(const float* d_real, const float* d_fake, int n, int n_global, int adv_mode, float* g_real,
                                      float* g_fake, double* losses, vg_stream_t stream) {
   VG_CHECK_ARG(d_real && d_fake && g_real && g_fake && losses && n >= 0 && n_global > 0, "bad args");
-  discriminator_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(d_real, d_fake, n, n_global, adv_mode, g_real, g_fake, losses);
+  vg::Launch(1, 256, 0, as_stream(stream))(discriminator_loss_kernel, d_real, d_fake, n, n_global, adv_mode, g_real, g_fake, losses);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -979,7 +1006,7 @@ extern "C" int vg_optimizer_step(float* p, const float* g, float* m, float* v, l
   if (n == 0) return VG_OK;
   bool al = ((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)v % 16 == 0) && (!m || (uintptr_t)m % 16 == 0);
   long long n4 = al ? n / 4 : 0;
-  optimizer_kernel<<<ew_grid(n, 8), 256, 0, as_stream(stream)>>>(p, g, m, v, n4, n, *d, step_ptr);
+  vg::Launch(ew_grid(n, 8), 256, 0, as_stream(stream))(optimizer_kernel, p, g, m, v, n4, n, *d, step_ptr);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -991,7 +1018,7 @@ extern "C" int vg_peer_allreduce_f64(double* vec, int n, const VgPeerDesc* pd, i
   VG_CHECK_ARG(pd->world >= 1 && pd->world <= VG_PEER_MAX_WORLD && pd->rank >= 0 && pd->rank < pd->world, "bad rank/world");
   VG_CHECK_ARG(slot >= 0 && slot < pd->n_slots, "slot %d out of range (n_slots %d)", slot, pd->n_slots);
   for (int r = 0; r < pd->world; ++r) VG_CHECK_ARG(pd->peer_data[r] && pd->peer_flags[r], "peer pointer %d is null", r);
-  peer_allreduce_f64_kernel<<<1, 256, 0, as_stream(stream)>>>(vec, n, *pd, slot, epoch_ptr);
+  vg::Launch(1, 256, 0, as_stream(stream))(peer_allreduce_f64_kernel, vec, n, *pd, slot, epoch_ptr);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1001,10 +1028,10 @@ extern "C" int vg_cast(const void* src, int src_dtype, void* dst, int dst_dtype,
   if (n == 0) return VG_OK;
   cudaStream_t s = as_stream(stream);
   int grid = ew_grid(n);
-  if (src_dtype == VG_F32 && dst_dtype == VG_BF16) cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n);
-  else if (src_dtype == VG_BF16 && dst_dtype == VG_F32) cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n);
-  else if (src_dtype == VG_F32 && dst_dtype == VG_F32) cast_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src, (float*)dst, n);
-  else if (src_dtype == VG_BF16 && dst_dtype == VG_BF16) cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  if (src_dtype == VG_F32 && dst_dtype == VG_BF16) vg::Launch(grid, 256, 0, s)(cast_kernel<float, __nv_bfloat16>, (const float*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == VG_BF16 && dst_dtype == VG_F32) vg::Launch(grid, 256, 0, s)(cast_kernel<__nv_bfloat16, float>, (const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == VG_F32 && dst_dtype == VG_F32) vg::Launch(grid, 256, 0, s)(cast_kernel<float, float>, (const float*)src, (float*)dst, n);
+  else if (src_dtype == VG_BF16 && dst_dtype == VG_BF16) vg::Launch(grid, 256, 0, s)(cast_kernel<__nv_bfloat16, __nv_bfloat16>, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
   else { set_error("bad dtypes %d -> %d", src_dtype, dst_dtype); return VG_EINVAL; }
   VG_LAUNCHED();
   return VG_OK;
@@ -1015,8 +1042,8 @@ extern "C" int vg_nchw_to_nhwc(const float* src, int n, int c, int h, int w, int
   if (n == 0) return VG_OK;
   VG_CHECK_ARG(n <= 65535, "n too large for this helper");
   dim3 grid((unsigned)cdiv(h * w, 32), (unsigned)cdiv(c, 32), (unsigned)n), block(32, 8);
-  if (dst_dtype == VG_BF16) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>(src, c, h * w, (__nv_bfloat16*)dst);
-  else nchw_to_nhwc_kernel<float><<<grid, block, 0, as_stream(stream)>>>(src, c, h * w, (float*)dst);
+  if (dst_dtype == VG_BF16) vg::Launch(grid, block, 0, as_stream(stream))(nchw_to_nhwc_kernel<__nv_bfloat16>, src, c, h * w, (__nv_bfloat16*)dst);
+  else vg::Launch(grid, block, 0, as_stream(stream))(nchw_to_nhwc_kernel<float>, src, c, h * w, (float*)dst);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1026,8 +1053,8 @@ extern "C" int vg_nhwc_to_nchw(const void* src, int src_dtype, int n, int c, int
   if (n == 0) return VG_OK;
   VG_CHECK_ARG(n <= 65535, "n too large for this helper");
   dim3 grid((unsigned)cdiv(h * w, 32), (unsigned)cdiv(c, 32), (unsigned)n), block(32, 8);
-  if (src_dtype == VG_BF16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, c, h * w, dst);
-  else nhwc_to_nchw_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)src, c, h * w, dst);
+  if (src_dtype == VG_BF16) vg::Launch(grid, block, 0, as_stream(stream))(nhwc_to_nchw_kernel<__nv_bfloat16>, (const __nv_bfloat16*)src, c, h * w, dst);
+  else vg::Launch(grid, block, 0, as_stream(stream))(nhwc_to_nchw_kernel<float>, (const float*)src, c, h * w, dst);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1037,7 +1064,7 @@ extern "C" int vg_fold_bn_into_conv(const float* w, const float* bias_in, const 
                                     float* bias_out, vg_stream_t stream) {
   VG_CHECK_ARG(w && gamma && beta && running_mean && running_var && w_out && bias_out && c_out > 0 && c_in > 0 && inner > 0, "bad args");
   const long long total = (long long)c_out * c_in * inner;
-  fold_bn_into_conv_kernel<<<ew_grid(total), 256, 0, as_stream(stream)>>>(w, bias_in, gamma, beta, running_mean, running_var, eps, c_out, c_in,
+  vg::Launch(ew_grid(total), 256, 0, as_stream(stream))(fold_bn_into_conv_kernel, w, bias_in, gamma, beta, running_mean, running_var, eps, c_out, c_in,
                                                                           inner, transposed, w_out, bias_out);
   VG_LAUNCHED();
   return VG_OK;
@@ -1046,7 +1073,7 @@ extern "C" int vg_fold_bn_into_conv(const float* w, const float* bias_in, const 
 extern "C" int vg_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, int c,
                                  float* scale, float* shift, vg_stream_t stream) {
   VG_CHECK_ARG(gamma && beta && running_mean && running_var && scale && shift && c > 0, "bad args");
-  bn_eval_affine_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(gamma, beta, running_mean, running_var, eps, c, scale, shift);
+  vg::Launch((c + 127) / 128, 128, 0, as_stream(stream))(bn_eval_affine_kernel, gamma, beta, running_mean, running_var, eps, c, scale, shift);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1056,9 +1083,9 @@ extern "C" int vg_scale(const void* src, const float* scale, long long n, int dt
   VG_CHECK_ARG(dtype == VG_F32 || dtype == VG_BF16, "bad dtype %d", dtype);
   if (n == 0) return VG_OK;
   if (dtype == VG_BF16)
-    scale_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, scale, n, (__nv_bfloat16*)dst);
+    vg::Launch(ew_grid(n), 256, 0, as_stream(stream))(scale_kernel<__nv_bfloat16>, (const __nv_bfloat16*)src, scale, n, (__nv_bfloat16*)dst);
   else
-    scale_kernel<float><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const float*)src, scale, n, (float*)dst);
+    vg::Launch(ew_grid(n), 256, 0, as_stream(stream))(scale_kernel<float>, (const float*)src, scale, n, (float*)dst);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1070,11 +1097,11 @@ extern "C" int vg_normalize_images(const void* raw, int raw_dtype, int n, long l
   cudaStream_t s = as_stream(stream);
   __nv_bfloat16* ob = (__nv_bfloat16*)out_bf16;
   switch (raw_dtype) {
-    case VG_RAW_U8: normalize_images_kernel<uint8_t><<<n, 256, 0, s>>>((const uint8_t*)raw, pixels_per_image, out_f32, ob); break;
-    case VG_RAW_U16: normalize_images_kernel<uint16_t><<<n, 256, 0, s>>>((const uint16_t*)raw, pixels_per_image, out_f32, ob); break;
-    case VG_RAW_I16: normalize_images_kernel<int16_t><<<n, 256, 0, s>>>((const int16_t*)raw, pixels_per_image, out_f32, ob); break;
-    case VG_RAW_F32: normalize_images_kernel<float><<<n, 256, 0, s>>>((const float*)raw, pixels_per_image, out_f32, ob); break;
-    case VG_RAW_F64: normalize_images_kernel<double><<<n, 256, 0, s>>>((const double*)raw, pixels_per_image, out_f32, ob); break;
+    case VG_RAW_U8: vg::Launch(n, 256, 0, s)(normalize_images_kernel<uint8_t>, (const uint8_t*)raw, pixels_per_image, out_f32, ob); break;
+    case VG_RAW_U16: vg::Launch(n, 256, 0, s)(normalize_images_kernel<uint16_t>, (const uint16_t*)raw, pixels_per_image, out_f32, ob); break;
+    case VG_RAW_I16: vg::Launch(n, 256, 0, s)(normalize_images_kernel<int16_t>, (const int16_t*)raw, pixels_per_image, out_f32, ob); break;
+    case VG_RAW_F32: vg::Launch(n, 256, 0, s)(normalize_images_kernel<float>, (const float*)raw, pixels_per_image, out_f32, ob); break;
+    case VG_RAW_F64: vg::Launch(n, 256, 0, s)(normalize_images_kernel<double>, (const double*)raw, pixels_per_image, out_f32, ob); break;
     default: set_error("unknown raw dtype %d", raw_dtype); return VG_EINVAL;
   }
   VG_LAUNCHED();

@@ -15,6 +15,7 @@ void set_error(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
 extern int g_num_sms;
 extern int g_force_simt;
+extern int g_pdl;   // VG_PDL: 1 (default) = kernels are launched with programmatic stream serialization, 0 = plain launches
 
 #define VG_CHECK_ARG(cond, ...)                  \
   do {                                           \
@@ -49,6 +50,43 @@ static inline cudaStream_t as_stream(vg_stream_t s) { return reinterpret_cast<cu
 static inline size_t dtype_size(int dt) { return dt == VG_BF16 ? 2 : 4; }
 static inline int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- kernel launch with programmatic dependent launch (PDL) --------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and calls
+// pdl_entry() before its first global-memory access: `griddepcontrol.wait` blocks until the grid it depends on has
+// completed and its memory is visible (a no-op for a plain launch), so no load or store of a kernel can pass the
+// previous kernel's - while the launch itself, the CTA rasterisation and whatever a kernel does BEFORE pdl_entry()
+// (mbarrier init, TMEM allocation, tensor-map prefetch in the tcgen05 / bulk-copy kernels) overlap the previous
+// kernel's tail.  Inside the captured iteration these become programmatic edges of the CUDA graph.
+// Measured on B200 (profiles/r2_pdl_ab.txt): batch 32 10.88 -> 10.59 ms/step, batch 256 unchanged.  An EARLY
+// `griddepcontrol.launch_dependents` right behind the wait (next grid resident while this one runs; build with
+// -DVG_PDL_TRIGGER=1) gave that gain back (10.88 ms) and cost 0.6 % at batch 256, so it is off.
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#if defined(VG_PDL_TRIGGER) && VG_PDL_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+struct Launch {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  Launch(dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+  }
+  template <typename... KArgs, typename... Args>
+  void operator()(void (*kernel)(KArgs...), Args&&... args) {
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in VG_LAUNCHED()
+  }
+};
 
 // ---- device helpers -----------------------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }
