@@ -51,6 +51,22 @@ const char* vg_last_error(void);
 unsigned long long vg_launch_count(void);  /* kernels launched by this library so far */
 /* force every convolution through the SIMT kernels (debug/bisect); returns previous value */
 int vg_set_force_simt(int on);
+/* Deterministic reductions (hard part 1; torch.use_deterministic_algorithms is what a user of the
+ * reference would reach for).  While on, no floating-point sum that crosses thread blocks uses atomics:
+ *   - per-channel / per-tap / scalar sums (BatchNorm statistics and backward sums, the second-order BatchNorm sums of
+ *     the gradient penalty, single-channel weight gradients, bias gradients, spectral-norm dots, generator-loss
+ *     scalars) are written as per-block partial sums into `scratch` and added in block order by a second small kernel;
+ *   - split-K tensor-core convolutions / Linear layers, the tensor-core and CUDA-core weight gradients and the small
+ *     GEMM keep their reductions but the splits of one output tile take turns in split order (`locks`: one int32 turn
+ *     counter per output tile, zeroed by the caller, left zeroed by every launch);
+ *   - BatchNorm statistics fused into a convolution epilogue and the bulk-copy single-channel weight gradient are
+ *     switched off; configurations without an ordered variant (BatchNorm with C % 8 != 0 and C != 1) return
+ *     VG_EUNSUPPORTED.
+ * Both buffers are caller-owned device memory and must stay valid (and `scratch` unused by anything else on the
+ * streams the library is called on) while the mode is on: scratch >= 1 MiB, 16-byte aligned (64 MiB covers every
+ * BASELINE configuration), n_locks >= 1024.  Process-wide, one device.  on = 0 switches back (buffers may be NULL). */
+int vg_set_deterministic(int on, void* scratch, size_t scratch_bytes, void* locks, int n_locks);
+int vg_get_deterministic(void);
 
 /* ---- convolutions: nn.Conv2d (README.md:148,151,163,165,170,379,383,387,441,556-571) and
  *      nn.ConvTranspose2d (README.md:156,158) -------------------------------------------- */

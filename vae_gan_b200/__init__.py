@@ -6,7 +6,8 @@ from .modules import (Decoder, Discriminator, Encoder, ResBlockDiscriminator, Re
                       SpatialVAECodeProcessor, UnsupervisedGeneratorNetwork, build_vae_gan, init_weights)
 from .train import VaeGanTrainer
 from .data import InputPipeline, normalize_images
+from ._lib import is_deterministic, set_deterministic
 
 __all__ = ["ResBlockVAE", "Encoder", "Decoder", "ResBlockDiscriminator", "Discriminator",
            "SpatialVAECodeProcessor", "UnsupervisedGeneratorNetwork", "init_weights", "build_vae_gan",
-           "VaeGanTrainer", "InputPipeline", "normalize_images", "functional", "compute_dtype", "config", "rng"]
+           "VaeGanTrainer", "InputPipeline", "normalize_images", "set_deterministic", "is_deterministic", "functional", "compute_dtype", "config", "rng"]

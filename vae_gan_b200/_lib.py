@@ -70,6 +70,8 @@ _PROTOS = {
     "vg_last_error": (C.c_char_p, []),
     "vg_launch_count": (c_ull, []),
     "vg_set_force_simt": (c_int, [c_int]),
+    "vg_set_deterministic": (c_int, [c_int, c_vp, C.c_size_t, c_vp, c_int]),
+    "vg_get_deterministic": (c_int, []),
     "vg_conv_pack_weights": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "vg_conv_pack_weights_batched": (c_int, [c_vp, c_int, c_int, c_vp]),
     "vg_conv_forward_scaled": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
@@ -169,6 +171,39 @@ def ensure_device(device: torch.device):
         if rc != 0:
             raise VgError(f"vg_init({idx}) failed ({rc}): {lib.vg_last_error().decode()}")
         _inited_devices.add(idx)
+        if os.environ.get("VG_DETERMINISTIC", "0") == "1" and _det_buffers is None:
+            set_deterministic(True, torch.device("cuda", idx))
+
+
+_det_buffers = None      # (scratch, locks): caller-owned memory of the deterministic mode, alive while it is on
+
+
+def set_deterministic(on: bool, device=None, scratch_mb: int = 64, n_locks: int = 1 << 16):
+    """Bit-reproducible reductions (include/vaegan_b200.h, vg_set_deterministic): every cross-block floating-point sum -
+    BatchNorm statistics / backward sums, split-K convolutions and Linear layers, weight gradients, bias gradients,
+    spectral-norm dots, loss scalars - is accumulated in a fixed order (per-block partial sums added in block order, or
+    the splits of one output tile taking turns) instead of with atomics, so two runs from the same state give identical
+    bits.  Costs a few percent (profiles/README.md).  Also enabled by VG_DETERMINISTIC=1 at the first use of a device."""
+    global _det_buffers
+    lib = load()
+    if not on:
+        rc = lib.vg_set_deterministic(0, None, 0, None, 0)
+        _det_buffers = None
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        ensure_device(dev)
+        scratch = torch.empty(scratch_mb << 20, dtype=torch.uint8, device=dev)
+        locks = torch.zeros(n_locks, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        rc = lib.vg_set_deterministic(1, scratch.data_ptr(), scratch.numel(), locks.data_ptr(), n_locks)
+        if rc == 0:
+            _det_buffers = (scratch, locks)
+    if rc != 0:
+        raise VgError(f"vg_set_deterministic failed ({rc}): {lib.vg_last_error().decode()}")
+
+
+def is_deterministic() -> bool:
+    return bool(load().vg_get_deterministic())
 
 
 def call(name: str, *args):

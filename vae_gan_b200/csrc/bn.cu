@@ -86,7 +86,8 @@ __host__ __device__ inline uint32_t thr16_of(float p) {
 // acc[v][8]: v-th quantity for the thread's 8 channels.  `fold`: all 8 lanes are channel 0.
 template <int NV>
 __device__ __forceinline__ void block_reduce_to_global(float (&acc)[NV][8], const RowMap& m, int c, bool fold,
-                                                       double* out /* [NV][c] */, float* smem) {
+                                                       double* out /* [NV][c] */, float* smem,
+                                                       double* partials = nullptr /* deterministic mode: [grid][NV][c] */) {
   const int tid = threadIdx.x;
   // smem layout [NV*8][kBnThreads]
 #pragma unroll
@@ -106,7 +107,8 @@ __device__ __forceinline__ void block_reduce_to_global(float (&acc)[NV][8], cons
       if (tid == 0) {
         double t = 0.0;
         for (int w = 0; w < kBnThreads / 32; ++w) t += wsum[w];
-        atomicAdd(&out[v * c], t);
+        if (partials) partials[(size_t)blockIdx.x * NV * c + v * c] = t;
+        else atomicAdd(&out[v * c], t);
       }
       __syncthreads();
     }
@@ -118,7 +120,8 @@ __device__ __forceinline__ void block_reduce_to_global(float (&acc)[NV][8], cons
     int g = ch >> 3, j = ch & 7;
     double s = 0.0;
     for (int r = 0; r < m.rpb; ++r) s += (double)smem[(v * 8 + j) * kBnThreads + r * m.cg + g];
-    atomicAdd(&out[v * c + ch], s);
+    if (partials) partials[(size_t)blockIdx.x * NV * c + idx] = s;
+    else atomicAdd(&out[v * c + ch], s);
   }
 }
 
@@ -127,7 +130,7 @@ __device__ __forceinline__ void block_reduce_to_global(float (&acc)[NV][8], cons
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_vec_kernel(const T* __restrict__ x, long long rows, int c,
-                                                                   bool fold, double* __restrict__ sums) {
+                                                                   bool fold, double* __restrict__ sums, double* __restrict__ partials) {
   vg::pdl_entry();
   extern __shared__ float smem[];
   const int cv = fold ? 8 : c;
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_vec_kernel(const T* __res
       for (int j = 0; j < 8; ++j) { acc[0][j] += v.v[j]; acc[1][j] += v.v[j] * v.v[j]; }
     }
   }
-  block_reduce_to_global<2>(acc, m, c, fold, sums, smem);
+  block_reduce_to_global<2>(acc, m, c, fold, sums, smem, partials);
 }
 
 template <typename T>
@@ -314,6 +317,7 @@ __global__ void __launch_bounds__(kBnThreads, APPLY ? 1 : 3) bn_act_bwd_vec_kern
                                                                      const float* __restrict__ mean_rstd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                      BnK k, double* __restrict__ sums_out /* reduce */,
+                                                                     double* __restrict__ partials /* reduce, deterministic mode */,
                                                                      const double* __restrict__ sums_in /* apply */, double count,
                                                                      const float* __restrict__ out_colscale,
                                                                      const T* __restrict__ addend, T* __restrict__ dx) {
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(kBnThreads, APPLY ? 1 : 3) bn_act_bwd_vec_kern
       }
     }
   }
-  if (!APPLY) block_reduce_to_global<2>(acc, m, k.c, k.fold, sums_out, smem);
+  if (!APPLY) block_reduce_to_global<2>(acc, m, k.c, k.fold, sums_out, smem, partials);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -430,7 +434,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_dbl_bwd_vec_kernel(const T* __r
                                                                     const T* __restrict__ G, const float* __restrict__ mean_rstd,
                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                     BnK k, const float* __restrict__ colscale,
-                                                                    double* __restrict__ sums_out, const double* __restrict__ sums_in,
+                                                                    double* __restrict__ sums_out, double* __restrict__ partials,
+                                                                    const double* __restrict__ sums_in,
                                                                     double count, T* __restrict__ g_dy, T* __restrict__ g_x) {
   vg::pdl_entry();
   extern __shared__ float smem[];
@@ -505,7 +510,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_dbl_bwd_vec_kernel(const T* __r
       }
     }
   }
-  if (!APPLY) block_reduce_to_global<5>(acc, m, k.c, false, sums_out, smem);
+  if (!APPLY) block_reduce_to_global<5>(acc, m, k.c, false, sums_out, smem, partials);
 }
 
 template <typename T, bool APPLY>
@@ -558,7 +563,8 @@ __global__ void __launch_bounds__(kBnThreads, 3) bn_add_vec_kernel(const T* __re
                                                                  const float* __restrict__ gA, const float* __restrict__ bA,
                                                                  const T* __restrict__ B, const float* __restrict__ mrB,
                                                                  const float* __restrict__ gB, const float* __restrict__ bB, BnK k,
-                                                                 T* __restrict__ out, double* __restrict__ stats) {
+                                                                 T* __restrict__ out, double* __restrict__ stats,
+                                                                 double* __restrict__ partials) {
   vg::pdl_entry();
   extern __shared__ float smem[];
   const int cv = k.fold ? 8 : k.c;
@@ -610,7 +616,7 @@ __global__ void __launch_bounds__(kBnThreads, 3) bn_add_vec_kernel(const T* __re
       }
     }
   }
-  if (STATS) block_reduce_to_global<2>(acc, m, k.c, k.fold, stats, smem);
+  if (STATS) block_reduce_to_global<2>(acc, m, k.c, k.fold, stats, smem, partials);
 }
 
 template <typename T>
@@ -790,11 +796,18 @@ extern "C" int vg_bn_stats(const void* x, const VgBnDesc* d, double* sums, vg_st
     int cv = fold ? 8 : d->c;
     RowMap m = make_rowmap(cv);
     int grid = grid_for(rows, m.rpb, kUnrollWide * 2, kReduceBlocksPerSm);
+    double* part = nullptr;
+    if (g_det.on && !(part = (double*)det_scratch((size_t)grid * 2 * d->c * sizeof(double)))) return VG_EINVAL;
     if (d->dtype == VG_BF16)
-      vg::Launch(grid, kBnThreads, vec_smem(), s)(bn_stats_vec_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, rows, d->c, fold, sums);
+      vg::Launch(grid, kBnThreads, vec_smem(), s)(bn_stats_vec_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, rows, d->c, fold, sums, part);
     else
-      vg::Launch(grid, kBnThreads, vec_smem(), s)(bn_stats_vec_kernel<float>, (const float*)x, rows, d->c, fold, sums);
+      vg::Launch(grid, kBnThreads, vec_smem(), s)(bn_stats_vec_kernel<float>, (const float*)x, rows, d->c, fold, sums, part);
+    if (part) {
+      VG_LAUNCHED();
+      return ordered_reduce_f64(part, grid, 2LL * d->c, sums, s);
+    }
   } else {
+    VG_DET_UNSUPPORTED("BatchNorm statistics with C % 8 != 0");
     long long total = d->rows * d->c;
     int grid = (int)std::min<long long>(cdiv(total, 256 * 8), (long long)num_sms() * 4);
     size_t sm = (size_t)2 * d->c * sizeof(double);
@@ -926,11 +939,18 @@ static int bn_act_backward_t(const T* dy, const T* x, const float* mr, const flo
     RowMap m = make_rowmap(k.fold ? 8 : d->c);
     int grid = grid_for(rows, m.rpb, APPLY ? kUnroll : kUnrollWide, APPLY ? apply_blocks_per_sm() : kReduceBlocksPerSm);
     size_t sm = APPLY ? 0 : vec_smem();
+    double* part = nullptr;
+    if (!APPLY && g_det.on && !(part = (double*)det_scratch((size_t)grid * 2 * d->c * sizeof(double)))) return VG_EINVAL;
     if (k.thr16)
-      vg::Launch(grid, kBnThreads, sm, s)(bn_act_bwd_vec_kernel<T, true, APPLY>, dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
+      vg::Launch(grid, kBnThreads, sm, s)(bn_act_bwd_vec_kernel<T, true, APPLY>, dy, x, mr, gamma, beta, k, sums_out, part, sums_in, count, ocs, addend, dx);
     else
-      vg::Launch(grid, kBnThreads, sm, s)(bn_act_bwd_vec_kernel<T, false, APPLY>, dy, x, mr, gamma, beta, k, sums_out, sums_in, count, ocs, addend, dx);
+      vg::Launch(grid, kBnThreads, sm, s)(bn_act_bwd_vec_kernel<T, false, APPLY>, dy, x, mr, gamma, beta, k, sums_out, part, sums_in, count, ocs, addend, dx);
+    if (part) {
+      VG_LAUNCHED();
+      return ordered_reduce_f64(part, grid, 2LL * d->c, sums_out, s);
+    }
   } else {
+    if (!APPLY) VG_DET_UNSUPPORTED("BatchNorm backward with C % 8 != 0");
     long long total = d->rows * d->c;
     int grid = (int)std::min<long long>(cdiv(total, 256 * 4), (long long)num_sms() * 8);
     size_t sm = APPLY ? 0 : (size_t)2 * d->c * sizeof(double);
@@ -1002,9 +1022,12 @@ static int bn_dbl_bwd_t(const T* dy, const T* x, const T* G, const float* mean_r
   RowMap m = make_rowmap(d->c);
   int grid = grid_for(d->rows, m.rpb, kUnroll, APPLY ? apply_blocks_per_sm() : kReduceBlocksPerSm);
   const size_t smem = APPLY ? 0 : (size_t)5 * 8 * kBnThreads * sizeof(float);
-  vg::Launch(grid, kBnThreads, smem, s)(bn_dbl_bwd_vec_kernel<T, APPLY>, dy, x, G, mean_rstd, gamma, beta, k, colscale, sums_out, sums_in, count,
-                                                                 g_dy, g_x);
+  double* part = nullptr;
+  if (!APPLY && g_det.on && !(part = (double*)det_scratch((size_t)grid * 5 * d->c * sizeof(double)))) return VG_EINVAL;
+  vg::Launch(grid, kBnThreads, smem, s)(bn_dbl_bwd_vec_kernel<T, APPLY>, dy, x, G, mean_rstd, gamma, beta, k, colscale, sums_out, part, sums_in,
+                                        count, g_dy, g_x);
   VG_LAUNCHED();
+  if (part) return ordered_reduce_f64(part, grid, 5LL * d->c, sums_out, s);
   return VG_OK;
 }
 
@@ -1054,11 +1077,18 @@ static int bn_add_t(const T* a, const float* mra, const float* ga, const float* 
     k.rows = rows;
     RowMap m = make_rowmap(k.fold ? 8 : d->c);
     int grid = grid_for(rows, m.rpb, kUnroll, stats ? kReduceBlocksPerSm : apply_blocks_per_sm());
+    double* part = nullptr;
+    if (stats && g_det.on && !(part = (double*)det_scratch((size_t)grid * 2 * d->c * sizeof(double)))) return VG_EINVAL;
     if (stats)
-      vg::Launch(grid, kBnThreads, vec_smem(), s)(bn_add_vec_kernel<T, true>, a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
+      vg::Launch(grid, kBnThreads, vec_smem(), s)(bn_add_vec_kernel<T, true>, a, mra, ga, ba, b, mrb, gb, bb, k, out, stats, part);
     else
-      vg::Launch(grid, kBnThreads, 0, s)(bn_add_vec_kernel<T, false>, a, mra, ga, ba, b, mrb, gb, bb, k, out, stats);
+      vg::Launch(grid, kBnThreads, 0, s)(bn_add_vec_kernel<T, false>, a, mra, ga, ba, b, mrb, gb, bb, k, out, stats, part);
+    if (part) {
+      VG_LAUNCHED();
+      return ordered_reduce_f64(part, grid, 2LL * d->c, stats, s);
+    }
   } else {
+    if (stats) VG_DET_UNSUPPORTED("residual add + statistics with C % 8 != 0");
     long long total = d->rows * d->c;
     int grid = (int)std::min<long long>(cdiv(total, 256 * 4), (long long)num_sms() * 8);
     size_t sm = stats ? (size_t)2 * d->c * sizeof(double) : 0;

@@ -64,6 +64,7 @@ struct Args {
   Chan A, B;
   // reductions
   double* sums_out;
+  double* partials;      // deterministic mode: per-block partial sums [grid][2 * c] instead of atomics on sums_out
   // backward apply
   const double* sums_in;
   double count;
@@ -396,7 +397,11 @@ __global__ void __launch_bounds__(kThreads, 2) bn_stream_kernel(const __grid_con
         double s = 0.0;
         for (int i = tid; i < 8 * kConsumers; i += kConsumers) s += (double)red[q * 8 * kConsumers + i];
         s = warp_sum(s);
-        if (lane == 0) atomicAdd(&a.sums_out[q * c], s);
+        // fold: c == 1; the 8 consumer warps each own a slot in deterministic mode
+        if (lane == 0) {
+          if (a.partials) a.partials[((size_t)blockIdx.x * 2 + q) * (kConsumers / 32) + warp] = s;
+          else atomicAdd(&a.sums_out[q * c], s);
+        }
       }
     } else {
       const int rpb = a.tpb / a.cg;
@@ -405,7 +410,8 @@ __global__ void __launch_bounds__(kThreads, 2) bn_stream_kernel(const __grid_con
         const int gg = ch >> 3, j = ch & 7;
         double s = 0.0;
         for (int r = 0; r < rpb; ++r) s += (double)red[(q * 8 + j) * kConsumers + r * a.cg + gg];
-        atomicAdd(&a.sums_out[q * c + ch], s);
+        if (a.partials) a.partials[(size_t)blockIdx.x * 2 * c + idx] = s;
+        else atomicAdd(&a.sums_out[q * c + ch], s);
       }
     }
   }
@@ -420,6 +426,24 @@ static int ctas_per_sm() {
   return v;
 }
 
+// folded (single-channel) tensors in deterministic mode: partials[block][q][warp] -> sums_out[q * c] (c == 1), one thread
+// per quantity walking blocks and warps in order (a few thousand fp64 adds)
+__global__ void ordered_reduce_fold_kernel(const double* __restrict__ partials, int nblocks, int c, double* __restrict__ out) {
+  vg::pdl_entry();
+  const int q = threadIdx.x;
+  if (q >= 2) return;
+  constexpr int W = kConsumers / 32;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b)
+    for (int w = 0; w < W; ++w) s += partials[((size_t)b * 2 + q) * W + w];
+  out[q * c] += s;
+}
+static int ordered_reduce_fold(const double* partials, int nblocks, double* out, int c, cudaStream_t s) {
+  vg::Launch(1, 32, 0, s)(ordered_reduce_fold_kernel, partials, nblocks, c, out);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
 template <typename T, int MODE, bool DROP>
 static int launch(const Args& a, cudaStream_t s) {
   using G = Geo<T, MODE>;
@@ -431,6 +455,18 @@ static int launch(const Args& a, cudaStream_t s) {
   VG_CUDA(attr_err);
   const long long cap = (long long)num_sms() * ctas_per_sm();
   const int grid = (int)std::max<long long>(1, std::min<long long>(a.ntiles, cap));
+  if (ModeTraits<MODE>::kReduce && g_det.on) {
+    // deterministic mode: per-block partial sums, added in block order by a second tiny kernel.  A folded single-channel
+    // tensor has 2 quantities x 8 warp slots per block, reduced as [grid * 8 "blocks"][2]... laid out [block][q][warp].
+    Args b = a;
+    const size_t per_block = a.fold ? (size_t)2 * (kConsumers / 32) : (size_t)2 * a.c;
+    b.partials = (double*)det_scratch((size_t)grid * per_block * sizeof(double));
+    if (!b.partials) return VG_EINVAL;
+    vg::Launch(grid, kThreads, G::kSmemBytes, s)(bn_stream_kernel<T, MODE, DROP>, b);
+    VG_LAUNCHED();
+    if (a.fold) return ordered_reduce_fold(b.partials, grid, a.sums_out, a.c, s);
+    return ordered_reduce_f64(b.partials, grid, 2LL * a.c, a.sums_out, s);
+  }
   vg::Launch(grid, kThreads, G::kSmemBytes, s)(bn_stream_kernel<T, MODE, DROP>, a);
   VG_LAUNCHED();
   return VG_OK;

@@ -532,10 +532,14 @@ __global__ void __launch_bounds__(256) conv_expand1_strip_kernel(const TI* __res
 
 template <typename T, bool FLIP>
 __global__ void __launch_bounds__(256) wgrad_degenerate_strip_kernel(const T* __restrict__ V, const T* __restrict__ S, int n, int h,
-                                                                     int w, int c, unsigned strips_per_block, float* __restrict__ dw) {
+                                                                     int w, int c, unsigned strips_per_block, float* __restrict__ dw,
+                                                                     float* __restrict__ partials) {
   vg::pdl_entry();
-  extern __shared__ float sacc[];   // [9 * c]
-  for (int i = threadIdx.x; i < 9 * c; i += blockDim.x) sacc[i] = 0.f;
+  // [9 * c]; deterministic mode (partials != nullptr): one such slot per warp, combined in warp order, and the block's
+  // sums go to partials[block][c * 9] (added in block order by ordered_reduce_f32) instead of atomics on dw
+  extern __shared__ float sacc[];
+  const int nslot = partials ? (int)(blockDim.x >> 5) : 1;
+  for (int i = threadIdx.x; i < nslot * 9 * c; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   const int groups = c / 8;
   const int lanes = blockDim.x / groups;
@@ -587,15 +591,25 @@ __global__ void __launch_bounds__(256) wgrad_degenerate_strip_kernel(const T* __
       acc[t][j] = a;
     }
   if (lid < groups || groups >= 32) {
+    float* slot = sacc + (partials ? (threadIdx.x >> 5) * 9 * c : 0);
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&sacc[t * c + grp * 8 + j], acc[t][j]);
+      for (int j = 0; j < 8; ++j) {
+        if (partials) slot[t * c + grp * 8 + j] = acc[t][j];       // one writer per (warp, tap, channel)
+        else atomicAdd(&slot[t * c + grp * 8 + j], acc[t][j]);
+      }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 9 * c; i += blockDim.x) {
     const int tap = i / c, ch = i % c;
-    atomicAdd(&dw[(long long)ch * 9 + tap], sacc[i]);
+    if (partials) {
+      float t = sacc[i];
+      for (int ws = 1; ws < nslot; ++ws) t += sacc[ws * 9 * c + i];
+      partials[(size_t)blockIdx.x * 9 * c + (size_t)ch * 9 + tap] = t;
+    } else {
+      atomicAdd(&dw[(long long)ch * 9 + tap], sacc[i]);
+    }
   }
 }
 
@@ -778,7 +792,7 @@ static int try_degenerate_stream(bool flip, const void* V, const void* S, int n,
   *taken = false;
   static int on = -1;
   if (on < 0) { const char* e = getenv("VG_DEG_STREAM"); on = e ? atoi(e) : 1; }
-  if (!on) return VG_OK;
+  if (!on || g_det.on) return VG_OK;      // deterministic mode: the strip kernel has the ordered reduction
   const int groups = c / 8;
   if (c % 8 != 0 || groups > 256 || 256 % groups != 0 || w % 8 != 0) return VG_OK;
   if (((size_t)w * sizeof(T)) % 16 != 0 || ((uintptr_t)V & 15) != 0 || ((uintptr_t)S & 15) != 0) return VG_OK;
@@ -823,11 +837,13 @@ static int try_degenerate_stream(bool flip, const void* V, const void* S, int n,
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256, 2) wgrad_degenerate_kernel(const T* __restrict__ V, const T* __restrict__ S, int n, int hv,
                                                                int wv, int c, int hs, int ws, int kh, int kw, int stride, int pad,
-                                                               bool a_mode, unsigned pix_per_block, float* __restrict__ dw) {
+                                                               bool a_mode, unsigned pix_per_block, float* __restrict__ dw,
+                                                               float* __restrict__ partials) {
   vg::pdl_entry();
-  extern __shared__ float sacc[];   // [taps * c]
+  extern __shared__ float sacc[];   // [taps * c]; deterministic mode: one slot per warp (see wgrad_degenerate_strip_kernel)
   const int taps = kh * kw;
-  for (int i = threadIdx.x; i < taps * c; i += blockDim.x) sacc[i] = 0.f;
+  const int nslot = partials ? (int)(blockDim.x >> 5) : 1;
+  for (int i = threadIdx.x; i < nslot * taps * c; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   const int groups = c / VEC;                 // channel groups per pixel
   const int lanes = blockDim.x / groups;      // pixels processed concurrently
@@ -910,8 +926,8 @@ __global__ void __launch_bounds__(256, 2) wgrad_degenerate_kernel(const T* __res
           if (ky >= kh || kx >= kw) continue;
 #pragma unroll
           for (int j = 0; j < VEC; ++j) {
-            float* dst = &sacc[(ky * kw + kx) * c + grp * VEC + j];
-            if (groups >= 32) atomicAdd(dst, acc[ky * 3 + kx][j]);        // wide layers: few threads per group
+            float* dst = &sacc[(partials ? (threadIdx.x >> 5) * taps * c : 0) + (ky * kw + kx) * c + grp * VEC + j];
+            if (partials) *dst = acc[ky * 3 + kx][j];                     // one writer per (warp, tap, channel)
             else atomicAdd(dst, acc[ky * 3 + kx][j]);                     // <= 8 warps contend per address
           }
         }
@@ -920,7 +936,13 @@ __global__ void __launch_bounds__(256, 2) wgrad_degenerate_kernel(const T* __res
   __syncthreads();
   for (int i = threadIdx.x; i < taps * c; i += blockDim.x) {
     const int tap = i / c, ch = i % c;
-    atomicAdd(&dw[(long long)ch * taps + tap], sacc[i]);
+    if (partials) {
+      float t = sacc[i];
+      for (int ws = 1; ws < nslot; ++ws) t += sacc[ws * taps * c + i];
+      partials[(size_t)blockIdx.x * taps * c + (size_t)ch * taps + tap] = t;
+    } else {
+      atomicAdd(&dw[(long long)ch * taps + tap], sacc[i]);
+    }
   }
 }
 
@@ -934,7 +956,7 @@ struct WgradGeom {
 
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(const T* __restrict__ U, const T* __restrict__ S, WgradGeom g,
-                                                          float* __restrict__ dw) {
+                                                          float* __restrict__ dw, int* __restrict__ det_locks) {
   vg::pdl_entry();
   __shared__ float su[32][33];
   __shared__ float ss[32][33];
@@ -983,6 +1005,12 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const T* __restrict__ U
     __syncthreads();
   }
   const int taps = g.kh * g.kw;
+  // deterministic mode: the pixel splits (blockIdx.z) of one (tile, tap) add in split order
+  int* const det_lock = det_locks ? det_locks + (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (det_lock) {
+    if (tid == 0) det_wait_turn(det_lock, (int)blockIdx.z);
+    __syncthreads();
+  }
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -990,18 +1018,25 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const T* __restrict__ U
       int cu = tile_u * 32 + tu * 2 + a, cs = tile_s * 32 + ts * 2 + b;
       if (cu < g.cu && cs < g.cs) atomicAdd(&dw[((long long)cu * g.cs + cs) * taps + tap], acc[a][b]);
     }
+  if (det_lock) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) det_publish_turn(det_lock, blockIdx.z + 1 == gridDim.z ? 0 : (int)blockIdx.z + 1);
+  }
 }
 
 // dbias[c] += sum over rows of dy[row][c]
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ x, long long rows, int c, long long rows_per_block, float* __restrict__ out) {
+__global__ void colsum_kernel(const T* __restrict__ x, long long rows, int c, long long rows_per_block, float* __restrict__ out,
+                              float* __restrict__ partials) {
   vg::pdl_entry();
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     float s = 0.f;
     for (long long r = r0; r < r1; ++r) s += to_f32(x[r * c + ch]);
-    atomicAdd(&out[ch], s);
+    if (partials) partials[(size_t)blockIdx.x * c + ch] = s;
+    else atomicAdd(&out[ch], s);
   }
 }
 
@@ -1115,14 +1150,21 @@ int simt_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* d
       unsigned spb = (unsigned)cdiv(nstrips, blocks);
       blocks = cdiv(nstrips, spb);
       size_t sm2 = (size_t)9 * c * sizeof(float);
+      float* part = nullptr;
+      if (g_det.on) {
+        sm2 *= 8;                                                    // one slot per warp
+        if (sm2 > 48 * 1024) VG_DET_UNSUPPORTED("single-channel weight gradient with more than 170 channels");
+        if (!(part = (float*)det_scratch((size_t)blocks * 9 * c * sizeof(float)))) return VG_EINVAL;
+      }
       if (d->act_dtype == VG_BF16) {
-        if (a_mode) vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<__nv_bfloat16, false>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, spb, dw);
-        else        vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<__nv_bfloat16, true>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, spb, dw);
+        if (a_mode) vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<__nv_bfloat16, false>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, spb, dw, part);
+        else        vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<__nv_bfloat16, true>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, spb, dw, part);
       } else {
-        if (a_mode) vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<float, false>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, spb, dw);
-        else        vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<float, true>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, spb, dw);
+        if (a_mode) vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<float, false>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, spb, dw, part);
+        else        vg::Launch((unsigned)blocks, 256, sm2, s)(wgrad_degenerate_strip_kernel<float, true>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, spb, dw, part);
       }
       VG_LAUNCHED();
+      if (part) return ordered_reduce_f32(part, (int)blocks, 9LL * c, dw, s);
       return VG_OK;
     }
     const int vec = (c % 8 == 0 && c / 8 <= 256) ? 8 : 1;
@@ -1131,14 +1173,21 @@ int simt_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* d
     unsigned ppb = (unsigned)cdiv(npix, blocks);
     blocks = cdiv(npix, ppb);
     size_t sm = (size_t)d->kh * d->kw * c * sizeof(float);
+    float* part = nullptr;
+    if (g_det.on) {
+      sm *= 8;
+      if (sm > 48 * 1024) VG_DET_UNSUPPORTED("single-channel weight gradient with this many channels");
+      if (!(part = (float*)det_scratch((size_t)blocks * d->kh * d->kw * c * sizeof(float)))) return VG_EINVAL;
+    }
     if (d->act_dtype == VG_BF16) {
-      if (vec == 8) vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<__nv_bfloat16, 8>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
-      else          vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<__nv_bfloat16, 1>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
+      if (vec == 8) vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<__nv_bfloat16, 8>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw, part);
+      else          vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<__nv_bfloat16, 1>, (const __nv_bfloat16*)V, (const __nv_bfloat16*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw, part);
     } else {
-      if (vec == 8) vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<float, 8>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
-      else          vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<float, 1>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw);
+      if (vec == 8) vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<float, 8>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw, part);
+      else          vg::Launch((unsigned)blocks, 256, sm, s)(wgrad_degenerate_kernel<float, 1>, (const float*)V, (const float*)Sx, d->n, hv, wv, c, hs, ws, d->kh, d->kw, d->stride, d->pad, a_mode, ppb, dw, part);
     }
     VG_LAUNCHED();
+    if (part) return ordered_reduce_f32(part, (int)blocks, (long long)d->kh * d->kw * c, dw, s);
     return VG_OK;
   }
   const int tiles = ((g.cu + 31) / 32) * ((g.cs + 31) / 32);
@@ -1149,10 +1198,12 @@ int simt_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* d
   g.q_per_split = cdiv(cdiv(qtot, splits), 32) * 32;
   splits = cdiv(qtot, g.q_per_split);
   dim3 grid(tiles, taps, (unsigned)splits);
+  int* locks = nullptr;
+  if (g_det.on && splits > 1 && !(locks = det_locks((long long)tiles * taps))) return VG_EINVAL;
   if (d->act_dtype == VG_BF16)
-    vg::Launch(grid, 256, 0, s)(wgrad_simt_kernel<__nv_bfloat16>, (const __nv_bfloat16*)U, (const __nv_bfloat16*)S, g, dw);
+    vg::Launch(grid, 256, 0, s)(wgrad_simt_kernel<__nv_bfloat16>, (const __nv_bfloat16*)U, (const __nv_bfloat16*)S, g, dw, locks);
   else
-    vg::Launch(grid, 256, 0, s)(wgrad_simt_kernel<float>, (const float*)U, (const float*)S, g, dw);
+    vg::Launch(grid, 256, 0, s)(wgrad_simt_kernel<float>, (const float*)U, (const float*)S, g, dw, locks);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -1163,11 +1214,14 @@ int simt_colsum(const void* x, long long rows, int c, int dtype, float* out, cud
   long long rpb = cdiv(rows, blocks);
   blocks = cdiv(rows, rpb);
   int threads = std::min(1024, ((c + 31) / 32) * 32);
+  float* part = nullptr;
+  if (g_det.on && !(part = (float*)det_scratch((size_t)blocks * c * sizeof(float)))) return VG_EINVAL;
   if (dtype == VG_BF16)
-    vg::Launch((int)blocks, threads, 0, s)(colsum_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, rows, c, rpb, out);
+    vg::Launch((int)blocks, threads, 0, s)(colsum_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, rows, c, rpb, out, part);
   else
-    vg::Launch((int)blocks, threads, 0, s)(colsum_kernel<float>, (const float*)x, rows, c, rpb, out);
+    vg::Launch((int)blocks, threads, 0, s)(colsum_kernel<float>, (const float*)x, rows, c, rpb, out, part);
   VG_LAUNCHED();
+  if (part) return ordered_reduce_f32(part, (int)blocks, c, out, s);
   return VG_OK;
 }
 

@@ -66,6 +66,7 @@ struct alignas(64) TcConvParams {
   const float* post_scale;
   const float* post_shift;
   float post_slope;
+  int* det_locks;        // deterministic mode, split-K: one turn counter per output tile (the splits add in split order)
 };
 
 struct alignas(64) TcWgradParams {
@@ -77,6 +78,7 @@ struct alignas(64) TcWgradParams {
   int n_boxes, boxes_per_split;
   int packed;    // 1: dw is the packed scratch [tap][c_s][c_u] (vector reductions); 0: torch layout [c_u][c_s][tap]
   float* dw;
+  int* det_locks;  // deterministic mode: one turn counter per (slab pair, c_u tile); the pixel splits add in split order
 };
 
 constexpr int kTcThreads = 256;
@@ -395,6 +397,12 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
     float st_s[BN / 32], st_q[BN / 32];
 #pragma unroll
     for (int c = 0; c < BN / 32; ++c) st_s[c] = st_q[c] = 0.f;
+    // deterministic split-K: this split's reductions go after those of split z - 1 of the same output tile
+    int* const det_lock = (p.det_locks != nullptr && p.ksplit > 1) ? p.det_locks + (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+    if (det_lock) {
+      if (lane == 0) det_wait_turn(det_lock, (int)blockIdx.z);
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int m = 0; m < nvalid; ++m) {
       const int gx = x0s[m] + xl, gy = y0s[m] + yl, gn = n0s[m] + nl;
@@ -424,6 +432,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
           atomicAdd(p.stats + p.n_out + col, (double)st_q[c]);
         }
       }
+    }
+    if (det_lock) {
+      __threadfence();
+      asm volatile("bar.sync 2, 128;" ::: "memory");      // the four epilogue warps
+      if (warp == 4 && lane == 0) det_publish_turn(det_lock, (int)blockIdx.z + 1 == p.ksplit ? 0 : (int)blockIdx.z + 1);
     }
   }
   ptx::tc_fence_before();
@@ -1071,6 +1084,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_wgrad_kernel(const __grid_const
     }
   }
 
+  int* const det_lock = p.det_locks != nullptr ? p.det_locks + (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (warp >= 4 && det_lock) {
+    if (lane == 0) det_wait_turn(det_lock, (int)blockIdx.z);
+    __syncwarp();
+  }
   if (warp >= 4 && num_k > 0) {
     const int q = warp - 4;
     const int row = q * 32 + lane;
@@ -1104,6 +1122,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_wgrad_kernel(const __grid_const
         }
       }
     }
+  }
+  if (warp >= 4 && det_lock) {
+    __threadfence();
+    asm volatile("bar.sync 2, 128;" ::: "memory");        // the four epilogue warps
+    if (warp == 4 && lane == 0) det_publish_turn(det_lock, blockIdx.z + 1 == gridDim.z ? 0 : (int)blockIdx.z + 1);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -1457,6 +1480,7 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
         p.ksplit = (int)cdiv(total_kb, p.k_per_split);
         grid.z = (unsigned)p.ksplit;
         VG_CUDA(cudaMemsetAsync(out, 0, (size_t)d->n * out_h * out_w * n_out * sizeof(float), s));
+        if (g_det.on && !(p.det_locks = det_locks(ctas))) return VG_EINVAL;
       }
     }
   }
@@ -1474,7 +1498,8 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   const bool big = mt_on && p.ksplit == 1 && ctas1 >= 6LL * num_sms();
   // 256-wide tiles go persistent as soon as there is more than one work item per SM (288 tiles of the 24x24 layers at
   // batch 64 ran as one-shot CTAs without epilogue overlap: 38-85 us for 31 us of tensor work)
-  const bool use_persist = persist && ((BN == 256 && ctas1 > (long long)num_sms()) ||
+  const bool use_persist = persist && !(g_det.on && p.ksplit > 1) &&       // deterministic split-K: the one-shot kernel takes turns
+                           ((BN == 256 && ctas1 > (long long)num_sms()) ||
                                        // 128-wide: the CTA-pair kernel (1000+ TFLOP/s) from two work items per pair on; below 6 x SMs tiles
                                        // these layers ran as one-shot CTAs (G 128->128 @48 at 32 images: 496 TFLOP/s)
                                        (BN == 128 && ctas1 >= 2LL * num_sms()) ||
@@ -1488,7 +1513,7 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   // 128->128 @96 151 -> 217 us, 512->512 @24 110 -> 125 us, whole step 63.7 -> 68.2 ms, against the 17 us streaming
   // statistics kernel it replaces: the epilogue warps are the bottleneck of the short-reduction layers and ~350 extra
   // instructions per chunk double their work.  Kept opt-in (VG_TC_FUSE_STATS=1) and parity-tested.
-  if (fuse_stats && stats != nullptr && p.ksplit == 1 && n_out % 32 == 0 && p.n_store != 1) {
+  if (fuse_stats && !g_det.on && stats != nullptr && p.ksplit == 1 && n_out % 32 == 0 && p.n_store != 1) {
     p.stats = stats;
     if (stats_fused) *stats_fused = true;
   }
@@ -1590,6 +1615,7 @@ int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, 
   p.boxes_per_split = (int)cdiv(p.n_boxes, splits);
   splits = cdiv(p.n_boxes, p.boxes_per_split);
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
+  if (g_det.on && !(p.det_locks = det_locks(tiles))) return VG_EINVAL;
   switch (NB) {
     case 1: rc = launch_wgrad<1, 6>(p, grid, s); break;
     case 2: rc = launch_wgrad<2, 5>(p, grid, s); break;

@@ -8,6 +8,56 @@ std::atomic<unsigned long long> g_launches{0};
 int g_num_sms = 0;
 int g_force_simt = 0;
 int g_pdl = 1;
+DetState g_det = {0, nullptr, 0, nullptr, 0};
+
+void* det_scratch(size_t bytes) {
+  if (bytes > g_det.scratch_bytes) {
+    set_error("deterministic mode: %zu bytes of partial sums exceed the %zu-byte scratch given to vg_set_deterministic", bytes,
+              g_det.scratch_bytes);
+    return nullptr;
+  }
+  return g_det.scratch;
+}
+int* det_locks(long long n) {
+  if (n > g_det.n_locks) {
+    set_error("deterministic mode: %lld output tiles exceed the %d turn counters given to vg_set_deterministic", n, g_det.n_locks);
+    return nullptr;
+  }
+  return g_det.locks;
+}
+
+// 32 values x 8 block slices per CTA; every slice sums its blocks in order, the slices are combined in order
+template <typename T>
+__global__ void __launch_bounds__(256) ordered_reduce_kernel(const T* __restrict__ partials, int nblocks, long long nvals,
+                                                             T* __restrict__ out) {
+  vg::pdl_entry();
+  __shared__ T sm[8][33];
+  const int x = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + x;
+  const int per = (nblocks + 7) / 8;
+  const int b0 = slice * per, b1 = min(nblocks, b0 + per);
+  T s = 0;
+  if (i < nvals)
+    for (int b = b0; b < b1; ++b) s += partials[(long long)b * nvals + i];
+  sm[slice][x] = s;
+  __syncthreads();
+  if (slice == 0 && i < nvals) {
+    T t = sm[0][x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sm[k][x];
+    out[i] += t;
+  }
+}
+int ordered_reduce_f64(const double* partials, int nblocks, long long nvals, double* out, cudaStream_t s) {
+  vg::Launch((unsigned)cdiv(nvals, 32), 256, 0, s)(ordered_reduce_kernel<double>, partials, nblocks, nvals, out);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+int ordered_reduce_f32(const float* partials, int nblocks, long long nvals, float* out, cudaStream_t s) {
+  vg::Launch((unsigned)cdiv(nvals, 32), 256, 0, s)(ordered_reduce_kernel<float>, partials, nblocks, nvals, out);
+  VG_LAUNCHED();
+  return VG_OK;
+}
 static thread_local char t_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -29,6 +79,19 @@ extern "C" int vg_set_force_simt(int on) {
   vg::g_force_simt = on ? 1 : 0;
   return prev;
 }
+
+extern "C" int vg_set_deterministic(int on, void* scratch, size_t scratch_bytes, void* locks, int n_locks) {
+  if (!on) {
+    vg::g_det = vg::DetState{0, nullptr, 0, nullptr, 0};
+    return VG_OK;
+  }
+  VG_CHECK_ARG(scratch && scratch_bytes >= (1u << 20) && locks && n_locks >= 1024,
+               "deterministic mode needs a scratch buffer (>= 1 MiB) and >= 1024 zeroed int32 turn counters");
+  VG_CHECK_ARG(((uintptr_t)scratch & 15) == 0, "scratch must be 16-byte aligned");
+  vg::g_det = vg::DetState{1, (unsigned char*)scratch, scratch_bytes, (int*)locks, n_locks};
+  return VG_OK;
+}
+extern "C" int vg_get_deterministic(void) { return vg::g_det.on; }
 
 extern "C" int vg_init(int device) {
   cudaDeviceProp prop;

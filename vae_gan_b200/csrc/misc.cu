@@ -15,7 +15,8 @@ namespace vg {
 template <typename TA, typename TB>
 __global__ void __launch_bounds__(256) gemm_small_kernel(const TA* __restrict__ A, long long sai, long long sal,
                                                           const TB* __restrict__ B, long long sbl, long long sbj, int I, int J,
-                                                          int L, int l_per_split, float* __restrict__ C, int mode) {
+                                                          int L, int l_per_split, float* __restrict__ C, int mode,
+                                                          int* __restrict__ det_locks) {
   vg::pdl_entry();
   __shared__ float sa[32][33];   // [l][i]
   __shared__ float sb[32][33];   // [l][j]
@@ -55,6 +56,12 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(const TA* __restrict__ 
     }
     __syncthreads();
   }
+  // deterministic mode: the reduction splits (blockIdx.z) of one output tile add in split order
+  int* const det_lock = (det_locks && mode == 2) ? det_locks + (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (det_lock) {
+    if (tid == 0) det_wait_turn(det_lock, (int)blockIdx.z);
+    __syncthreads();
+  }
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -67,6 +74,11 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(const TA* __restrict__ 
         else atomicAdd(c, acc[a][b]);
       }
     }
+  if (det_lock) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) det_publish_turn(det_lock, blockIdx.z + 1 == gridDim.z ? 0 : (int)blockIdx.z + 1);
+  }
 }
 
 __global__ void bias_lrelu_kernel(float* __restrict__ y, const float* __restrict__ bias, long long total, int n, float slope) {
@@ -92,7 +104,9 @@ static int launch_gemm(const TA* A, long long sai, long long sal, const TB* B, l
   if (lps < 32) lps = 32;
   splits = (int)cdiv(L, lps);
   dim3 grid((unsigned)cdiv(J, 32), (unsigned)cdiv(I, 32), (unsigned)splits);
-  vg::Launch(grid, 256, 0, s)(gemm_small_kernel<TA, TB>, A, sai, sal, B, sbl, sbj, I, J, L, lps, C, mode);
+  int* locks = nullptr;
+  if (g_det.on && mode == 2 && splits > 1 && !(locks = det_locks((long long)grid.x * grid.y))) return VG_EINVAL;
+  vg::Launch(grid, 256, 0, s)(gemm_small_kernel<TA, TB>, A, sai, sal, B, sbl, sbj, I, J, L, lps, C, mode, locks);
   VG_LAUNCHED();
   return VG_OK;
 }
@@ -288,11 +302,11 @@ struct SnTable {
   int s_off[VG_SN_MAX];
   int n;
 };
-__global__ void sn_wt_u_batched_kernel(const __grid_constant__ SnTable tb, float* __restrict__ ws) {
+__global__ void sn_wt_u_batched_kernel(const __grid_constant__ SnTable tb, float* __restrict__ ws, int one_slice) {
   vg::pdl_entry();
   const VgSnItem& it = tb.it[blockIdx.z];
   const int rows = it.rows, cols = it.cols;
-  const int slices = max(1, min(rows / 8, 64));
+  const int slices = one_slice ? 1 : max(1, min(rows / 8, 64));     // deterministic mode: a single contributor per t[j]
   const int rps = (rows + slices - 1) / slices;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int r0 = blockIdx.y * rps;
@@ -392,7 +406,8 @@ __global__ void sn_finish_batched_kernel(const __grid_constant__ SnTable tb, con
     *it.sigma = tot;
   }
 }
-__global__ void sn_bwd_dot_kernel(const float* __restrict__ dwh, const float* __restrict__ w, long long n, float* __restrict__ acc) {
+__global__ void sn_bwd_dot_kernel(const float* __restrict__ dwh, const float* __restrict__ w, long long n, float* __restrict__ acc,
+                                  float* __restrict__ partials) {
   vg::pdl_entry();
   float part = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -404,7 +419,8 @@ __global__ void sn_bwd_dot_kernel(const float* __restrict__ dwh, const float* __
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += red[k];
-    atomicAdd(acc, tot);
+    if (partials) partials[blockIdx.x] = tot;
+    else atomicAdd(acc, tot);
   }
 }
 __global__ void sn_bwd_apply_kernel(const float* __restrict__ dwh, const float* __restrict__ u, const float* __restrict__ v,
@@ -456,7 +472,7 @@ __global__ void reparam_bwd_kernel(const T* __restrict__ dz, const float* __rest
 // ------------------------------------------------------------------------------------------
 // fused generator loss + gradients
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_atomic_add(double v, double* dst) {
+__device__ __forceinline__ void block_atomic_add(double v, double* dst, double* partial = nullptr) {
   __shared__ double red[32];
   v = warp_sum(v);
   __syncthreads();
@@ -465,7 +481,8 @@ __device__ __forceinline__ void block_atomic_add(double v, double* dst) {
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    atomicAdd(dst, t);
+    if (partial) *partial = t;          // deterministic mode: per-block partial, added in block order afterwards
+    else atomicAdd(dst, t);
   }
 }
 __device__ __forceinline__ float softplus_f(float x) { return x > 0.f ? x + log1pf(expf(-x)) : log1pf(expf(x)); }
@@ -476,7 +493,8 @@ __global__ void __launch_bounds__(256) generator_loss_kernel(const T* __restrict
                                                               const float* __restrict__ mu, const float* __restrict__ lv,
                                                               const float* __restrict__ logits, VgLossDesc d, T* __restrict__ d_xhat,
                                                               float* __restrict__ d_mu, float* __restrict__ d_lv,
-                                                              float* __restrict__ d_logits, double* __restrict__ losses) {
+                                                              float* __restrict__ d_logits, double* __restrict__ losses,
+                                                              double* __restrict__ partials) {
   vg::pdl_entry();
   const long long gsz = (long long)gridDim.x * blockDim.x;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -512,10 +530,11 @@ __global__ void __launch_bounds__(256) generator_loss_kernel(const T* __restrict
   }
   recon *= (double)inv_pix;
   adv *= (double)inv_b;
-  block_atomic_add(recon, &losses[1]);
-  block_atomic_add(kl, &losses[2]);
-  block_atomic_add(adv, &losses[3]);
-  block_atomic_add((double)d.w_recon * recon + (double)d.w_kl * kl + (double)d.w_adv * adv, &losses[0]);
+  double* pp = partials ? partials + (size_t)blockIdx.x * 4 : nullptr;
+  block_atomic_add(recon, &losses[1], pp ? pp + 1 : nullptr);
+  block_atomic_add(kl, &losses[2], pp ? pp + 2 : nullptr);
+  block_atomic_add(adv, &losses[3], pp ? pp + 3 : nullptr);
+  block_atomic_add((double)d.w_recon * recon + (double)d.w_kl * kl + (double)d.w_adv * adv, &losses[0], pp);
 }
 
 __global__ void discriminator_loss_kernel(const float* __restrict__ d_real, const float* __restrict__ d_fake, int n, int n_global,
@@ -880,7 +899,7 @@ extern "C" int vg_spectral_norm_sigma(const float* w_orig, int rows, int cols, f
   float* sv = workspace + cols;    // [rows]
   if (training) {
     VG_CUDA(cudaMemsetAsync(t, 0, (size_t)cols * sizeof(float), s));
-    int slices = std::max(1, std::min(rows / 8, 64));
+    int slices = g_det.on ? 1 : std::max(1, std::min(rows / 8, 64));   // deterministic mode: one slice, no cross-block sum
     int rps = (int)cdiv(rows, slices);
     dim3 g1((unsigned)cdiv(cols, 128), (unsigned)cdiv(rows, rps));
     vg::Launch(g1, 128, 0, s)(sn_wt_u_kernel, w_orig, u, rows, cols, rps, t);
@@ -918,9 +937,9 @@ extern "C" int vg_spectral_norm_sigma_batched(const VgSnItem* items, int n_items
     VG_CHECK_ARG(off <= workspace_floats, "workspace too small: need %zu floats, have %zu", off, workspace_floats);
     if (training) {
       VG_CUDA(cudaMemsetAsync(workspace, 0, off * sizeof(float), s));
-      const int max_slices = std::max(1, std::min(max_rows / 8, 64));
+      const int max_slices = g_det.on ? 1 : std::max(1, std::min(max_rows / 8, 64));
       dim3 g1((unsigned)cdiv(max_cols, 128), (unsigned)max_slices, (unsigned)tb.n);
-      vg::Launch(g1, 128, 0, s)(sn_wt_u_batched_kernel, tb, workspace);
+      vg::Launch(g1, 128, 0, s)(sn_wt_u_batched_kernel, tb, workspace, g_det.on);
       VG_LAUNCHED();
     }
     dim3 g2((unsigned)max_rows, (unsigned)tb.n);
@@ -939,8 +958,15 @@ extern "C" int vg_spectral_norm_backward(const float* dw_hat, const float* w_ori
   cudaStream_t s = as_stream(stream);
   long long n = (long long)rows * cols;
   VG_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float), s));
-  vg::Launch(ew_grid(n), 256, 0, s)(sn_bwd_dot_kernel, dw_hat, w_orig, n, workspace);
+  float* part = nullptr;
+  const int dot_grid = ew_grid(n);
+  if (g_det.on && !(part = (float*)det_scratch((size_t)dot_grid * sizeof(float)))) return VG_EINVAL;
+  vg::Launch(dot_grid, 256, 0, s)(sn_bwd_dot_kernel, dw_hat, w_orig, n, workspace, part);
   VG_LAUNCHED();
+  if (part) {
+    int rc = ordered_reduce_f32(part, dot_grid, 1, workspace, s);
+    if (rc) return rc;
+  }
   vg::Launch(ew_grid(n), 256, 0, s)(sn_bwd_apply_kernel, dw_hat, u, v, sigma, workspace, rows, cols, dw_orig);
   VG_LAUNCHED();
   return VG_OK;
@@ -980,13 +1006,16 @@ extern "C" int vg_generator_loss(const void* xhat, const float* x, const float* 
   int grid = ew_grid(work, 8);
   VgLossDesc dd = *d;
   if (dd.n_logits_global <= 0) dd.n_logits_global = 1;
+  double* part = nullptr;
+  if (g_det.on && !(part = (double*)det_scratch((size_t)grid * 4 * sizeof(double)))) return VG_EINVAL;
   if (d->xhat_dtype == VG_BF16)
     vg::Launch(grid, 256, 0, as_stream(stream))(generator_loss_kernel<__nv_bfloat16>, (const __nv_bfloat16*)xhat, x, mu, lv, logits, dd,
-                                                                               (__nv_bfloat16*)d_xhat, d_mu, d_lv, d_logits, losses);
+                                                (__nv_bfloat16*)d_xhat, d_mu, d_lv, d_logits, losses, part);
   else
     vg::Launch(grid, 256, 0, as_stream(stream))(generator_loss_kernel<float>, (const float*)xhat, x, mu, lv, logits, dd, (float*)d_xhat, d_mu, d_lv,
-                                                                       d_logits, losses);
+                                                d_logits, losses, part);
   VG_LAUNCHED();
+  if (part) return ordered_reduce_f64(part, grid, 4, losses, as_stream(stream));
   return VG_OK;
 }
 

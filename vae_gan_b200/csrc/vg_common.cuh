@@ -15,6 +15,22 @@ void set_error(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
 extern int g_num_sms;
 extern int g_force_simt;
+// deterministic-reduction mode (vg_set_deterministic): caller-owned scratch for per-block partial sums and a zeroed
+// int array of turn counters for the split-K epilogues
+struct DetState {
+  int on;
+  unsigned char* scratch;
+  size_t scratch_bytes;
+  int* locks;
+  int n_locks;
+};
+extern DetState g_det;
+// out[i] += sum over b (in block order) of partials[b * nvals + i]; one writer per element
+int ordered_reduce_f64(const double* partials, int nblocks, long long nvals, double* out, cudaStream_t s);
+int ordered_reduce_f32(const float* partials, int nblocks, long long nvals, float* out, cudaStream_t s);
+// scratch for `bytes` of partial sums, or nullptr (with the error set) when the caller's buffer is too small
+void* det_scratch(size_t bytes);
+int* det_locks(long long n);
 extern int g_pdl;   // VG_PDL: 1 (default) = kernels are launched with programmatic stream serialization, 0 = plain launches
 
 #define VG_CHECK_ARG(cond, ...)                  \
@@ -32,6 +48,16 @@ extern int g_pdl;   // VG_PDL: 1 (default) = kernels are launched with programma
       vg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
       return VG_ECUDA;                                                                   \
     }                                                                                    \
+  } while (0)
+
+// kernels whose reductions have no ordered variant refuse to run in deterministic mode (loudly, like every other
+// unsupported configuration) instead of silently breaking the bit-reproducibility the caller asked for
+#define VG_DET_UNSUPPORTED(what)                                                          \
+  do {                                                                                    \
+    if (vg::g_det.on) {                                                                   \
+      vg::set_error("deterministic mode: no ordered reduction for %s", what);             \
+      return VG_EUNSUPPORTED;                                                             \
+    }                                                                                     \
   } while (0)
 
 // call after every kernel launch
@@ -87,6 +113,31 @@ struct Launch {
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in VG_LAUNCHED()
   }
 };
+
+// ---- deterministic split-K: the splits of one output tile add their partial sums in split order --------------------
+// `turn`-th contributor waits until the tile's counter equals `turn`, adds its values, then publishes turn + 1 (the
+// last one resets the counter to 0 for the next launch).  Lower splits have lower block / work-item indices, so they
+// are always scheduled first: no deadlock (the serial split-K of CUTLASS relies on the same ordering).
+__device__ __forceinline__ void det_wait_turn(const int* lock, int turn) {
+  int v;
+  long long t0 = 0;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(lock) : "memory");
+    if (v != turn) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 8000000000LL) {
+        printf("vaegan_b200: deterministic split-K turn wait timed out (block %d,%d,%d turn %d saw %d)\n", blockIdx.x, blockIdx.y,
+               blockIdx.z, turn, v);
+        __trap();
+      }
+      __nanosleep(64);
+    }
+  } while (v != turn);
+}
+__device__ __forceinline__ void det_publish_turn(int* lock, int next) {
+  __threadfence();
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(lock), "r"(next) : "memory");
+}
 
 // ---- device helpers -----------------------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }
