@@ -159,6 +159,20 @@ int vg_bn_eval_affine(const float* gamma, const float* beta, const float* runnin
 int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* dbias,
                   float* workspace, vg_stream_t stream);
 
+/* Tile table ("shapes outside the tuned set ... autotuned tile table").  For one layer shape
+ * (every field of `d` that describes geometry, including the batch n) and direction (dgrad = 0: vg_conv_forward*,
+ * 1: vg_conv_dgrad*) pin the tensor-core kernel's N tile `bn` (64 / 128 / 256, must divide the output channels; 0 = keep
+ * the heuristic) and its form (0 heuristic, 1 one-shot CTAs, 2 persistent CTAs, 3 persistent CTA pairs / cta_group::2; a
+ * form the shape cannot take falls back to the next one).  bn = 0 and form = 0 removes the entry.  Shapes without an
+ * entry use the built-in heuristics.  vg_conv_tune_record(1) starts collecting the distinct
+ * (shape, direction) keys the tensor-core path is called with, vg_conv_tune_seen copies up to max_keys of them as
+ * int[10] = {dgrad, n, h_in, w_in, c_in, c_out, k, stride, pad, transposed} and returns the total in *count -
+ * vae_gan_b200/tune.py uses the pair to autotune whatever model is run.  Host-side state only; thread-safe. */
+int vg_conv_tune_set(const VgConvDesc* d, int dgrad, int bn, int form);
+int vg_conv_tune_clear(void);
+int vg_conv_tune_record(int on);
+int vg_conv_tune_seen(int* keys, int max_keys, int* count);
+
 /* ---- BatchNorm2d (+LeakyReLU +Dropout) fused family: README.md:143,152,159,166,169,172,
  *      144/180/190 (nn.Dropout), 376,382,388,394,442 --------------------------------------- */
 typedef struct {

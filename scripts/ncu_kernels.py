@@ -31,7 +31,7 @@ for name, cin, cout, h, k, st, pad, tr in SHAPES:
     wsb = torch.empty(w.numel(), dtype=torch.float32, device=dev)
     keep = (x, w, pk, pn, y, dy, dw, wsb, d)
     jobs.append((name + " fwd", lambda d=d, x=x, pk=pk, pn=pn, y=y: _lib.call("vg_conv_forward", C.byref(d), x.data_ptr(), pk.data_ptr(), pn.data_ptr(), None, None, y.data_ptr(), None, s), keep))
-    jobs.append((name + " wgrad", lambda d=d, x=x, dy=dy, dw=dw, wsb=wsb: _lib.call("vg_conv_wgrad", C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), wsb.data_ptr(), s), keep))
+    jobs.append((name + " wgrad", lambda d=d, x=x, dy=dy, dw=dw, wsb=wsb: _lib.call("vg_conv_wgrad", C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), None, wsb.data_ptr(), s), keep))
 for _, fn, _k in jobs:
     fn(); fn()
 torch.cuda.synchronize()

@@ -73,6 +73,10 @@ _PROTOS = {
     "vg_set_deterministic": (c_int, [c_int, c_vp, C.c_size_t, c_vp, c_int]),
     "vg_get_deterministic": (c_int, []),
     "vg_conv_pack_weights": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vg_conv_tune_set": (c_int, [C.POINTER(VgConvDesc), c_int, c_int, c_int]),
+    "vg_conv_tune_clear": (c_int, []),
+    "vg_conv_tune_record": (c_int, [c_int]),
+    "vg_conv_tune_seen": (c_int, [c_vp, c_int, C.POINTER(c_int)]),
     "vg_conv_pack_weights_batched": (c_int, [c_vp, c_int, c_int, c_vp]),
     "vg_conv_forward_scaled": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "vg_conv_forward_fused": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, C.POINTER(VgConvEpilogue), c_vp, c_vp, c_vp]),
@@ -171,6 +175,9 @@ def ensure_device(device: torch.device):
         if rc != 0:
             raise VgError(f"vg_init({idx}) failed ({rc}): {lib.vg_last_error().decode()}")
         _inited_devices.add(idx)
+        if len(_inited_devices) == 1:
+            from . import tune       # the tile table measured on B200 for the BASELINE shapes (VG_TILE_TABLE=0: heuristics only)
+            tune.apply_default()
         if os.environ.get("VG_DETERMINISTIC", "0") == "1" and _det_buffers is None:
             set_deterministic(True, torch.device("cuda", idx))
 

@@ -17,6 +17,10 @@ int tc_conv_run(const VgConvDesc*, bool dgrad, const void* in, const void* wpack
                 const float* sigma, int sigma_group_n, void* out, int out_dtype, double* stats, bool* stats_fused, cudaStream_t,
                 const VgConvEpilogue* ep = nullptr);
 int tc_wgrad_run(const VgConvDesc*, const void* x, const void* dy, float* dw, float* workspace, cudaStream_t);
+int tc_tune_set(const VgConvDesc*, int dgrad, int bn, int form);
+void tc_tune_clear();
+void tc_tune_record(int on);
+int tc_tune_seen(int* keys, int max_keys);
 }  // namespace vg
 
 using namespace vg;
@@ -134,4 +138,20 @@ extern "C" int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy,
   if (rc) return rc;
   if (dbias != nullptr) rc = simt_colsum(dy, (long long)d->n * d->h_out * d->w_out, d->c_out, d->act_dtype, dbias, s);
   return rc;
+}
+
+// ---- tile table ------------------------------------------------------------------------------
+extern "C" int vg_conv_tune_set(const VgConvDesc* d, int dgrad, int bn, int form) { return vg::tc_tune_set(d, dgrad, bn, form); }
+extern "C" int vg_conv_tune_clear(void) {
+  vg::tc_tune_clear();
+  return VG_OK;
+}
+extern "C" int vg_conv_tune_record(int on) {
+  vg::tc_tune_record(on);
+  return VG_OK;
+}
+extern "C" int vg_conv_tune_seen(int* keys, int max_keys, int* count) {
+  VG_CHECK_ARG(count != nullptr && max_keys >= 0 && (keys != nullptr || max_keys == 0), "bad args");
+  *count = vg::tc_tune_seen(keys, max_keys);
+  return VG_OK;
 }

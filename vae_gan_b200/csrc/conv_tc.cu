@@ -23,7 +23,10 @@
 //   64-pixel boxes (split-K across CTAs, fp32 atomics into the torch-layout gradient).  Both
 //   operands are MN-major (channels contiguous, pixels along K) straight from the same TMA boxes.
 #include <algorithm>
+#include <array>
+#include <map>
 #include <mutex>
+#include <vector>
 #include "vg_common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -67,6 +70,8 @@ struct alignas(64) TcConvParams {
   const float* post_shift;
   float post_slope;
   int* det_locks;        // deterministic mode, split-K: one turn counter per output tile (the splits add in split order)
+  long long det_split_stride;  // deterministic mode, split-K: != 0 -> split z STORES its partial tile at out + z * stride (scratch);
+                               //   ordered_reduce_f32 adds the splits in order afterwards (no serialisation, no atomics)
 };
 
 struct alignas(64) TcWgradParams {
@@ -79,6 +84,7 @@ struct alignas(64) TcWgradParams {
   int packed;    // 1: dw is the packed scratch [tap][c_s][c_u] (vector reductions); 0: torch layout [c_u][c_s][tap]
   float* dw;
   int* det_locks;  // deterministic mode: one turn counter per (slab pair, c_u tile); the pixel splits add in split order
+  long long det_split_stride;  // deterministic mode: != 0 -> split z STORES its partial sums at dw + z * stride (scratch)
 };
 
 constexpr int kTcThreads = 256;
@@ -233,10 +239,17 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint
       // split-K partial sums: 16-byte vector reductions (a quarter of the RED instructions of scalar atomics - the
       // Linear layers' one-shot CTAs spent most of their time issuing them; n_out % 64 == 0 keeps them aligned)
       float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol;
+      if (p.det_split_stride != 0) {
+        // deterministic mode: this split's partial tile goes to its own scratch slab (one-shot kernel: split = blockIdx.z)
+        o += (long long)blockIdx.z * p.det_split_stride;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
-                     : "memory");
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                       : "memory");
+      }
     } else if (p.out_f32) {
       float* o = reinterpret_cast<float*>(p.out) + opix * p.n_out + ncol;
 #pragma unroll
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 #pragma unroll 1
     for (int m = 0; m < nvalid; ++m) {
       const int gx = x0s[m] + xl, gy = y0s[m] + yl, gn = n0s[m] + nl;
-      const bool valid = gx < p.gw && gy < p.gh && gn < p.gn && !(p.ksplit > 1 && num_k == 0);
+      const bool valid = gx < p.gw && gy < p.gh && gn < p.gn && !(p.ksplit > 1 && num_k == 0 && p.det_split_stride == 0);
       const long long opix = ((long long)gn * p.OH + (long long)gy * p.os + ph.oy_off) * p.OW + (long long)gx * p.os + ph.ox_off;
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
@@ -1107,17 +1120,25 @@ __global__ void __launch_bounds__(kTcThreads) tc_wgrad_kernel(const __grid_const
         const int cu0 = blockIdx.y * BN + c0;
         if (p.packed) {
           // 32 consecutive c_u of one (tap, c_s) row: eight 16-byte vector reductions
-          float* dst = p.dw + ((long long)tap * p.cs + cs) * p.cu + cu0;
+          float* dst = p.dw + (long long)blockIdx.z * p.det_split_stride + ((long long)tap * p.cs + cs) * p.cu + cu0;
+          if (p.det_split_stride != 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
-                         "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
-                         : "memory");
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                                                __uint_as_float(r[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+                           "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                           : "memory");
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float* dst = p.dw + ((long long)(cu0 + j) * p.cs + cs) * p.ntaps + tap;
-            atomicAdd(dst, __uint_as_float(r[j]));
+            float* dst = p.dw + (long long)blockIdx.z * p.det_split_stride + ((long long)(cu0 + j) * p.cs + cs) * p.ntaps + tap;
+            if (p.det_split_stride != 0) *dst = __uint_as_float(r[j]);
+            else atomicAdd(dst, __uint_as_float(r[j]));
           }
         }
       }
@@ -1394,6 +1415,52 @@ static void build_scatter_phase(TcPhase* ph, int k, int stride, int pad, int n_o
   }
 }
 
+// ---- tile table: per (layer shape, batch, direction) the N tile and the kernel form that an
+// autotune run measured fastest (vae_gan_b200/tune.py fills it through vg_conv_tune_set; vae_gan_b200/tile_table.json is the
+// table measured on B200 for the BASELINE configurations).  Shapes without an entry use the heuristics below.
+enum TuneForm { kFormAuto = 0, kFormOneShot = 1, kFormPersist = 2, kFormPair = 3 };
+using TuneKey = std::array<int, 10>;   // dgrad, n, h_in, w_in, c_in, c_out, k, stride, pad, transposed
+struct TuneVal { int bn, form; };
+static std::map<TuneKey, TuneVal> g_tune;
+static std::vector<TuneKey> g_tune_seen;
+static bool g_tune_record = false;
+static std::mutex g_tune_mu;
+static TuneKey tune_key(const VgConvDesc* d, bool dgrad) {
+  return TuneKey{dgrad ? 1 : 0, d->n, d->h_in, d->w_in, d->c_in, d->c_out, d->kh, d->stride, d->pad, d->transposed ? 1 : 0};
+}
+static TuneVal tune_lookup(const VgConvDesc* d, bool dgrad) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  const TuneKey k = tune_key(d, dgrad);
+  if (g_tune_record && std::find(g_tune_seen.begin(), g_tune_seen.end(), k) == g_tune_seen.end()) g_tune_seen.push_back(k);
+  auto it = g_tune.find(k);
+  return it == g_tune.end() ? TuneVal{0, kFormAuto} : it->second;
+}
+int tc_tune_set(const VgConvDesc* d, int dgrad, int bn, int form) {
+  VG_CHECK_ARG(d != nullptr, "null descriptor");
+  VG_CHECK_ARG(bn == 0 || bn == 64 || bn == 128 || bn == 256, "N tile must be 0 (heuristic), 64, 128 or 256 (got %d)", bn);
+  VG_CHECK_ARG(form >= kFormAuto && form <= kFormPair, "kernel form must be 0..3 (got %d)", form);
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  if (bn == 0 && form == kFormAuto) g_tune.erase(tune_key(d, dgrad != 0));
+  else g_tune[tune_key(d, dgrad != 0)] = TuneVal{bn, form};
+  return VG_OK;
+}
+void tc_tune_clear() {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  g_tune.clear();
+}
+void tc_tune_record(int on) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  g_tune_record = on != 0;
+  if (on) g_tune_seen.clear();
+}
+int tc_tune_seen(int* keys, int max_keys) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  const int n = (int)std::min<size_t>(g_tune_seen.size(), (size_t)std::max(0, max_keys));
+  for (int i = 0; i < n && keys != nullptr; ++i)
+    for (int j = 0; j < 10; ++j) keys[i * 10 + j] = g_tune_seen[i][j];
+  return (int)g_tune_seen.size();
+}
+
 static int pick_bn(int n_out) {
   static int forced = -1;
   if (forced < 0) {
@@ -1457,7 +1524,8 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
     if ((rc = make_act_map(&p.in_maps[0], in, d->n, in_h, in_w, in_c, 1, 0, 0, p.TW, p.TH, p.TN))) return rc;
     p.in_maps[1] = p.in_maps[2] = p.in_maps[3] = p.in_maps[0];
   }
-  const int BN = (n_out == 1) ? 64 : pick_bn(n_out);
+  const TuneVal tuned = tune_lookup(d, dgrad);
+  const int BN = (n_out == 1) ? 64 : ((tuned.bn != 0 && n_out % tuned.bn == 0) ? tuned.bn : pick_bn(n_out));
   p.n_store = (n_out == 1) ? 1 : BN;
   if ((rc = make_weight_map(&p.w_map, wpack, (long long)k * k * n_out, in_c, BN))) return rc;
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.tiles_n), (unsigned)std::max(1, n_out / BN), (unsigned)nphase);
@@ -1479,8 +1547,18 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
         p.k_per_split = (int)cdiv(total_kb, ks);
         p.ksplit = (int)cdiv(total_kb, p.k_per_split);
         grid.z = (unsigned)p.ksplit;
-        VG_CUDA(cudaMemsetAsync(out, 0, (size_t)d->n * out_h * out_w * n_out * sizeof(float), s));
-        if (g_det.on && !(p.det_locks = det_locks(ctas))) return VG_EINVAL;
+        const size_t out_elems = (size_t)d->n * out_h * out_w * n_out;
+        VG_CUDA(cudaMemsetAsync(out, 0, out_elems * sizeof(float), s));
+        if (g_det.on) {
+          // deterministic mode: every split stores its partial tile into its own scratch slab and ordered_reduce_f32 adds
+          // the slabs in split order (below); if the caller's scratch is too small the splits take turns instead
+          if ((size_t)p.ksplit * out_elems * sizeof(float) <= g_det.scratch_bytes) {
+            p.out = g_det.scratch;
+            p.det_split_stride = (long long)out_elems;
+          } else if (!(p.det_locks = det_locks(ctas))) {
+            return VG_EINVAL;
+          }
+        }
       }
     }
   }
@@ -1498,12 +1576,15 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   const bool big = mt_on && p.ksplit == 1 && ctas1 >= 6LL * num_sms();
   // 256-wide tiles go persistent as soon as there is more than one work item per SM (288 tiles of the 24x24 layers at
   // batch 64 ran as one-shot CTAs without epilogue overlap: 38-85 us for 31 us of tensor work)
-  const bool use_persist = persist && !(g_det.on && p.ksplit > 1) &&       // deterministic split-K: the one-shot kernel takes turns
+  const bool heur_persist = persist && !(g_det.on && p.ksplit > 1) &&       // deterministic split-K: the one-shot kernel takes turns
                            ((BN == 256 && ctas1 > (long long)num_sms()) ||
                                        // 128-wide: the CTA-pair kernel (1000+ TFLOP/s) from two work items per pair on; below 6 x SMs tiles
                                        // these layers ran as one-shot CTAs (G 128->128 @48 at 32 images: 496 TFLOP/s)
                                        (BN == 128 && ctas1 >= 2LL * num_sms()) ||
                                        (BN == 64 && ctas1 >= 2LL * num_sms() && ctas1 >= (long long)mt_min * num_sms()));
+  // a tile-table entry overrides the form (split-K launches keep the heuristic: only the one-shot kernel was tuned for them)
+  const int form = p.ksplit > 1 ? kFormAuto : tuned.form;
+  const bool use_persist = form == kFormAuto ? heur_persist : (form != kFormOneShot);
   // BatchNorm statistics of the output can be accumulated by the epilogue warps of the 8-warp persistent
   // kernels (parity-tested), but it is OPT-IN (VG_TC_FUSE_STATS=1): measured on B200 the per-chunk smem
   // transposes cost the L2/smem-bound main loop more (+35 % per launch with 8 epilogue warps, +60 % with
@@ -1520,9 +1601,9 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   // CTA pairs (cta_group::2) halve the per-SM shared-memory operand reads that bound the narrow tiles
   static int pair_on = -1;
   if (pair_on < 0) { const char* e = getenv("VG_TC_PAIR"); pair_on = e ? atoi(e) : 6; }   // bit0: BN=64, bit1: BN=128, bit2: BN=256
-  if (use_persist && pair_on && p.n_store != 1) {
+  if (use_persist && form != kFormPersist && (pair_on || form == kFormPair) && p.n_store != 1) {
     const int mt = BN == 64 ? 4 : (BN == 128 ? 2 : 1);
-    if (grid.x % (2 * mt) == 0 && (pair_on & (BN == 64 ? 1 : (BN == 128 ? 2 : 4)))) {
+    if (grid.x % (2 * mt) == 0 && (form == kFormPair || (pair_on & (BN == 64 ? 1 : (BN == 128 ? 2 : 4))))) {
       if ((rc = make_weight_map(&p.w_map, wpack, (long long)k * k * n_out, in_c, BN / 2))) return rc;
       switch (BN) {
         case 64: return launch_conv_pair<64, 4, 3, 4>(p, grid, s);
@@ -1550,11 +1631,14 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
     }
   }
   switch (BN) {
-    case 64: return big ? launch_conv<64, 2, 4>(p, grid, s) : launch_conv<64, 1, 4>(p, grid, s);
-    case 128: return big ? launch_conv<128, 2, 4>(p, grid, s) : launch_conv<128, 1, 3>(p, grid, s);
-    case 256: return launch_conv<256, 1, 4>(p, grid, s);
+    case 64: rc = big ? launch_conv<64, 2, 4>(p, grid, s) : launch_conv<64, 1, 4>(p, grid, s); break;
+    case 128: rc = big ? launch_conv<128, 2, 4>(p, grid, s) : launch_conv<128, 1, 3>(p, grid, s); break;
+    case 256: rc = launch_conv<256, 1, 4>(p, grid, s); break;
     default: set_error("unsupported BN %d", BN); return VG_EUNSUPPORTED;
   }
+  if (rc == VG_OK && p.det_split_stride != 0)
+    rc = ordered_reduce_f32((const float*)p.out, p.ksplit, p.det_split_stride, (float*)out, s);
+  return rc;
 }
 
 int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* workspace, cudaStream_t s) {
@@ -1615,12 +1699,22 @@ int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, 
   p.boxes_per_split = (int)cdiv(p.n_boxes, splits);
   splits = cdiv(p.n_boxes, p.boxes_per_split);
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
-  if (g_det.on && !(p.det_locks = det_locks(tiles))) return VG_EINVAL;
+  float* const wgrad_dst = p.dw;
+  if (g_det.on && splits > 1) {
+    // deterministic mode: per-split scratch slabs + ordered reduce (see the forward's split-K), turn-taking as the fallback
+    if ((size_t)splits * welems * sizeof(float) <= g_det.scratch_bytes) {
+      p.dw = (float*)g_det.scratch;
+      p.det_split_stride = (long long)welems;
+    } else if (!(p.det_locks = det_locks(tiles))) {
+      return VG_EINVAL;
+    }
+  }
   switch (NB) {
     case 1: rc = launch_wgrad<1, 6>(p, grid, s); break;
     case 2: rc = launch_wgrad<2, 5>(p, grid, s); break;
     default: rc = launch_wgrad<4, 4>(p, grid, s); break;
   }
+  if (rc == VG_OK && p.det_split_stride != 0) rc = ordered_reduce_f32(p.dw, (int)splits, p.det_split_stride, wgrad_dst, s);
   if (rc || !p.packed) return rc;
   dim3 ug((unsigned)cdiv((long long)cs * p.ntaps, 32), (unsigned)cdiv(cu, 32));
   vg::Launch(ug, 256, 0, s)(wgrad_unpack_kernel, workspace, cu, cs, p.ntaps, dw);
