@@ -34,3 +34,23 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _fresh_philox_state(request):
+    """The Philox site / step counters and the deterministic-mode switch are process-global (like torch's default
+    generator): every GPU test starts from step 0 / site 0 / atomic mode, so no test depends on what ran before it."""
+    if "gpu" not in request.keywords:
+        yield
+        return
+    import torch
+    if not torch.cuda.is_available():
+        yield
+        return
+    import vae_gan_b200 as v
+    dev = torch.device("cuda", torch.cuda.current_device())
+    v.rng.reset_sites()
+    v.rng.step_tensor(dev).zero_()
+    yield
+    if v.is_deterministic():
+        v.set_deterministic(False)

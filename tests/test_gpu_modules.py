@@ -257,7 +257,7 @@ def test_discriminator_full_size_vs_oracle(dtype):
 # ------------------------------------------------------------------------------------------------
 # the training iteration
 # ------------------------------------------------------------------------------------------------
-def _run_trainer_vs_oracle(dtype, loss_mode, opt, B, S, fs, steps, tol_loss, max_bad_frac):
+def _run_trainer_vs_oracle(dtype, loss_mode, opt, B, S, fs, steps, tol_loss, max_bad_frac, depth=2, length=1, disc=None):
     """`steps` iterations of VaeGanTrainer vs oracle.train_step (fp64) with identical weights, inputs,
     Philox masks and noise.  Losses are compared at tol_loss.  Parameters: both optimizers normalise
     the gradient (the first Adam step is exactly lr*sign(g)), so elements whose gradient is rounding
@@ -265,16 +265,20 @@ def _run_trainer_vs_oracle(dtype, loss_mode, opt, B, S, fs, steps, tol_loss, max
     of elements whose update deviates by more than lr/2 instead of a max-norm."""
     v = V()
     lr = 3e-4
-    spec_g = O.GeneratorSpec(depth=2, length=1, feature_size=fs)
-    spec_d = O.DiscriminatorSpec(1, fs, (1, 1, 1), (1, 2, 2), (2 * fs, 4 * fs, 8 * fs), input_size=S)
+    # disc = (num_blocks, num_strides_res, num_features_res) of the discriminator; default = experiment()'s (README.md:903)
+    nb, ns, nf = disc if disc is not None else ((1, 1, 1), (1, 2, 2), (2 * fs, 4 * fs, 8 * fs))
+    spec_g = O.GeneratorSpec(depth=depth, length=length, feature_size=fs)
+    spec_d = O.DiscriminatorSpec(1, fs, tuple(nb), tuple(ns), tuple(nf), input_size=S)
     Pg = O.make_generator_params(spec_g, seed=5)
     Pd = O.make_discriminator_params(spec_d, seed=6)
     gen = torch.Generator().manual_seed(31)
     xs = [torch.rand(B, 1, S, S, generator=gen) for _ in range(steps)]
-    epss = [torch.randn(B, spec_g.feature_depth, S // 4, S // 4, generator=gen) for _ in range(steps)]
+    epss = [torch.randn(B, spec_g.feature_depth, S // 2 ** depth, S // 2 ** depth, generator=gen) for _ in range(steps)]
     seed = 4242
     with v.compute_dtype(dtype):
-        G, D = v.build_vae_gan(feature_size=fs, image_size=S)
+        G, D = v.build_vae_gan(depth=depth, length=length, feature_size=fs, image_size=S,
+                               disc_params=dict(num_stride_conv1=1, num_features_conv1=fs, num_blocks=list(nb), num_strides_res=list(ns),
+                                                num_features_res=list(nf)))
         load_params_into(G, Pg)
         load_params_into(D, Pd)
         G, D = G.to(dev()).train(), D.to(dev()).train()
