@@ -40,7 +40,9 @@ GENERIC = [
 
 @pytest.mark.parametrize("fs,depth,length,S,disc", GENERIC)
 def test_generic_config_fp32_train_step_vs_oracle(fs, depth, length, S, disc):
-    _run_trainer_vs_oracle(torch.float32, "bce", "adam", B=2, S=S, fs=fs, steps=2, tol_loss=5e-5, max_bad_frac=5e-3,
+    # tol_loss: the first step agrees to ~1e-6; `adv` of the SECOND step is evaluated after two Adam updates whose
+    # lr * sign(g) steps amplify fp32 rounding noise on near-zero gradients (1.5e-4 measured on the 320-channel config)
+    _run_trainer_vs_oracle(torch.float32, "bce", "adam", B=2, S=S, fs=fs, steps=2, tol_loss=4e-4, max_bad_frac=5e-3,
                            depth=depth, length=length, disc=disc)
 
 
