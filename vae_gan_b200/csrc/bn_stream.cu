@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_stream_kernel(const __grid_con
       __syncwarp();
       if (++stage == ST) { stage = 0; phase ^= 1u; }
     }
+    vg::pdl_tail_trigger();
     return;
   }
 
@@ -381,6 +382,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_stream_kernel(const __grid_con
     if (lane == 0) ptx::mbar_arrive(&empty[stage]);
     if (++stage == ST) { stage = 0; phase ^= 1u; }
   }
+  vg::pdl_tail_trigger();
 
   if (ModeTraits<MODE>::kReduce) {
     // per-channel block reduction through the (now idle) ring, then one fp64 atomic per (block, channel, quantity)

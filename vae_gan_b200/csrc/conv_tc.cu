@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
       }
       if (ptx::elect_one()) ptx::mma_commit(tmem_full);
       __syncwarp();
+      vg::pdl_tail_trigger();
     }
   }
 
@@ -656,6 +657,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
       __syncwarp();
       ++it;
     }
+    vg::pdl_tail_trigger();
   } else if (warp >= 4) {
     const int ew = warp - 4;
     const int q = ew & 3;                 // TMEM lane quarter this warp may access
@@ -908,6 +910,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
         ++it;
       }
     }
+    vg::pdl_tail_trigger();
   } else if (warp >= 4) {
     const int ew = warp - 4;
     const int q = ew & 3;
@@ -1094,6 +1097,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_wgrad_kernel(const __grid_const
       }
       if (ptx::elect_one()) ptx::mma_commit(tmem_full);
       __syncwarp();
+      vg::pdl_tail_trigger();
     }
   }
 

@@ -94,6 +94,15 @@ __device__ __forceinline__ void pdl_entry() {
 #endif
 }
 
+// experiment switch (-DVG_PDL_TAIL_TRIGGER=1): the long kernels signal `launch_dependents` when a CTA has issued its last
+// loads / MMAs, so the next grid's CTAs can take over SMs as this grid's CTAs retire instead of after the whole grid.
+// Measured on B200 (profiles/r2_pdl_ab.txt): 0.3 - 1.3 % SLOWER than the implicit trigger at CTA exit; off.
+__device__ __forceinline__ void pdl_tail_trigger() {
+#if defined(VG_PDL_TAIL_TRIGGER) && VG_PDL_TAIL_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 struct Launch {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
