@@ -15,7 +15,11 @@
  *   - the caller owns every buffer (incl. workspaces); no compute entry point allocates device
  *     memory or keeps a pointer after it returns (the only allocator calls are the setup-time
  *     vg_peer_alloc / vg_peer_free helpers of the NVLink exchange buffers, which must be plain
- *     cudaMalloc memory so that their IPC handles can be opened by the other ranks);
+ *     cudaMalloc memory so that their IPC handles can be opened by the other ranks; the only pointers kept
+ *     are the caller-owned scratch / turn counters registered with vg_set_deterministic, until it is switched off);
+ *   - kernels are launched with programmatic stream serialization and wait (griddepcontrol.wait) before their first
+ *     global-memory access: stream-order semantics are unchanged, the launch latency overlaps the previous kernel's
+ *     tail (VG_PDL=0 in the environment restores plain launches);
  *   - all work is enqueued on `stream` (a cudaStream_t); no host synchronisation, CUDA-graph
  *     capturable;
  *   - return value: VG_OK or a negative VgStatus; vg_last_error() gives a thread-local
