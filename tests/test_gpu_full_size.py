@@ -4,8 +4,8 @@ the fp64 CPU oracle can run in a test, so the kernels are checked there through 
 * adjointness: <conv(x), dy> = <x, dgrad(dy)> = <W, wgrad(x, dy)> ties the three tensor-core GEMMs of a layer together with
   no reference at all (every indexing / tiling / padding / stride-phase bug breaks it), on the step's hottest layer shapes
   at batch 256;
-* BatchNorm identities at full size: training-mode output statistics are (beta, gamma^2), the input gradient sums to zero
-  per channel and is orthogonal to x_hat;
+* BatchNorm + LeakyReLU forward / backward on full-size tensors against plain torch fp32 math on the same GPU, elementwise
+  at bf16 rounding, with the parameter gradients and torch's running-statistics rule;
 * batch-mate independence: in eval mode a sample's reconstruction / logit does not depend on the other 255 samples
   (batch 256 vs slices of 64) - the pixel tiles of the convolutions span images (TN > 1 boxes), so this is a real check;
 * one full-size training iteration: finite losses, the BCE discriminator loss of an untrained network of order 2 ln 2, every
@@ -65,7 +65,14 @@ def test_conv_adjointness_at_batch_256(cin, cout, h, k, stride, pad, tr):
 
 
 @pytest.mark.parametrize("c,h", [(128, 96), (512, 24), (1, 96)])
-def test_batchnorm_identities_at_batch_256(c, h):
+def test_batchnorm_against_torch_fp32_at_batch_256(c, h):
+    """Training-mode BatchNorm + LeakyReLU forward / backward on a full-size tensor (2.4 M values per channel) against plain
+    torch fp32 math on the same GPU, elementwise at bf16 rounding; statistics identities of the output; running statistics.
+    (The textbook identities sum(dx) = 0 and sum(dx * x_hat) = 0 cannot be tested on the bf16 result itself: dx = a * g + c0 +
+    c1 * (x - mean) with |c0|, |c1 (x - mean)| ~ 1e-3 far below the bf16 resolution of a * g, and a * g takes few distinct
+    mantissas for a bf16 g, so the rounding of dx is not unbiased with respect to those terms - measured sum(dx) up to 10 % of
+    a * sum(g); the fp32 reference below has the same property once rounded.)"""
+    import torch.nn.functional as F
     vf = VF()
     g = torch.Generator(device=dev()).manual_seed(c + h)
     x = vf.as_act(torch.randn(B, c, h, h, generator=g, device=dev()) * 1.7 + 0.3, torch.bfloat16).requires_grad_(True)
@@ -73,22 +80,26 @@ def test_batchnorm_identities_at_batch_256(c, h):
     with torch.no_grad():
         bn.weight.copy_(1 + 0.3 * torch.randn(c, generator=g, device=dev()))
         bn.bias.copy_(0.2 * torch.randn(c, generator=g, device=dev()))
-    y = vf.bn_act(x, bn, slope=1.0, training=True)                     # BatchNorm alone (slope 1 = no activation)
-    yf = y.detach().float()
-    mean, var = yf.mean((0, 2, 3)), yf.var((0, 2, 3), unbiased=False)
-    assert float((mean - bn.bias).abs().max()) <= 4e-3                  # bf16 output rounding, averaged over 2.4 M values
-    assert float((var / bn.weight.detach() ** 2 - 1).abs().max()) <= 1e-2
+    y = vf.bn_act(x, bn, slope=0.2, training=True)
     dy = vf.as_act(torch.randn(y.shape, generator=g, device=dev()), torch.bfloat16)
     y.backward(dy)
-    dx = x.grad.float()
-    n = float(B * h * h)
+    # reference: torch fp32 on the same (bf16-rounded) inputs
+    xr = x.detach().float().contiguous().requires_grad_(True)
+    gam, bet = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
+    yr = F.leaky_relu(F.batch_norm(xr, None, None, gam, bet, True, 0.1, 1e-5), 0.2)
+    yr.backward(dy.float())
+    ulp = 2.0 ** -8                                          # bf16 round-to-nearest: relative error <= 2^-9; 2x margin
+    yerr = (y.detach().float() - yr.detach()).abs() - ulp * yr.detach().abs()
+    assert float(yerr.max()) <= 1e-5, float(yerr.max())
+    # dx: elements whose pre-activation is within fp32 rounding of the LeakyReLU kink (|gamma x_hat + beta| < ~1e-7; a few
+    # tens of 3e8) may take the other slope in one of the two implementations
+    dxerr = (x.grad.float() - xr.grad).abs() - ulp * xr.grad.abs()
+    n_bad = int((dxerr > 1e-5).sum())
+    assert n_bad <= max(2, int(1e-6 * dxerr.numel())), (n_bad, float(dxerr.max()))
+    # parameter gradients: sums of 1.5e5 .. 2.4e6 terms; a kink flip (above) moves one by up to 0.8 * |dy * x_hat| ~ 1
+    assert float((bn.weight.grad - gam.grad).abs().max()) <= 2e-4 * float(gam.grad.abs().max()) + 2.0
+    assert float((bn.bias.grad - bet.grad).abs().max()) <= 2e-4 * float(bet.grad.abs().max()) + 2.0
     xf = x.detach().float()
-    xhat = (xf - xf.mean((0, 2, 3), keepdim=True)) / xf.var((0, 2, 3), unbiased=False, keepdim=True).add(1e-5).sqrt()
-    # sum_n dx = 0 and sum_n dx * x_hat = 0 per channel (the two projections the backward removes); sums of n terms of size
-    # |gamma * rstd| ~ 0.6, each rounded to bf16
-    assert float(dx.sum((0, 2, 3)).abs().max()) <= 2e-2 * math.sqrt(n)
-    assert float((dx * xhat).sum((0, 2, 3)).abs().max()) <= 2e-2 * math.sqrt(n)
-    # torch's own running-statistics rule: momentum 0.1, unbiased variance
     assert float((bn.running_mean - 0.1 * xf.mean((0, 2, 3))).abs().max()) <= 1e-4
     assert float((bn.running_var - (0.9 + 0.1 * xf.var((0, 2, 3), unbiased=True))).abs().max()) <= 1e-3
 
@@ -112,9 +123,10 @@ def test_eval_outputs_do_not_depend_on_batch_mates_at_batch_256():
             assert gerr <= 2e-2 * max(1.0, float(full_gen.abs().max())), f"reconstruction of samples {lo}.. depends on the batch: {gerr}"
             if gerr != 0.0:
                 print(f"note: batch 64 vs 256 reconstructions differ by {gerr} (not bit-identical)")
-            # the Linear head runs split-K (atomics, batch-dependent split count): equal to fp32 rounding
+            # the Linear head runs split-K with a batch-dependent split count: its fp32 sums differ in the last bits, and
+            # re-rounding them to bf16 for the next Linear layer flips single ulps (2^-8) - measured 4.5e-3 of the largest logit
             err = float((part_logit - full_logit[lo:lo + 64]).abs().max())
-            assert err <= 1e-4 * max(1.0, float(full_logit.abs().max())), err
+            assert err <= 2e-2 * max(1.0, float(full_logit.abs().max())), err
 
 
 def test_full_size_training_iteration_sanity():
