@@ -351,6 +351,18 @@ int vg_spectral_norm_sigma_batched(const VgSnItem* items, int n_items, int train
 int vg_spectral_norm_backward(const float* dw_hat, const float* w_orig, const float* u,
                               const float* v, const float* sigma, int rows, int cols,
                               float* dw_orig, float* workspace, vg_stream_t stream);
+/* Weight gradient of a spectral-normed convolution in ONE call (README.md:378-387: `utils.spectral_norm(nn.Conv2d(...))`
+ * under autograd): dw_orig += (dW - <dW, w_orig / sigma> u v^T) / sigma with dW = vg_conv_wgrad(x, dy), for tensor-core
+ * layers only (vg_conv_wgrad_sn_supported(d) == 1: bf16 activations, channels % 64 == 0; otherwise VG_EUNSUPPORTED - use
+ * vg_conv_wgrad + vg_spectral_norm_backward).  The gradient stays in the tensor-core kernel's own layout
+ * [tap][c_s][c_u] and the spectral-norm correction is applied while it is transposed into torch's layout, so the
+ * unpack pass, the temporary dW and two of the three memsets of the two-call sequence disappear (7 -> 4 graph nodes per
+ * layer and backward pass).  u, v, sigma: as saved by the forward.  workspace: float[kh*kw*c_in*c_out + 4], contents
+ * undefined afterwards.  dbias (nullable) += column sums of dy. */
+int vg_conv_wgrad_sn_supported(const VgConvDesc* d);
+int vg_conv_wgrad_sn(const VgConvDesc* d, const void* x, const void* dy, const float* w_orig, const float* u, const float* v,
+                     const float* sigma, float* dw_orig, float* dbias, float* workspace, vg_stream_t stream);
+
 
 /* ---- reparameterisation (README.md:575-582) --------------------------------------------- */
 /* lv = clamp(lv_raw, -50, 50); z = mu + exp(0.5 lv) * eps (training) or mu (eval). z in z_dtype */

@@ -710,3 +710,37 @@ def test_folded_generator_matches_oracle_and_module_eval():
     replay()
     torch.cuda.synchronize()
     assert_close(out, dec, 1e-6, "graphed decode == eager decode")
+
+
+# ------------------------------------------------------------------------------------------------
+# weight gradient of a spectral-normed convolution in one call (vg_conv_wgrad_sn)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,h,k,stride,pad", [(128, 256, 24, 3, 2, 1), (128, 256, 24, 1, 2, 0), (64, 64, 16, 3, 1, 1),
+                                                     (256, 256, 12, 3, 1, 1)])
+def test_fused_spectral_norm_wgrad_matches_two_call_sequence(cin, cout, h, k, stride, pad):
+    """vg_conv_wgrad_sn (packed gradient + spectral-norm correction applied during the transpose) against vg_conv_wgrad +
+    vg_spectral_norm_backward on the same inputs, accumulating into a non-zero gradient buffer like the trainer's."""
+    vf = VF()
+    g = torch.Generator().manual_seed(cin + cout + k)
+    x0 = torch.randn(6, cin, h, h, generator=g).to(dev())
+    w0 = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(dev())
+    u0 = F.normalize(torch.randn(cout, generator=g), dim=0).to(dev())
+    v0 = F.normalize(torch.randn(cin * k * k, generator=g), dim=0).to(dev())
+    grads = []
+    for fused in (False, True):
+        vf._SN_FUSED_WGRAD = fused
+        try:
+            x = vf.as_act(x0, torch.bfloat16).requires_grad_(True)
+            w = w0.clone().requires_grad_(True)
+            w.grad = torch.full_like(w, 0.25)             # the call ACCUMULATES (autograd adds its return value to .grad)
+            u, v = u0.clone(), v0.clone()
+            y = vf.conv(x, w, None, geom=vf.ConvGeom(k, stride, pad, False), sn=(u, v), training=True)
+            dy = vf.as_act(torch.randn(y.shape, generator=torch.Generator().manual_seed(9)).to(dev()), torch.bfloat16)
+            y.backward(dy)
+            torch.cuda.synchronize()
+            grads.append((w.grad.clone(), x.grad.float().clone()))
+        finally:
+            vf._SN_FUSED_WGRAD = True
+    (gw_a, gx_a), (gw_b, gx_b) = grads
+    assert torch.equal(gx_a, gx_b)
+    assert_close(gw_b, gw_a, 2e-5, "dW of the fused call vs the two-call sequence")

@@ -73,6 +73,8 @@ _PROTOS = {
     "vg_set_deterministic": (c_int, [c_int, c_vp, C.c_size_t, c_vp, c_int]),
     "vg_get_deterministic": (c_int, []),
     "vg_conv_pack_weights": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vg_conv_wgrad_sn_supported": (c_int, [C.POINTER(VgConvDesc)]),
+    "vg_conv_wgrad_sn": (c_int, [C.POINTER(VgConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "vg_conv_tune_set": (c_int, [C.POINTER(VgConvDesc), c_int, c_int, c_int]),
     "vg_conv_tune_clear": (c_int, []),
     "vg_conv_tune_record": (c_int, [c_int]),

@@ -16,7 +16,12 @@ bool tc_wgrad_supported(const VgConvDesc*);
 int tc_conv_run(const VgConvDesc*, bool dgrad, const void* in, const void* wpack, const float* bias, const float* colscale,
                 const float* sigma, int sigma_group_n, void* out, int out_dtype, double* stats, bool* stats_fused, cudaStream_t,
                 const VgConvEpilogue* ep = nullptr);
-int tc_wgrad_run(const VgConvDesc*, const void* x, const void* dy, float* dw, float* workspace, cudaStream_t);
+int tc_wgrad_run(const VgConvDesc*, const void* x, const void* dy, float* dw, float* workspace, cudaStream_t, bool acc_only = false);
+int sn_backward_run(const float* dw_hat, const float* w_orig, const float* u, const float* v, const float* sigma, int rows, int cols,
+                    float* dw_orig, float* dot_ws, cudaStream_t s);
+int sn_backward_packed_run(const float* acc, const float* w_orig, const float* u, const float* v, const float* sigma, int cu, int cs,
+                           int taps, float* dw_orig, float* dot_ws, cudaStream_t s);
+int simt_colsum(const void* x, long long rows, int c, int dtype, float* out, cudaStream_t s);
 int tc_tune_set(const VgConvDesc*, int dgrad, int bn, int form);
 void tc_tune_clear();
 void tc_tune_record(int on);
@@ -137,6 +142,35 @@ extern "C" int vg_conv_wgrad(const VgConvDesc* d, const void* x, const void* dy,
     rc = simt_conv_wgrad(d, x, dy, dw, s);
   if (rc) return rc;
   if (dbias != nullptr) rc = simt_colsum(dy, (long long)d->n * d->h_out * d->w_out, d->c_out, d->act_dtype, dbias, s);
+  return rc;
+}
+
+// ---- weight gradient of a spectral-normed convolution in one call ----------------------------------------------------------
+extern "C" int vg_conv_wgrad_sn_supported(const VgConvDesc* d) { return (d != nullptr && vg::tc_wgrad_supported(d)) ? 1 : 0; }
+
+extern "C" int vg_conv_wgrad_sn(const VgConvDesc* d, const void* x, const void* dy, const float* w_orig, const float* u,
+                                const float* v, const float* sigma, float* dw_orig, float* dbias, float* workspace,
+                                vg_stream_t stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  if (d->n == 0) return VG_OK;
+  VG_CHECK_ARG(x && dy && w_orig && u && v && sigma && dw_orig && workspace, "null pointer");
+  if (!tc_wgrad_supported(d)) {
+    set_error("vg_conv_wgrad_sn needs a tensor-core layer (bf16, channels %% 64 == 0): use vg_conv_wgrad + vg_spectral_norm_backward");
+    return VG_EUNSUPPORTED;
+  }
+  cudaStream_t s = as_stream(stream);
+  const int taps = d->kh * d->kw;
+  const int cu = d->transposed ? d->c_in : d->c_out, cs = d->transposed ? d->c_out : d->c_in;
+  const size_t welems = (size_t)taps * cu * cs;
+  // ONE memset for the gradient accumulator and the dot-product cell behind it
+  VG_CUDA(cudaMemsetAsync(workspace, 0, (welems + 4) * sizeof(float), s));
+  if ((rc = tc_wgrad_run(d, x, dy, nullptr, workspace, s, /*acc_only=*/true))) return rc;
+  // spectral norm: rows = dim 0 of the torch-layout weight (c_u), cols = the rest (c_s * taps)
+  if (taps > 1) rc = sn_backward_packed_run(workspace, w_orig, u, v, sigma, cu, cs, taps, dw_orig, workspace + welems, s);
+  else rc = sn_backward_run(workspace, w_orig, u, v, sigma, cu, cs, dw_orig, workspace + welems, s);
+  if (rc) return rc;
+  if (dbias) rc = simt_colsum(dy, (long long)d->n * d->h_out * d->w_out, d->c_out, d->act_dtype, dbias, s);
   return rc;
 }
 

@@ -1645,7 +1645,9 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   return rc;
 }
 
-int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* workspace, cudaStream_t s) {
+// acc_only: leave the result in `workspace` - packed [tap][c_s][c_u] for k > 1, torch layout [c_u][c_s] for k = 1 (the
+// caller zeroed it and consumes it itself: vg_conv_wgrad_sn) - instead of adding it into dw
+int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, float* workspace, cudaStream_t s, bool acc_only) {
   TcWgradParams p;
   memset(&p, 0, sizeof(p));
   // dw[cu][cs][tap] += sum_q U[q][cu] * S[q*stride - pad + k][cs]
@@ -1666,10 +1668,10 @@ int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, 
   // reductions are coalesced (32 lanes = 32 consecutive c_s) and the scratch + memset + unpack round trip is skipped
   static int direct11 = -1;
   if (direct11 < 0) { const char* e = getenv("VG_WGRAD_DIRECT_1X1"); direct11 = e ? atoi(e) : 1; }
-  p.packed = workspace != nullptr && (tmp.ntaps > 1 || !direct11);
-  p.dw = p.packed ? workspace : dw;
+  p.packed = workspace != nullptr && (tmp.ntaps > 1 || (!direct11 && !acc_only));
+  p.dw = (p.packed || acc_only) ? workspace : dw;
   const size_t welems = (size_t)k * k * cs * cu;
-  if (p.packed) VG_CUDA(cudaMemsetAsync(workspace, 0, welems * sizeof(float), s));
+  if (p.packed && !acc_only) VG_CUDA(cudaMemsetAsync(workspace, 0, welems * sizeof(float), s));
   int rc;
   if (st == 2) {
     for (int py = 0; py < 2; ++py)
@@ -1719,7 +1721,7 @@ int tc_wgrad_run(const VgConvDesc* d, const void* x, const void* dy, float* dw, 
     default: rc = launch_wgrad<4, 4>(p, grid, s); break;
   }
   if (rc == VG_OK && p.det_split_stride != 0) rc = ordered_reduce_f32(p.dw, (int)splits, p.det_split_stride, wgrad_dst, s);
-  if (rc || !p.packed) return rc;
+  if (rc || !p.packed || acc_only) return rc;
   dim3 ug((unsigned)cdiv((long long)cs * p.ntaps, 32), (unsigned)cdiv(cu, 32));
   vg::Launch(ug, 256, 0, s)(wgrad_unpack_kernel, workspace, cu, cs, p.ntaps, dw);
   VG_LAUNCHED();

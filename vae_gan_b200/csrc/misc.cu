@@ -436,6 +436,60 @@ __global__ void sn_bwd_apply_kernel(const float* __restrict__ dwh, const float* 
   }
 }
 
+// The same two steps reading the weight gradient in the tensor-core kernel's PACKED layout acc[tap][c_s][c_u] (what
+// tc_wgrad_kernel reduces into), so that no unpack pass is needed: dw_orig[c_u][c_s][tap] is torch's layout,
+// rows = c_u (u), cols = c_s * taps + tap (v).
+__global__ void sn_bwd_dot_packed_kernel(const float* __restrict__ acc, const float* __restrict__ w, int cu, int cs, int taps,
+                                         float* __restrict__ out, float* __restrict__ partials) {
+  vg::pdl_entry();
+  const long long n = (long long)taps * cs * cu;
+  float part = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c_u = (int)(i % cu);
+    const long long t = i / cu;
+    const int c_s = (int)(t % cs), tap = (int)(t / cs);
+    part = fmaf(acc[i], w[((long long)c_u * cs + c_s) * taps + tap], part);      // w: a few MB, L2 resident
+  }
+  part = warp_sum(part);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += red[k];
+    if (partials) partials[blockIdx.x] = tot;
+    else atomicAdd(out, tot);
+  }
+}
+// 32 x 32 shared-memory transpose between c_u and r = c_s * taps + tap (as wgrad_unpack_kernel), with the spectral-norm
+// correction applied on the way: dw[c_u][r] += (acc - c * u[c_u] * v[r]) / sigma
+__global__ void __launch_bounds__(256) sn_bwd_apply_packed_kernel(const float* __restrict__ acc, const float* __restrict__ u,
+                                                                  const float* __restrict__ v, const float* __restrict__ sigma,
+                                                                  const float* __restrict__ dot, int cu_n, int cs_n, int taps,
+                                                                  float* __restrict__ dw) {
+  vg::pdl_entry();
+  __shared__ float tile[32][33];
+  const int R = cs_n * taps;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float inv = 1.0f / *sigma;
+  const float c = *dot * inv;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, cu = c0 + tx;
+    float val = 0.f;
+    if (r < R && cu < cu_n) {
+      const int cs = r / taps, tap = r - cs * taps;
+      val = acc[((long long)tap * cs_n + cs) * cu_n + cu];
+    }
+    tile[i][tx] = val;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int cu = c0 + i, r = r0 + tx;
+    if (cu < cu_n && r < R) dw[(long long)cu * R + r] += (tile[tx][i] - c * u[cu] * v[r]) * inv;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // reparameterisation
 // ------------------------------------------------------------------------------------------
@@ -951,13 +1005,42 @@ extern "C" int vg_spectral_norm_sigma_batched(const VgSnItem* items, int n_items
   return VG_OK;
 }
 
+namespace vg {
+int sn_backward_run(const float* dw_hat, const float* w_orig, const float* u, const float* v, const float* sigma, int rows, int cols,
+                    float* dw_orig, float* workspace, cudaStream_t s);
+}
 extern "C" int vg_spectral_norm_backward(const float* dw_hat, const float* w_orig, const float* u, const float* v,
                                          const float* sigma, int rows, int cols, float* dw_orig, float* workspace,
                                          vg_stream_t stream) {
   VG_CHECK_ARG(dw_hat && w_orig && u && v && sigma && dw_orig && workspace && rows > 0 && cols > 0, "bad args");
   cudaStream_t s = as_stream(stream);
-  long long n = (long long)rows * cols;
   VG_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float), s));
+  return vg::sn_backward_run(dw_hat, w_orig, u, v, sigma, rows, cols, dw_orig, workspace, s);
+}
+
+namespace vg {
+// dot_ws: one float, ZEROED by the caller
+int sn_backward_packed_run(const float* acc, const float* w_orig, const float* u, const float* v, const float* sigma, int cu, int cs,
+                           int taps, float* dw_orig, float* dot_ws, cudaStream_t s) {
+  const long long n = (long long)taps * cs * cu;
+  float* part = nullptr;
+  const int dot_grid = ew_grid(n);
+  if (g_det.on && !(part = (float*)det_scratch((size_t)dot_grid * sizeof(float)))) return VG_EINVAL;
+  vg::Launch(dot_grid, 256, 0, s)(sn_bwd_dot_packed_kernel, acc, w_orig, cu, cs, taps, dot_ws, part);
+  VG_LAUNCHED();
+  if (part) {
+    int rc = ordered_reduce_f32(part, dot_grid, 1, dot_ws, s);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)cdiv((long long)cs * taps, 32), (unsigned)cdiv(cu, 32));
+  vg::Launch(grid, 256, 0, s)(sn_bwd_apply_packed_kernel, acc, u, v, sigma, dot_ws, cu, cs, taps, dw_orig);
+  VG_LAUNCHED();
+  return VG_OK;
+}
+
+int sn_backward_run(const float* dw_hat, const float* w_orig, const float* u, const float* v, const float* sigma, int rows, int cols,
+                    float* dw_orig, float* workspace, cudaStream_t s) {
+  long long n = (long long)rows * cols;
   float* part = nullptr;
   const int dot_grid = ew_grid(n);
   if (g_det.on && !(part = (float*)det_scratch((size_t)dot_grid * sizeof(float)))) return VG_EINVAL;
@@ -971,6 +1054,7 @@ extern "C" int vg_spectral_norm_backward(const float* dw_hat, const float* w_ori
   VG_LAUNCHED();
   return VG_OK;
 }
+}  // namespace vg
 
 extern "C" int vg_reparam_forward(const float* mu, const float* lv_raw, const float* eps, long long n, int training, int z_dtype,
                                   void* z, float* lv_clamped, vg_stream_t stream) {

@@ -315,6 +315,10 @@ def _conv_desc(x_shape, c_out, g: ConvGeom, act_dtype, out_dtype):
     return d, ho, wo
 
 
+# VG_SN_FUSED_WGRAD=0: the two-call sequence vg_conv_wgrad + vg_spectral_norm_backward (A/B, and the reference for the test)
+_SN_FUSED_WGRAD = _os.environ.get("VG_SN_FUSED_WGRAD", "1") == "1"
+
+
 class ConvFn(Function):
     """nn.Conv2d / nn.ConvTranspose2d (optionally spectral-normed, optionally followed by the
     per-(n,c) Dropout2d scale) - README.md:148-170, 378-387, 441, 556-571.
@@ -403,9 +407,24 @@ class ConvFn(Function):
             bbuf = live_grad_buf(ctx.bias_ref)
             fused = wbuf is not None
             direct = fused and not ctx.has_sn
-            dwh = wbuf if direct else zeros_f32(ctx.wshape, x.device)
             if ctx.has_bias:
                 db = bbuf if bbuf is not None else zeros_f32((d.c_out,), x.device)
+            if ctx.has_sn and x.dtype == torch.bfloat16 and _SN_FUSED_WGRAD and _lib.load().vg_conv_wgrad_sn_supported(C.byref(d)):
+                # tensor-core layer: weight gradient + spectral-norm backward in one call (the gradient stays in the kernel's
+                # packed layout and is corrected while it is transposed: no unpack pass, no temporary dW, one memset)
+                dw = wbuf if fused else zeros_f32(ctx.wshape, x.device)
+                numel = 1
+                for n_ in ctx.wshape:
+                    numel *= n_
+                ws = torch.empty(numel + 4, dtype=torch.float32, device=x.device)
+                call("vg_conv_wgrad_sn", C.byref(d), ptr(x), ptr(dy), ptr(w), ptr(u), ptr(v), ptr(sigma), ptr(dw), ptr(db), ptr(ws), s)
+                if fused:
+                    dw = None
+                if bbuf is not None:
+                    db = None
+                note_done(ctx.noted)
+                return dx, dw, db, None, None, None, None, None, None, None, None
+            dwh = wbuf if direct else zeros_f32(ctx.wshape, x.device)
             ws = torch.empty(dwh.numel(), dtype=torch.float32, device=x.device) if x.dtype == torch.bfloat16 else None
             call("vg_conv_wgrad", C.byref(d), ptr(x), ptr(dy), ptr(dwh), ptr(db), ptr(ws), s)
             if ctx.has_sn:
