@@ -742,5 +742,7 @@ def test_fused_spectral_norm_wgrad_matches_two_call_sequence(cin, cout, h, k, st
         finally:
             vf._SN_FUSED_WGRAD = True
     (gw_a, gx_a), (gw_b, gx_b) = grads
-    assert torch.equal(gx_a, gx_b)
+    # the input gradient does not go through the new call, but sigma comes from a power iteration with atomic partial sums:
+    # its last bits - and with them single bf16 roundings of dx - differ from run to run (not in deterministic mode)
+    assert_close(gx_b, gx_a, 1e-2, "dx")
     assert_close(gw_b, gw_a, 2e-5, "dW of the fused call vs the two-call sequence")
