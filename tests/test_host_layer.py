@@ -107,3 +107,52 @@ def test_bn_double_backward_closed_form_matches_autograd():
         assert (o_dy - g_dy).abs().max() < 1e-12
         assert (o_x - g_x).abs().max() < 1e-12
         assert (o_g.double() - g_gamma).abs().max() < 1e-5      # returned in fp32
+
+
+def test_tile_table_and_deterministic_switch_host_logic(tmp_path):
+    """Host-side state of the library that needs no GPU: the tile table (set / record / list / clear, argument checks, the
+    JSON round trip of vae_gan_b200.tune, the committed B200 table parses and applies) and the argument checks of
+    vg_set_deterministic."""
+    from vae_gan_b200 import _lib, tune
+    from vae_gan_b200.build import build
+    build()
+    lib = _lib.load()
+    # --- tile table
+    tune.clear()
+    key = (0, 32, 24, 24, 256, 256, 3, 1, 1, 0)
+    tune.set_entry(key, 128, 1)
+    tune.set_entry((1,) + key[1:], 256, 3)
+    tune.set_entry(key, 0, 0)                       # removes the entry again
+    for bad in ((96, 1), (64, 7), (512, 2), (128, -1)):
+        try:
+            tune.set_entry(key, *bad)
+            raise AssertionError(f"accepted N tile / form {bad}")
+        except _lib.VgError as e:
+            assert "tile" in str(e) or "form" in str(e)
+    cnt = C.c_int(-1)
+    _lib.call("vg_conv_tune_record", 1)
+    _lib.call("vg_conv_tune_record", 0)
+    _lib.call("vg_conv_tune_seen", None, 0, C.byref(cnt))
+    assert cnt.value == 0                           # nothing was launched while recording
+    table = {key: {"bn": 128, "form": 1, "ms": 0.025, "heuristic_ms": 0.027}}
+    path = tmp_path / "table.json"
+    tune.save(table, path, meta={"gpu": "none"})
+    assert tune.load(path) == table
+    tune.apply(tune.load(path))
+    shipped = tune.load(tune.DEFAULT_TABLE)
+    assert len(shipped) >= 20
+    for k, e in shipped.items():
+        assert len(k) == 10 and k[0] in (0, 1) and e["bn"] in (64, 128, 256) and e["form"] in (1, 2, 3)
+        assert e["ms"] <= 0.95 * e["heuristic_ms"]          # only >= 5 % measured wins are shipped
+        n_out = k[4] if k[0] else k[5]
+        assert n_out % e["bn"] == 0
+    tune.apply(shipped)
+    tune.clear()
+    # --- deterministic mode: argument checks happen before anything touches a device
+    assert lib.vg_get_deterministic() == 0
+    assert lib.vg_set_deterministic(1, None, 0, None, 0) != 0
+    assert b"scratch" in lib.vg_last_error()
+    assert lib.vg_set_deterministic(1, C.c_void_p(16), 1 << 10, C.c_void_p(16), 4096) != 0       # scratch too small
+    assert lib.vg_set_deterministic(1, C.c_void_p(24), 1 << 20, C.c_void_p(16), 4096) != 0       # scratch misaligned
+    assert lib.vg_get_deterministic() == 0
+    assert lib.vg_set_deterministic(0, None, 0, None, 0) == 0
