@@ -69,6 +69,8 @@ struct alignas(64) TcConvParams {
   const float* post_scale;
   const float* post_shift;
   float post_slope;
+  CUtensorMap out_map;   // bf16 output as {32 channels, bx, by, bn} boxes (64-byte swizzle = the staging buffer's XOR pattern)
+  int tma_store;         // 1: the staged 32 x 32 output chunks leave through cp.async.bulk.tensor stores (out_map)
   int* det_locks;        // deterministic mode, split-K: one turn counter per output tile (the splits add in split order)
   long long det_split_stride;  // deterministic mode, split-K: != 0 -> split z STORES its partial tile at out + z * stride (scratch);
                                //   ordered_reduce_f32 adds the splits in order afterwards (no serialisation, no atomics)
@@ -94,7 +96,7 @@ constexpr int kStageBytes = 32 * 64;  // per epilogue warp: 32 rows x 32 bf16 of
 template <int BN, int MT, int STAGES>
 struct ConvSmem {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 1) * 8 + 16 + 1024 + 4 * kStageBytes + 16;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 1) * 8 + 16 + 1024 + 4 * kStageBytes + 16 + 512;
 };
 
 
@@ -133,7 +135,8 @@ __device__ __forceinline__ float colsum32(float (&v)[32], int lane) {
 template <bool INF>
 __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint32_t (&r)[32], bool valid, bool add_bias,
                                                long long opix, int gn, int ncol, bool first_chunk, bool do_stats, int lane,
-                                               float& st_sum, float& st_sq, uint8_t* stage = nullptr) {
+                                               float& st_sum, float& st_sq, uint8_t* stage = nullptr, int sx = 0, int sy = 0,
+                                               int sn = 0) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -164,10 +167,27 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint
       __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
       w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
+    const bool tma_out = !INF && p.tma_store != 0;
+    if (tma_out) {
+      // the previous chunk's bulk store must have READ the staging buffer before it is overwritten
+      if (lane == 0) ptx::bulk_wait_group_read0();
+      __syncwarp();
+    }
     uint4* srow = reinterpret_cast<uint4*>(stage + lane * 64);
     const int sw = (lane >> 1) & 3;
 #pragma unroll
     for (int q = 0; q < 4; ++q) srow[q ^ sw] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    if (tma_out) {
+      // TMA-store epilogue: the warp's 32 pixels are a {bx, by, bn} sub-box of the tile starting at (sx, sy, sn); pixels
+      // outside the tensor are clipped by the TMA unit (= the `valid` mask of the manual path)
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_4d(&p.out_map, stage, ncol, sx, sy, sn);
+        ptx::bulk_commit_group();
+      }
+      __syncwarp();
+    } else {
     __syncwarp();
     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
     const bool post = INF && (p.residual != nullptr || p.out2 != nullptr);       // kernel-uniform; compiled out of the training kernels
@@ -227,6 +247,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint
       }
     }
     __syncwarp();                      // the buffer is rewritten by this warp's next chunk
+    }
   } else if (valid) {
     if (p.n_store == 1) {
       // single-channel output (Conv2d C->1 forward / Conv2d 1->C dgrad): only column 0 is real
@@ -300,7 +321,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
+  // 512-byte aligned: the staging buffers' XOR pattern is then exactly TMA's 64-byte swizzle (absolute address bits)
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 511) & ~(uintptr_t)511);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TcPhase& ph = p.phases[p.ksplit > 1 ? 0 : blockIdx.z];
@@ -403,6 +425,9 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
     const int xl = row & (p.TW - 1);
     const int yl = (row >> p.tw_log2) & (p.TH - 1);
     const int nl = row >> (p.tw_log2 + p.th_log2);
+    // first pixel of this warp's 32-row quarter inside the tile: origin of its TMA-store sub-box
+    const int row0 = q * 32;
+    const int xl0 = row0 & (p.TW - 1), yl0 = (row0 >> p.tw_log2) & (p.TH - 1), nl0 = row0 >> (p.tw_log2 + p.th_log2);
     if (num_k > 0) {
       ptx::mbar_wait(tmem_full, 0);
       ptx::tc_fence_after();
@@ -434,7 +459,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
         epilogue_chunk<INF>(p, r, valid, p.ksplit <= 1 || blockIdx.z == 0, opix, gn, ncol0 + c0, c == 0, do_stats, lane, st_s[c], st_q[c],
-                       stage_base + q * kStageBytes);
+                       stage_base + q * kStageBytes, x0s[m] + xl0, y0s[m] + yl0, n0s[m] + nl0);
       }
     }
     if (do_stats) {
@@ -452,6 +477,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
       asm volatile("bar.sync 2, 128;" ::: "memory");      // the four epilogue warps
       if (warp == 4 && lane == 0) det_publish_turn(det_lock, (int)blockIdx.z + 1 == p.ksplit ? 0 : (int)blockIdx.z + 1);
     }
+    if (!INF && p.tma_store && lane == 0) ptx::bulk_wait_group0();      // this warp's bulk stores have landed
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -477,7 +503,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
 template <int BN, int MT, int STAGES, int EW>
 struct ConvPersistSmem {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024 + EW * kStageBytes + 16;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024 + EW * kStageBytes + 16 + 512;
 };
 
 // EW = number of epilogue warps (4 or 8).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so with
@@ -504,7 +530,8 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
   uint64_t* acc_full = empty + STAGES;       // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
+  // 512-byte aligned: the staging buffers' XOR pattern is then exactly TMA's 64-byte swizzle (absolute address bits)
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 511) & ~(uintptr_t)511);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
@@ -666,6 +693,9 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
     const int xl = row & (p.TW - 1);
     const int yl = (row >> p.tw_log2) & (p.TH - 1);
     const int nl = row >> (p.tw_log2 + p.th_log2);
+    // first pixel of this warp's 32-row quarter inside the tile: origin of its TMA-store sub-box
+    const int row0 = q * 32;
+    const int xl0 = row0 & (p.TW - 1), yl0 = (row0 >> p.tw_log2) & (p.TH - 1), nl0 = row0 >> (p.tw_log2 + p.th_log2);
     int it = 0;
     const bool do_stats = p.stats != nullptr && p.ksplit <= 1;
     float st_s[BN / 32], st_q[BN / 32];
@@ -726,7 +756,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
           epilogue_chunk<INF>(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, do_stats && has_k, lane, st_s[c], st_q[c],
-                         stage_base + ew * kStageBytes);
+                         stage_base + ew * kStageBytes, x0 + xl0, y0 + yl0, n0 + nl0);
         }
       }
       if (has_k) {
@@ -738,6 +768,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
       }
     }
     if (do_stats) flush_stats();
+    if (!INF && p.tma_store && lane == 0) ptx::bulk_wait_group0();      // this warp's bulk stores have landed
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -761,7 +792,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
 template <int BN, int MT, int STAGES, int EW>
 struct ConvPairSmem {
   static constexpr int kBBytes = (BN / 2) * 128;
-  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024 + EW * kStageBytes + 16;
+  static constexpr int kBytes = STAGES * (MT * kABytes + kBBytes) + (2 * STAGES + 4) * 8 + 16 + 1024 + EW * kStageBytes + 16 + 512;
 };
 
 template <int BN, int MT, int STAGES, int EW, bool INF>
@@ -784,7 +815,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
   uint64_t* acc_full = empty + STAGES;       // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
+  // 512-byte aligned: the staging buffers' XOR pattern is then exactly TMA's 64-byte swizzle (absolute address bits)
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 511) & ~(uintptr_t)511);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -919,6 +951,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
     const int xl = row & (p.TW - 1);
     const int yl = (row >> p.tw_log2) & (p.TH - 1);
     const int nl = row >> (p.tw_log2 + p.th_log2);
+    // first pixel of this warp's 32-row quarter inside the tile: origin of its TMA-store sub-box
+    const int row0 = q * 32;
+    const int xl0 = row0 & (p.TW - 1), yl0 = (row0 >> p.tw_log2) & (p.TH - 1), nl0 = row0 >> (p.tw_log2 + p.th_log2);
     int it = 0;
     // BatchNorm statistics of the stored output, accumulated per lane (= column of the chunk) across this CTA's work
     // items and flushed with fp64 atomics whenever the N tile changes
@@ -980,7 +1015,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
           epilogue_chunk<INF>(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, do_stats && has_k, lane, st_s[c], st_q[c],
-                         stage_base + ew * kStageBytes);
+                         stage_base + ew * kStageBytes, x0 + xl0, y0 + yl0, n0 + nl0);
         }
       }
       if (has_k) {
@@ -991,6 +1026,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
       }
     }
     if (do_stats) flush_stats();
+    if (!INF && p.tma_store && lane == 0) ptx::bulk_wait_group0();      // this warp's bulk stores have landed
   }
   // neither CTA may retire while the other can still signal its barriers or read its shared memory
   ptx::tc_fence_before();
@@ -1232,6 +1268,27 @@ static int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, i
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(activation) failed: %d (n=%d h=%d w=%d c=%d s=%d box=%d,%d,%d)", (int)r, n, h, w, c, s, TW, TH, TN);
+    return VG_ECUDA;
+  }
+  return VG_OK;
+}
+
+// bf16 output tensor (N, OH, OW, C) as {32 channels, bx, by, bn} boxes with the 64-byte swizzle (TMA-store epilogue)
+static int make_out_map(CUtensorMap* m, void* base, int n, int h, int w, int c, int bx, int by, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return VG_ECUDA;
+  }
+  bind_context_once();
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(output) failed: %d (n=%d h=%d w=%d c=%d box=%d,%d,%d)", (int)r, n, h, w, c, bx, by, bn);
     return VG_ECUDA;
   }
   return VG_OK;
@@ -1571,6 +1628,16 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   // Measured on B200 (scripts/sweep_conv.py): a persistent single-tile CTA loses to two co-resident
   // one-shot CTAs, and multi-tile CTAs without the double-buffered accumulator are slower still
   // (128->128 @96: 897 -> 769 TFLOP/s), so those stay opt-in (VG_TC_MT=1).
+  // TMA-store epilogue (VG_TC_TMA_STORE): bf16 outputs of gather-type launches (output on the GEMM's own pixel grid)
+  // without split-K and without the inference epilogue leave the staging buffers as cp.async.bulk.tensor stores
+  static int tma_store = -1;
+  if (tma_store < 0) { const char* e = getenv("VG_TC_TMA_STORE"); tma_store = e ? atoi(e) : 0; }
+  if (tma_store && !p.out_f32 && p.ksplit == 1 && p.n_store != 1 && p.os == 1 && nphase == 1 &&
+      p.act_slope == 1.0f && p.residual == nullptr && p.out2 == nullptr) {
+    const int bx = std::min(p.TW, 32), by = std::min(p.TH, 32 / bx), bn = 32 / (bx * by);
+    if ((rc = make_out_map(&p.out_map, out, d->n, out_h, out_w, n_out, bx, by, bn))) return rc;
+    p.tma_store = 1;
+  }
   static int mt_on = -1, persist = -1, mt_min = -1, fuse_stats = -1;
   if (mt_on < 0) { const char* e = getenv("VG_TC_MT"); mt_on = (e && atoi(e)) ? 1 : 0; }
   if (persist < 0) { const char* e = getenv("VG_TC_PERSIST"); persist = e ? atoi(e) : 1; }
