@@ -69,7 +69,8 @@ struct alignas(64) TcConvParams {
   const float* post_scale;
   const float* post_shift;
   float post_slope;
-  CUtensorMap out_map;   // bf16 output as {32 channels, bx, by, bn} boxes (64-byte swizzle = the staging buffer's XOR pattern)
+  CUtensorMap out_maps[4];  // bf16 output as {32 channels, bx, by, bn} boxes (64-byte swizzle = the staging buffer's XOR
+                            // pattern); one per output phase: a stride-2 scatter writes four interleaved sub-grids
   int tma_store;         // 1: the staged 32 x 32 output chunks leave through cp.async.bulk.tensor stores (out_map)
   int* det_locks;        // deterministic mode, split-K: one turn counter per output tile (the splits add in split order)
   long long det_split_stride;  // deterministic mode, split-K: != 0 -> split z STORES its partial tile at out + z * stride (scratch);
@@ -136,7 +137,7 @@ template <bool INF>
 __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint32_t (&r)[32], bool valid, bool add_bias,
                                                long long opix, int gn, int ncol, bool first_chunk, bool do_stats, int lane,
                                                float& st_sum, float& st_sq, uint8_t* stage = nullptr, int sx = 0, int sy = 0,
-                                               int sn = 0) {
+                                               int sn = 0, int out_phase = 0) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -183,7 +184,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvParams& p, const uint
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        ptx::tma_store_4d(&p.out_map, stage, ncol, sx, sy, sn);
+        ptx::tma_store_4d(&p.out_maps[out_phase], stage, ncol, sx, sy, sn);
         ptx::bulk_commit_group();
       }
       __syncwarp();
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_conv_kernel(const __grid_consta
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
         epilogue_chunk<INF>(p, r, valid, p.ksplit <= 1 || blockIdx.z == 0, opix, gn, ncol0 + c0, c == 0, do_stats, lane, st_s[c], st_q[c],
-                       stage_base + q * kStageBytes, x0s[m] + xl0, y0s[m] + yl0, n0s[m] + nl0);
+                       stage_base + q * kStageBytes, x0s[m] + xl0, y0s[m] + yl0, n0s[m] + nl0, (int)blockIdx.z);
       }
     }
     if (do_stats) {
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, 1) tc_conv_persist_kernel(const
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
           epilogue_chunk<INF>(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, do_stats && has_k, lane, st_s[c], st_q[c],
-                         stage_base + ew * kStageBytes, x0 + xl0, y0 + yl0, n0 + nl0);
+                         stage_base + ew * kStageBytes, x0 + xl0, y0 + yl0, n0 + nl0, z);
         }
       }
       if (has_k) {
@@ -1015,7 +1016,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
           epilogue_chunk<INF>(p, r, valid, p.ksplit <= 1 || z == 0, opix, gn, ncol0 + c0, c == 0, do_stats && has_k, lane, st_s[c], st_q[c],
-                         stage_base + ew * kStageBytes, x0 + xl0, y0 + yl0, n0 + nl0);
+                         stage_base + ew * kStageBytes, x0 + xl0, y0 + yl0, n0 + nl0, z);
         }
       }
       if (has_k) {
@@ -1274,17 +1275,21 @@ static int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, i
 }
 
 // bf16 output tensor (N, OH, OW, C) as {32 channels, bx, by, bn} boxes with the 64-byte swizzle (TMA-store epilogue)
-static int make_out_map(CUtensorMap* m, void* base, int n, int h, int w, int c, int bx, int by, int bn) {
+// (s, py, px): the sub-grid of output pixels (py + s*i, px + s*j) a scatter phase writes (s = 1: the whole tensor)
+static int make_out_map(CUtensorMap* m, void* base, int n, int h, int w, int c, int bx, int by, int bn, int s = 1, int py = 0,
+                        int px = 0) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
     return VG_ECUDA;
   }
   bind_context_once();
-  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  const int hs = (h - py + s - 1) / s, ws = (w - px + s - 1) / s;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)std::max(ws, 1), (cuuint64_t)std::max(hs, 1), (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)s * c * 2, (cuuint64_t)s * w * c * 2, (cuuint64_t)h * w * c * 2};
   cuuint32_t box[4] = {32, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bn};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  base = (void*)((char*)base + ((size_t)py * w + px) * c * 2);
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1631,11 +1636,14 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   // TMA-store epilogue (VG_TC_TMA_STORE): bf16 outputs of gather-type launches (output on the GEMM's own pixel grid)
   // without split-K and without the inference epilogue leave the staging buffers as cp.async.bulk.tensor stores
   static int tma_store = -1;
-  if (tma_store < 0) { const char* e = getenv("VG_TC_TMA_STORE"); tma_store = e ? atoi(e) : 0; }
-  if (tma_store && !p.out_f32 && p.ksplit == 1 && p.n_store != 1 && p.os == 1 && nphase == 1 &&
+  if (tma_store < 0) { const char* e = getenv("VG_TC_TMA_STORE"); tma_store = e ? atoi(e) : 1; }
+  if (tma_store && !p.out_f32 && p.ksplit == 1 && p.n_store != 1 && (p.os == 1 || tma_store >= 2) &&
       p.act_slope == 1.0f && p.residual == nullptr && p.out2 == nullptr) {
     const int bx = std::min(p.TW, 32), by = std::min(p.TH, 32 / bx), bn = 32 / (bx * by);
-    if ((rc = make_out_map(&p.out_map, out, d->n, out_h, out_w, n_out, bx, by, bn))) return rc;
+    // a scatter launch (ConvTranspose2d forward, stride-2 dgrad) writes st x st interleaved sub-grids, one per phase (grid.z)
+    for (int ph = 0; ph < nphase; ++ph)
+      if ((rc = make_out_map(&p.out_maps[ph], out, d->n, out_h, out_w, n_out, bx, by, bn, p.os, p.phases[ph].oy_off, p.phases[ph].ox_off)))
+        return rc;
     p.tma_store = 1;
   }
   static int mt_on = -1, persist = -1, mt_min = -1, fuse_stats = -1;
