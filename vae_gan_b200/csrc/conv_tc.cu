@@ -1633,10 +1633,13 @@ int tc_conv_run(const VgConvDesc* d, bool dgrad, const void* in, const void* wpa
   // Measured on B200 (scripts/sweep_conv.py): a persistent single-tile CTA loses to two co-resident
   // one-shot CTAs, and multi-tile CTAs without the double-buffered accumulator are slower still
   // (128->128 @96: 897 -> 769 TFLOP/s), so those stay opt-in (VG_TC_MT=1).
-  // TMA-store epilogue (VG_TC_TMA_STORE): bf16 outputs of gather-type launches (output on the GEMM's own pixel grid)
-  // without split-K and without the inference epilogue leave the staging buffers as cp.async.bulk.tensor stores
+  // TMA-store epilogue (VG_TC_TMA_STORE, default 2): bf16 outputs without split-K and without the inference epilogue leave
+  // the staging buffers as cp.async.bulk.tensor stores - 1: gather-type launches only (output on the GEMM's own pixel grid),
+  // 2: also the scatter launches (one strided output map per phase), 0: the manual coalesced stores.  Measured on B200
+  // (profiles/r2_tma_store_ab.txt): 60.2 -> 59.2 ms/step at batch 256, 10.58 -> 10.36 at 32; 64->64 @96 74 -> 67 us,
+  // 64->128 @96 110 -> 97 us, 1x1 stride-2 51 -> 43 us; the scatter phases add another 0.3 %.
   static int tma_store = -1;
-  if (tma_store < 0) { const char* e = getenv("VG_TC_TMA_STORE"); tma_store = e ? atoi(e) : 1; }
+  if (tma_store < 0) { const char* e = getenv("VG_TC_TMA_STORE"); tma_store = e ? atoi(e) : 2; }
   if (tma_store && !p.out_f32 && p.ksplit == 1 && p.n_store != 1 && (p.os == 1 || tma_store >= 2) &&
       p.act_slope == 1.0f && p.residual == nullptr && p.out2 == nullptr) {
     const int bx = std::min(p.TW, 32), by = std::min(p.TH, 32 / bx), bn = 32 / (bx * by);
